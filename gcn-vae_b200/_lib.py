@@ -1,0 +1,113 @@
+"""ctypes binding of libkgvae_b200.so (the C ABI declared in include/kgvae_b200.h).
+
+There is no CPU fallback: every op raises if the library is missing or the tensors are not
+CUDA tensors.
+"""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkgvae_b200.so")
+
+_P, _I, _F, _L, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/kgvae_b200.h one to one
+_SIGNATURES = {
+    "kg_last_error": (ctypes.c_char_p, []),
+    "kg_version": (_I, []),
+    "kg_device_info": (_I, [_P, _P, _P]),
+    "kg_graph_build_workspace_bytes": (_Z, [_I]),
+    "kg_graph_build": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_graph_index_workspace_bytes": (_Z, [_I]),
+    "kg_graph_index": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_embedding_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
+    "kg_embedding_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
+    "kg_bdd_weight_layouts": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "kg_bdd_aggregate_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "kg_bdd_aggregate_bwd_dx": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "kg_bdd_aggregate_bwd_dw": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),
+    "kg_colsum_workspace_bytes": (_Z, [_I, _I]),
+    "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
+    "kg_gemm_f32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "kg_reparam_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "kg_reparam_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "kg_kl_mog_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "kg_kl_mog_bwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "kg_iaf_update_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "kg_iaf_update_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "kg_reverse_columns": (_I, [_P, _I, _I, _P, _P]),
+    "kg_distmult_score": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "kg_reduce_workspace_bytes": (_Z, [_L]),
+    "kg_bce_logits_fwd": (_I, [_P, _P, _I, _P, _P, _P, _Z, _P]),
+    "kg_sum_squares": (_I, [_P, _L, _P, _P, _Z, _P]),
+    "kg_sum": (_I, [_P, _L, _P, _P, _Z, _P]),
+    "kg_triplet_index_workspace_bytes": (_Z, [_I]),
+    "kg_triplet_index": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_distmult_bwd_dz": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"kgvae_b200: {LIB_PATH} is missing - build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise RuntimeError with kg_last_error() on failure."""
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {handle.kg_last_error().decode()}")
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("kgvae_b200 ops need CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"kgvae_b200: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("kgvae_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def f32(t):
+    return ptr(t, torch.float32)
+
+
+def i32(t):
+    return ptr(t, torch.int32)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def device_info():
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    call("kg_device_info", ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return {"sm_count": a.value, "cc": (b.value, c.value)}

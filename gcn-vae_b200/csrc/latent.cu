@@ -1,0 +1,283 @@
+// a5 / a6 / a7: latent-variable kernels - mean/variance heads with the reparameterised sample,
+// the single-sample KL estimate against the mixture-of-Gaussians prior, and the element update of
+// one IAF (MADE) pass.  Each replaces a chain of 5-15 ATen elementwise/reduction launches with
+// broadcast temporaries ([N, k, h] for the mixture) in the reference.
+#include "common.cuh"
+
+static constexpr int kThreads = 256;
+static constexpr int kMaxMix = 16;
+#define KG_LOG_SQRT_2PI 0.91893853320467274178f
+
+// ------------------------------------------------------------------------------------------
+// a5  gaussian_parameters + sample_gaussian   (reference kgvae/utils.py:323-361)
+// ------------------------------------------------------------------------------------------
+__global__ void reparam_fwd_kernel(const float* __restrict__ h2, const float* __restrict__ eps, int n,
+                                   int h, float* __restrict__ zm, float* __restrict__ zv,
+                                   float* __restrict__ z) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * h) return;
+  int i = (int)(t / h), d = (int)(t % h);
+  const float m = h2[(size_t)i * 2 * h + d];
+  const float v = kg_softplus(h2[(size_t)i * 2 * h + h + d]) + 1e-8f;   // utils.py:338
+  zm[t] = m;
+  zv[t] = v;
+  z[t] = m + eps[t] * sqrtf(v);                                         // utils.py:359-360
+}
+
+__global__ void reparam_bwd_kernel(const float* __restrict__ h2, const float* __restrict__ eps,
+                                   const float* __restrict__ zv, const float* __restrict__ dz,
+                                   const float* __restrict__ dmean, const float* __restrict__ dvar,
+                                   int n, int h, float* __restrict__ dh2) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * h) return;
+  int i = (int)(t / h), d = (int)(t % h);
+  const float g = dz ? dz[t] : 0.f;
+  float gm = g, gv = g * eps[t] * 0.5f / sqrtf(zv[t]);
+  if (dmean) gm += dmean[t];
+  if (dvar) gv += dvar[t];
+  dh2[(size_t)i * 2 * h + d] = gm;
+  dh2[(size_t)i * 2 * h + h + d] = gv * kg_sigmoid(h2[(size_t)i * 2 * h + h + d]);
+}
+
+extern "C" int kg_reparam_fwd(const float* h2, const float* eps, int n, int h, float* z_mean,
+                              float* z_var, float* z, void* stream) {
+  KG_REQUIRE(n >= 0 && h > 0, "reparam fwd: bad sizes");
+  if (n == 0) return KG_OK;
+  reparam_fwd_kernel<<<kg_div_up((long long)n * h, kThreads), kThreads, 0, kg_stream(stream)>>>(
+      h2, eps, n, h, z_mean, z_var, z);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+extern "C" int kg_reparam_bwd(const float* h2, const float* eps, const float* z_var, const float* dz,
+                              const float* dmean, const float* dvar, int n, int h, float* dh2,
+                              void* stream) {
+  KG_REQUIRE(n >= 0 && h > 0, "reparam bwd: bad sizes");
+  if (n == 0) return KG_OK;
+  reparam_bwd_kernel<<<kg_div_up((long long)n * h, kThreads), kThreads, 0, kg_stream(stream)>>>(
+      h2, eps, z_var, dz, dmean, dvar, n, h, dh2);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// a7  KL estimate   (reference kgvae/model.py:82-87, utils.py:364-428)
+// prior_ws [3, k, h]: variance, 1/(2 variance), log(sqrt(variance)) of each mixture component
+// ------------------------------------------------------------------------------------------
+__global__ void prior_prepare_kernel(const float* __restrict__ z_pre, int k, int h,
+                                     float* __restrict__ ws) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k * h) return;
+  const float v = kg_softplus(z_pre[(size_t)k * h + t]) + 1e-8f;
+  ws[t] = v;
+  ws[(size_t)k * h + t] = 1.f / (2.f * v);
+  ws[(size_t)2 * k * h + t] = logf(sqrtf(v));
+}
+
+__global__ void __launch_bounds__(kThreads)
+kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
+                  const float* __restrict__ zv, const float* __restrict__ z_pre,
+                  const float* __restrict__ ws, int n, int h, int k, float* __restrict__ kl_rows,
+                  float* __restrict__ resp) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* inv2v = ws + (size_t)k * h;
+  const float* lsq = ws + (size_t)2 * k * h;
+  float a = 0.f, b[kMaxMix];
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i) b[i] = 0.f;
+  for (int d = lane; d < h; d += 32) {
+    const float zc = z[(size_t)row * h + d];
+    const float t = zc - zm[(size_t)row * h + d];
+    const float v = zv[(size_t)row * h + d];
+    a += -(t * t) / (2.f * v) - logf(sqrtf(v)) - KG_LOG_SQRT_2PI;          // utils.py:396
+#pragma unroll
+    for (int i = 0; i < kMaxMix; ++i)
+      if (i < k) {
+        const float u = zc - __ldg(z_pre + (size_t)i * h + d);
+        b[i] += -(u * u) * __ldg(inv2v + (size_t)i * h + d) - __ldg(lsq + (size_t)i * h + d) - KG_LOG_SQRT_2PI;
+      }
+  }
+  a = kg_warp_sum(a);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i)
+    if (i < k) {
+      b[i] = kg_warp_sum(b[i]);
+      mx = fmaxf(mx, b[i]);
+    }
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i)
+    if (i < k) se += expf(b[i] - mx);
+  const float lse = mx + logf(se);                                          // utils.py:413-415
+  if (lane == 0) kl_rows[row] = a - (lse - logf((float)k));                 // utils.py:428, model.py:86
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i)
+    if (i < k && lane == (i & 31)) resp[(size_t)row * k + i] = expf(b[i] - lse);
+}
+
+static constexpr int kKlRows = 64;   // rows per CTA in the backward kernel
+
+__global__ void __launch_bounds__(128)
+kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
+                  const float* __restrict__ zv, const float* __restrict__ z_pre,
+                  const float* __restrict__ ws, const float* __restrict__ resp, float scale, int n,
+                  int h, int k, float* __restrict__ dz, float* __restrict__ dmean,
+                  float* __restrict__ dvar, float* __restrict__ dz_pre) {
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= h) return;
+  const int r0 = blockIdx.x * kKlRows, r1 = min(n, r0 + kKlRows);
+  float pm[kMaxMix], ipv[kMaxMix], gpm[kMaxMix], gpv[kMaxMix];
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i) {
+    pm[i] = i < k ? z_pre[(size_t)i * h + d] : 0.f;
+    ipv[i] = i < k ? 1.f / ws[(size_t)i * h + d] : 0.f;
+    gpm[i] = 0.f;
+    gpv[i] = 0.f;
+  }
+  for (int row = r0; row < r1; ++row) {
+    const size_t off = (size_t)row * h + d;
+    const float zc = z[off], v = zv[off];
+    const float t = zc - zm[off];
+    const float iv = 1.f / v;
+    float gz = -t * iv;                      // d/dz log N(z; m, v)
+    dmean[off] = scale * t * iv;
+    dvar[off] = scale * (0.5f * t * t * iv * iv - 0.5f * iv);
+#pragma unroll
+    for (int i = 0; i < kMaxMix; ++i)
+      if (i < k) {
+        const float ri = __ldg(resp + (size_t)row * k + i);
+        const float u = zc - pm[i];
+        const float q = ri * u * ipv[i];     // resp_i * (z - m_i)/v_i
+        gz += q;                             // d/dz of -log MoG
+        gpm[i] -= q;
+        gpv[i] -= ri * (0.5f * u * u * ipv[i] * ipv[i] - 0.5f * ipv[i]);
+      }
+    dz[off] = scale * gz;
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxMix; ++i)
+    if (i < k) {
+      atomicAdd(dz_pre + (size_t)i * h + d, scale * gpm[i]);
+      atomicAdd(dz_pre + (size_t)(k + i) * h + d,
+                scale * gpv[i] * kg_sigmoid(z_pre[(size_t)(k + i) * h + d]));
+    }
+}
+
+extern "C" int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z_var,
+                             const float* z_pre, int n, int h, int k, float* prior_ws, float* kl_rows,
+                             float* resp, void* stream) {
+  KG_REQUIRE(n >= 0 && h > 0 && k > 0 && k <= kMaxMix, "kl fwd: need 0 < k <= 16");
+  cudaStream_t st = kg_stream(stream);
+  prior_prepare_kernel<<<kg_div_up((long long)k * h, kThreads), kThreads, 0, st>>>(z_pre, k, h, prior_ws);
+  KG_LAUNCH_OK();
+  if (n == 0) return KG_OK;
+  kl_mog_fwd_kernel<<<kg_div_up((long long)n * 32, kThreads), kThreads, 0, st>>>(
+      z, z_mean, z_var, z_pre, prior_ws, n, h, k, kl_rows, resp);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+extern "C" int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z_var,
+                             const float* z_pre, const float* prior_ws, const float* resp, float scale,
+                             int n, int h, int k, float* dz, float* dmean, float* dvar, float* dz_pre,
+                             void* stream) {
+  KG_REQUIRE(n >= 0 && h > 0 && k > 0 && k <= kMaxMix, "kl bwd: need 0 < k <= 16");
+  if (n == 0) return KG_OK;
+  dim3 grid(kg_div_up(n, kKlRows), kg_div_up(h, 128));
+  kl_mog_bwd_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, z_mean, z_var, z_pre, prior_ws, resp, scale, n,
+                                                         h, k, dz, dmean, dvar, dz_pre);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// a6  IAF element update   (reference kgvae/flow_network.py:91-96)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+iaf_update_fwd_kernel(const float* __restrict__ z, const float* __restrict__ net,
+                      const float* __restrict__ x_old, int n, int d, int skip_last,
+                      float* __restrict__ x_new, float* __restrict__ log_det) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* mu = net + (size_t)row * 2 * d;
+  const float* alpha = mu + d;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float al = alpha[j];
+    s += al;
+    const size_t off = (size_t)row * d + j;
+    if (skip_last && j == d - 1) x_new[off] = x_old[off];
+    else x_new[off] = z[off] * expf(al + mu[j]);                          // flow_network.py:95
+  }
+  if (log_det) {
+    s = kg_warp_sum(s);
+    if (lane == 0) log_det[row] = s;                                       // flow_network.py:96
+  }
+}
+
+__global__ void iaf_update_bwd_kernel(const float* __restrict__ z, const float* __restrict__ net,
+                                      const float* __restrict__ dx_new,
+                                      const float* __restrict__ dlog_det, int n, int d, int skip_last,
+                                      float* __restrict__ dz, float* __restrict__ dnet,
+                                      float* __restrict__ dx_old) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * d) return;
+  const int row = (int)(t / d), j = (int)(t % d);
+  const float g = dx_new[t];
+  const float gl = dlog_det ? dlog_det[row] : 0.f;
+  float* dmu = dnet + (size_t)row * 2 * d;
+  if (skip_last && j == d - 1) {
+    dz[t] = 0.f;
+    dmu[j] = 0.f;
+    dmu[d + j] = gl;
+    dx_old[t] = g;
+  } else {
+    const float e = expf(net[(size_t)row * 2 * d + d + j] + net[(size_t)row * 2 * d + j]);
+    const float gx = g * z[t] * e;
+    dz[t] = g * e;
+    dmu[j] = gx;
+    dmu[d + j] = gx + gl;
+    dx_old[t] = 0.f;
+  }
+}
+
+extern "C" int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old, int n, int d,
+                                 int skip_last, float* x_new, float* log_det, void* stream) {
+  KG_REQUIRE(n >= 0 && d > 0, "iaf fwd: bad sizes");
+  KG_REQUIRE(!skip_last || x_old, "iaf fwd: skip_last needs x_old");
+  if (n == 0) return KG_OK;
+  iaf_update_fwd_kernel<<<kg_div_up((long long)n * 32, kThreads), kThreads, 0, kg_stream(stream)>>>(
+      z, net_out, x_old, n, d, skip_last, x_new, log_det);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+extern "C" int kg_iaf_update_bwd(const float* z, const float* net_out, const float* dx_new,
+                                 const float* dlog_det, int n, int d, int skip_last, float* dz,
+                                 float* dnet_out, float* dx_old, void* stream) {
+  KG_REQUIRE(n >= 0 && d > 0, "iaf bwd: bad sizes");
+  if (n == 0) return KG_OK;
+  iaf_update_bwd_kernel<<<kg_div_up((long long)n * d, kThreads), kThreads, 0, kg_stream(stream)>>>(
+      z, net_out, dx_new, dlog_det, n, d, skip_last, dz, dnet_out, dx_old);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+__global__ void reverse_columns_kernel(const float* __restrict__ x, int n, int d, float* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * d) return;
+  const int row = (int)(t / d), j = (int)(t % d);
+  out[t] = x[(size_t)row * d + (d - 1 - j)];                               // flow_network.py:26,29
+}
+
+extern "C" int kg_reverse_columns(const float* x, int n, int d, float* out, void* stream) {
+  KG_REQUIRE(n >= 0 && d > 0, "reverse: bad sizes");
+  if (n == 0) return KG_OK;
+  reverse_columns_kernel<<<kg_div_up((long long)n * d, kThreads), kThreads, 0, kg_stream(stream)>>>(x, n, d, out);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}

@@ -1,0 +1,207 @@
+"""Link prediction head and training driver with the reference's surface (kgvae/link_predict.py).
+
+``LinkPredict`` keeps the constructor, ``forward`` / ``calc_score`` / ``regularization_loss`` /
+``get_loss`` and the ``w_relation`` parameter.  ``main`` keeps the reference's flags and loop;
+evaluation stays on the GPU (the reference moves the model to the CPU for it).
+"""
+import argparse
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import datasets, ops, utils
+from .model import KGVAE, RGCN
+
+
+class LinkPredict(nn.Module):
+    def __init__(self, model_class, in_dim, h_dim, num_rels, num_bases=-1, num_hidden_layers=1,
+                 dropout=0, use_cuda=True, reg_param=0, kl_param=0, mmd_param=0, k=1, n_flows=0):
+        super().__init__()
+        kwargs = dict(num_nodes=in_dim, h_dim=h_dim, out_dim=h_dim, num_rels=num_rels * 2,
+                      num_bases=num_bases, num_hidden_layers=num_hidden_layers, dropout=dropout,
+                      use_self_loop=use_cuda, use_cuda=use_cuda)
+        if model_class is KGVAE:          # the reference passes k/n_flows to RGCN too and crashes
+            kwargs.update(k=k, n_flows=n_flows)
+        self.encoder = model_class(**kwargs)
+        self.reg_param, self.kl_param, self.mmd_param = reg_param, kl_param, mmd_param
+        self.w_relation = nn.Parameter(torch.Tensor(num_rels, h_dim))
+        self.use_cuda, self.k, self.n_flows = use_cuda, k, n_flows
+        nn.init.xavier_uniform_(self.w_relation, gain=nn.init.calculate_gain("relu"))
+
+    def _flow_shift(self):
+        if self.n_flows > 0 and isinstance(self.encoder, KGVAE):
+            return self.encoder.get_flow_log_prob()
+        return None
+
+    def calc_score(self, embedding, triplets, shift=None):
+        """DistMult score of each (s, r, o) row (link_predict.py:57-63)."""
+        trip = ops.as_i32(triplets, embedding.device)
+        return ops.DistMultScoreFn.apply(embedding, self.w_relation, trip, shift)
+
+    def forward(self, g, h, r, norm):
+        return self.encoder.forward(g, h, r, norm)
+
+    def regularization_loss(self, embedding):
+        return ops.MeanSquareFn.apply(embedding) + ops.MeanSquareFn.apply(self.w_relation)
+
+    def get_loss(self, g, embed, triplets, labels):
+        """(loss, predict_loss, kl, mmd) as in link_predict.py:71-92."""
+        score = self.calc_score(embed, triplets, self._flow_shift())
+        predict_loss = ops.BceLogitsFn.apply(score, labels)
+        reg_loss = self.regularization_loss(embed)
+        zero = lambda: torch.zeros(1, device=embed.device)
+        kl = self.encoder.get_kl(embed) if self.kl_param > 0 else zero()
+        mmd = self.encoder.get_mmd(embed) if self.mmd_param > 0 else zero()
+        loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl + self.mmd_param * mmd
+        return loss, predict_loss, kl, mmd
+
+
+def node_norm_to_edge_norm(g, node_norm):
+    """edge_norm[e] = node_norm[dst[e]] (link_predict.py:95-100)."""
+    g = g.local_var()
+    g.ndata["norm"] = node_norm
+    g.apply_edges(lambda edges: {"norm": edges.dst["norm"]})
+    return g.edata["norm"]
+
+
+def _graph_inputs(graph, rel, norm, num_nodes, device):
+    node_id = torch.arange(0, num_nodes, dtype=torch.long).view(-1, 1).to(device)
+    rel_t = torch.from_numpy(rel).to(device)
+    edge_norm = node_norm_to_edge_norm(graph, torch.from_numpy(norm).view(-1, 1)).to(device)
+    return node_id, rel_t, edge_norm
+
+
+def main(args):
+    data = datasets.load_data(args.dataset)
+    num_nodes, num_rels = data.num_nodes, data.num_rels
+    train_data, valid_data, test_data = data.train, data.valid, data.test
+    if not torch.cuda.is_available():
+        raise RuntimeError("kgvae_b200 needs a CUDA device (no CPU fallback)")
+    device = torch.device("cuda", max(args.gpu, 0))
+    torch.cuda.set_device(device)
+
+    model_class = KGVAE if args.model_class == "KGVAE" else RGCN
+    model = LinkPredict(model_class=model_class, in_dim=num_nodes, h_dim=args.n_hidden,
+                        num_rels=num_rels, num_bases=args.n_bases, num_hidden_layers=args.n_layers,
+                        dropout=args.dropout, use_cuda=True, reg_param=args.regularization,
+                        kl_param=args.kl_param, mmd_param=args.mmd_param, k=args.mog_k,
+                        n_flows=args.n_flows).to(device)
+
+    valid_t = torch.LongTensor(valid_data)
+    val_graph, val_rel, val_norm = utils.build_test_graph(num_nodes, num_rels, valid_t)
+    val_node_id, val_rel, val_norm = _graph_inputs(val_graph, val_rel, val_norm, num_nodes, device)
+    adj_list, degrees = utils.get_adj_and_degrees(num_nodes, train_data)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
+    forward_time, backward_time = [], []
+
+    if args.test_mode:
+        print("\nstart testing:")
+        checkpoint = torch.load(args.model_state_file, map_location=device)
+        test_t = torch.LongTensor(test_data)
+        test_graph, test_rel, test_norm = utils.build_test_graph(num_nodes, num_rels, test_t)
+        test_node_id, test_rel, test_norm = _graph_inputs(test_graph, test_rel, test_norm, num_nodes, device)
+        model.eval()
+        model.load_state_dict(checkpoint["state_dict"])
+        print("Using best epoch: {}".format(checkpoint["epoch"]))
+        with torch.no_grad():
+            embed = model(test_graph, test_node_id, test_rel, test_norm)
+        return utils.calc_mrr(embed, model.w_relation, test_t, hits=[1, 3, 10],
+                              eval_bz=args.eval_batch_size, all_batches=True,
+                              flow_log_prob=model._flow_shift())
+
+    print("start training...")
+    epoch, best_mrr = 0, 0
+    if args.load:
+        print(f"Loading checkpoint file {args.model_state_file} for training")
+        checkpoint = torch.load(args.model_state_file, map_location=device)
+        model.load_state_dict(checkpoint["state_dict"])
+        epoch = checkpoint["epoch"]
+
+    while True:
+        model.train()
+        epoch += 1
+        g, node_id, edge_type, node_norm, batch, labels = utils.generate_sampled_graph_and_labels(
+            train_data, args.graph_batch_size, args.graph_split_size, num_rels, adj_list, degrees,
+            args.negative_sample, args.edge_sampler)
+        node_id = torch.from_numpy(node_id).view(-1, 1).long().to(device)
+        edge_type = torch.from_numpy(edge_type).to(device)
+        edge_norm = node_norm_to_edge_norm(g, torch.from_numpy(node_norm).view(-1, 1)).to(device)
+        batch, labels = torch.from_numpy(batch).to(device), torch.from_numpy(labels).to(device)
+
+        torch.cuda.synchronize()
+        t0 = time.time()
+        embed = model(g, node_id, edge_type, edge_norm)
+        loss, pred_loss, kl, mmd = model.get_loss(g, embed, batch, labels)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), args.grad_norm)
+        optimizer.step()
+        torch.cuda.synchronize()
+        t2 = time.time()
+        forward_time.append(t1 - t0)
+        backward_time.append(t2 - t1)
+        print("Epoch {:04d} | Loss {:.4f} | Best MRR {:.4f} | pred_loss {:.4f} | kl {:.4f} | mmd {:.4f}".format(
+            epoch, loss.item(), best_mrr, pred_loss.item(), kl.item(), mmd.item()))
+        optimizer.zero_grad()
+
+        if epoch % args.evaluate_every == 0:
+            model.eval()
+            print("start eval")
+            torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
+            with torch.no_grad():
+                embed = model(val_graph, val_node_id, val_rel, val_norm)
+            mrr = utils.calc_mrr(embed, model.w_relation, valid_t, hits=[1, 3, 10],
+                                 eval_bz=args.eval_batch_size, all_batches=False,
+                                 flow_log_prob=model._flow_shift())
+            if mrr < best_mrr:
+                torch.save({"state_dict": model.state_dict(), "epoch": epoch},
+                           args.model_state_file + "_latest")
+            else:
+                best_mrr = mrr
+                torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
+        if epoch >= args.n_epochs:
+            break
+
+    print("training done")
+    print("Mean forward time: {:4f}s".format(np.mean(forward_time)))
+    print("Mean Backward time: {:4f}s".format(np.mean(backward_time)))
+    return best_mrr
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Link Prediction")
+    p.add_argument("--dropout", type=float, default=0.2)
+    p.add_argument("--n-hidden", type=int, default=500)
+    p.add_argument("--gpu", type=int, default=-1)
+    p.add_argument("--lr", type=float, default=1e-3)
+    p.add_argument("--n-bases", type=int, default=100)
+    p.add_argument("--n-layers", type=int, default=2)
+    p.add_argument("--n-epochs", type=int, default=int(1e5))
+    p.add_argument("-d", "--dataset", type=str, required=True)
+    p.add_argument("--eval-batch-size", type=int, default=400)
+    p.add_argument("--regularization", type=float, default=0.01)
+    p.add_argument("--kl-param", type=float, default=1e-5)
+    p.add_argument("--mmd-param", type=float, default=0)
+    p.add_argument("--mog-k", type=int, default=10)
+    p.add_argument("--n-flows", type=int, default=0)
+    p.add_argument("--grad-norm", type=float, default=1.0)
+    p.add_argument("--graph-batch-size", type=int, default=20000)
+    p.add_argument("--graph-split-size", type=float, default=0.5)
+    p.add_argument("--negative-sample", type=int, default=10)
+    p.add_argument("--evaluate-every", type=int, default=200)
+    p.add_argument("--edge-sampler", type=str, default="uniform")
+    p.add_argument("--test-mode", type=bool, default=False)
+    p.add_argument("--model-state-file", type=str, default="model_state.pth")
+    p.add_argument("--model-class", type=str, default="KGVAE")
+    p.add_argument("--load", type=bool, default=False)
+    p.add_argument("--generate", type=bool, default=False)
+    return p
+
+
+if __name__ == "__main__":
+    parsed = build_parser().parse_args()
+    print(parsed)
+    main(parsed)

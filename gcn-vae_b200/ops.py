@@ -1,0 +1,458 @@
+"""torch.autograd.Function wrappers over the C ABI (include/kgvae_b200.h).
+
+Each Function is one fused operator of the link-prediction path and names the reference
+code it replaces.  All tensors are CUDA, fp32 / int32, contiguous; PyTorch supplies device
+memory, the stream and autograd bookkeeping only.
+"""
+import torch
+
+from . import _lib as L
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def as_i32(t, device=None):
+    """int32 contiguous view/copy of an index tensor (reference tensors are int64)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if device is not None and t.device != torch.device(device):
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return _c(t)
+
+
+# ---------------------------------------------------------------------------------------------
+# graph index (a1)
+# ---------------------------------------------------------------------------------------------
+class GraphIndex:
+    """Device-resident edge orderings for one (graph, etypes, norm) triple."""
+
+    __slots__ = ("n_nodes", "n_edges", "n_etypes", "row_ptr", "fwd_pack", "col_ptr", "bwd_pack",
+                 "rel_ptr", "rel_pack", "e_src", "e_dst", "e_type", "node_norm")
+
+    def __init__(self, n_nodes, n_edges, n_etypes, device):
+        self.n_nodes, self.n_edges, self.n_etypes = int(n_nodes), int(n_edges), int(n_etypes)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.row_ptr = torch.empty(n_nodes + 1, **i32)
+        self.col_ptr = torch.empty(n_nodes + 1, **i32)
+        self.rel_ptr = torch.empty(n_etypes + 1, **i32)
+        self.fwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
+        self.bwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
+        self.rel_pack = torch.empty((max(n_edges, 1), 4), **i32)
+        self.e_src = self.e_dst = self.e_type = self.node_norm = None
+
+
+def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes):
+    """kg_graph_index: CSR by destination / source / relation for an edge list given in the
+    reference's order (DGLGraph.add_edges + etypes + norm, kgvae/utils.py:141-148)."""
+    dev = e_src.device
+    E = int(e_src.numel())
+    gi = GraphIndex(n_nodes, E, n_etypes, dev)
+    gi.e_src, gi.e_dst, gi.e_type = e_src, e_dst, e_type
+    ws = L.workspace(L.lib().kg_graph_index_workspace_bytes(E), dev)
+    norm = None if e_norm is None else _c(e_norm.reshape(-1).to(torch.float32))
+    L.call("kg_graph_index", L.i32(e_src), L.i32(e_dst), L.i32(e_type), L.f32(norm), E, n_nodes,
+           n_etypes, L.i32(gi.row_ptr), L.i32(gi.fwd_pack), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
+           L.i32(gi.rel_ptr), L.i32(gi.rel_pack), L.ptr(ws), ws.numel(), L.stream())
+    return gi
+
+
+def graph_build(src, rel, dst, n_nodes, n_rels):
+    """kg_graph_build: the whole of utils.build_graph_from_triplets + node_norm_to_edge_norm
+    (kgvae/utils.py:127-150, kgvae/link_predict.py:95-100) on the device."""
+    dev = src.device
+    T = int(src.numel())
+    gi = GraphIndex(n_nodes, 2 * T, 2 * n_rels, dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    gi.e_src, gi.e_dst, gi.e_type = (torch.empty(max(2 * T, 1), **i32) for _ in range(3))
+    gi.node_norm = torch.empty(n_nodes, dtype=torch.float32, device=dev)
+    ws = L.workspace(L.lib().kg_graph_build_workspace_bytes(T), dev)
+    L.call("kg_graph_build", L.i32(src), L.i32(rel), L.i32(dst), T, n_nodes, n_rels,
+           L.i32(gi.e_src), L.i32(gi.e_dst), L.i32(gi.e_type), L.i32(gi.row_ptr), L.f32(gi.node_norm),
+           L.i32(gi.fwd_pack), L.i32(gi.col_ptr), L.i32(gi.bwd_pack), L.i32(gi.rel_ptr),
+           L.i32(gi.rel_pack), L.ptr(ws), ws.numel(), L.stream())
+    gi.e_src, gi.e_dst, gi.e_type = gi.e_src[:2 * T], gi.e_dst[:2 * T], gi.e_type[:2 * T]
+    return gi
+
+
+# ---------------------------------------------------------------------------------------------
+# dense GEMM helper
+# ---------------------------------------------------------------------------------------------
+def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, addend=None, relu=False, mask=None,
+         accumulate=False):
+    """out[M,N] (+)= epilogue(op(a) @ op(b)); a, b, out 2-D contiguous fp32."""
+    M, N = out.shape
+    K = a.shape[0] if trans_a else a.shape[1]
+    L.call("kg_gemm_f32", L.f32(a), a.shape[1], int(trans_a), L.f32(b), b.shape[1], int(trans_b),
+           L.f32(out), out.shape[1], M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask),
+           int(accumulate), L.stream())
+    return out
+
+
+def colsum(x):
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    ws = L.workspace(L.lib().kg_colsum_workspace_bytes(rows, cols), x.device)
+    L.call("kg_colsum", L.f32(x), rows, cols, L.f32(out), L.ptr(ws), ws.numel(), L.stream())
+    return out
+
+
+def _reduce(name, x):
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    ws = L.workspace(L.lib().kg_reduce_workspace_bytes(x.numel()), x.device)
+    L.call(name, L.f32(x), x.numel(), L.f32(out), L.ptr(ws), ws.numel(), L.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a2  embedding
+# ---------------------------------------------------------------------------------------------
+class EmbeddingFn(torch.autograd.Function):
+    """EmbeddingLayer.forward (kgvae/model.py:185-191)."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        table = _c(table)
+        out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+        L.call("kg_embedding_fwd", L.f32(table), L.i32(ids), ids.numel(), table.shape[1], L.f32(out),
+               L.stream())
+        ctx.save_for_backward(ids)
+        ctx.shape = table.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        g = _c(g)
+        grad = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        L.call("kg_embedding_bwd", L.f32(g), L.i32(ids), ids.numel(), ctx.shape[1], L.f32(grad),
+               L.stream())
+        return grad, None
+
+
+# ---------------------------------------------------------------------------------------------
+# a3  RelGraphConv("bdd") layer
+# ---------------------------------------------------------------------------------------------
+class BddConvFn(torch.autograd.Function):
+    """One RelGraphConv(bdd) layer: out = dropout(act(sum_e norm_e W_{r_e} x_src + h_bias +
+    x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59."""
+
+    @staticmethod
+    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask):
+        x, weight = _c(x), _c(weight)
+        dev = x.device
+        n, in_feat = x.shape
+        R = weight.shape[0]
+        si = in_feat // num_bases
+        so = weight.shape[1] // (num_bases * si)
+        out_feat = num_bases * so
+        if n != gi.n_nodes:
+            raise RuntimeError(f"RelGraphConv: {n} feature rows for a graph of {gi.n_nodes} nodes")
+        w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
+        w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
+        L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
+               L.f32(w_bwd), L.stream())
+        agg = torch.empty((n, out_feat), dtype=torch.float32, device=dev)
+        L.call("kg_bdd_aggregate_fwd", L.f32(x), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), L.f32(w_fwd),
+               n, num_bases, si, so, L.f32(agg), L.stream())
+        out = torch.empty_like(agg)
+        bias = None if h_bias is None else _c(h_bias)
+        mask = None if drop_mask is None else _c(drop_mask)
+        if loop_weight is not None:
+            loop_weight = _c(loop_weight)
+            gemm(x, loop_weight, out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
+        else:   # K = 0: the GEMM epilogue alone applies bias / activation / dropout
+            gemm(x[:, :0], agg[:0], out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
+        ctx.save_for_backward(x, weight, loop_weight, out, mask, w_bwd)
+        ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
+        ctx.has_bias = h_bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, loop_weight, out, mask, w_bwd = ctx.saved_tensors
+        gi, B, si, so = ctx.gi, ctx.num_bases, ctx.si, ctx.so
+        g = _c(g)
+        n = x.shape[0]
+        gpre = torch.empty_like(out)
+        L.call("kg_act_dropout_bwd", L.f32(g), L.f32(out), L.f32(mask), ctx.act, out.numel(),
+               L.f32(gpre), L.stream())
+        dx = dw = dloop = dbias = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.call("kg_bdd_aggregate_bwd_dx", L.f32(gpre), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
+                   L.f32(w_bwd), n, B, si, so, L.f32(dx), L.stream())
+            if loop_weight is not None:
+                gemm(gpre, loop_weight, dx, trans_b=True, accumulate=True)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(weight)
+            L.call("kg_bdd_aggregate_bwd_dw", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges,
+                   B, si, so, L.f32(dw), L.stream())
+        if loop_weight is not None and ctx.needs_input_grad[2]:
+            dloop = torch.empty_like(loop_weight)
+            gemm(x, gpre, dloop, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            dbias = colsum(gpre)
+        return dx, dw, dloop, dbias, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# a5  heads + reparameterised sample
+# ---------------------------------------------------------------------------------------------
+class ReparamFn(torch.autograd.Function):
+    """gaussian_parameters + sample_gaussian (kgvae/utils.py:323-361): returns (mean, var, z)."""
+
+    @staticmethod
+    def forward(ctx, h2, eps):
+        h2, eps = _c(h2), _c(eps)
+        n, h = eps.shape
+        zm, zv, z = (torch.empty_like(eps) for _ in range(3))
+        L.call("kg_reparam_fwd", L.f32(h2), L.f32(eps), n, h, L.f32(zm), L.f32(zv), L.f32(z), L.stream())
+        ctx.save_for_backward(h2, eps, zv)
+        return zm, zv, z
+
+    @staticmethod
+    def backward(ctx, gm, gv, gz):
+        h2, eps, zv = ctx.saved_tensors
+        n, h = eps.shape
+        gm = None if gm is None else _c(gm)
+        gv = None if gv is None else _c(gv)
+        gz = None if gz is None else _c(gz)
+        dh2 = torch.empty_like(h2)
+        L.call("kg_reparam_bwd", L.f32(h2), L.f32(eps), L.f32(zv), L.f32(gz), L.f32(gm), L.f32(gv),
+               n, h, L.f32(dh2), L.stream())
+        return dh2, None
+
+
+# ---------------------------------------------------------------------------------------------
+# a7  KL against the MoG prior
+# ---------------------------------------------------------------------------------------------
+class KlMogFn(torch.autograd.Function):
+    """mean_n[log N(z; m, v) - log MoG(z)] (kgvae/model.py:82-87 without the scalar flow term,
+    which the caller adds)."""
+
+    @staticmethod
+    def forward(ctx, z, z_mean, z_var, z_pre):
+        z, z_mean, z_var = _c(z), _c(z_mean), _c(z_var)
+        zp = _c(z_pre.reshape(-1, z_pre.shape[-1]))
+        n, h = z.shape
+        k = zp.shape[0] // 2
+        dev = z.device
+        ws = torch.empty((3, k, h), dtype=torch.float32, device=dev)
+        rows = torch.empty(n, dtype=torch.float32, device=dev)
+        resp = torch.empty((n, k), dtype=torch.float32, device=dev)
+        L.call("kg_kl_mog_fwd", L.f32(z), L.f32(z_mean), L.f32(z_var), L.f32(zp), n, h, k, L.f32(ws),
+               L.f32(rows), L.f32(resp), L.stream())
+        ctx.save_for_backward(z, z_mean, z_var, zp, ws, resp)
+        ctx.pre_shape = z_pre.shape
+        return _reduce("kg_sum", rows) / n
+
+    @staticmethod
+    def backward(ctx, g):
+        z, z_mean, z_var, zp, ws, resp = ctx.saved_tensors
+        n, h = z.shape
+        k = zp.shape[0] // 2
+        dz, dm, dv = (torch.empty_like(z) for _ in range(3))
+        dzp = torch.zeros_like(zp)
+        # the upstream gradient is a device scalar: apply it with a broadcast multiply below
+        L.call("kg_kl_mog_bwd", L.f32(z), L.f32(z_mean), L.f32(z_var), L.f32(zp), L.f32(ws),
+               L.f32(resp), 1.0 / n, n, h, k, L.f32(dz), L.f32(dm), L.f32(dv), L.f32(dzp), L.stream())
+        return dz * g, dm * g, dv * g, (dzp * g).view(ctx.pre_shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# a6  IAF pieces
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = [relu](x @ w^T + b): MaskedLinear (+ the in-place ReLU after it) with the masked
+    weight precomputed once per MADE call (kgvae/flow_network.py:15,53-63)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x, w = _c(x), _c(w)
+        y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+        gemm(x, w, y, trans_b=True, bias=None if b is None else _c(b), relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        g = _c(g)
+        if ctx.relu:
+            gp = torch.empty_like(g)
+            L.call("kg_act_dropout_bwd", L.f32(g), L.f32(y), None, 1, g.numel(), L.f32(gp), L.stream())
+            g = gp
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(g, w, dx)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            gemm(g, x, dw, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(g)
+        return dx, dw, db, None
+
+
+class IafUpdateFn(torch.autograd.Function):
+    """One pass of MADE.forward's update x[:, idx] = z[:, idx] * exp(alpha + mu) and, on request,
+    log_det = sum_j alpha_j (kgvae/flow_network.py:93-96)."""
+
+    @staticmethod
+    def forward(ctx, z, net_out, x_old, skip_last, want_log_det):
+        z, net_out = _c(z), _c(net_out)
+        n, d = z.shape
+        x_new = torch.empty_like(z)
+        log_det = torch.empty(n, dtype=torch.float32, device=z.device) if want_log_det else None
+        xo = None if x_old is None else _c(x_old)
+        L.call("kg_iaf_update_fwd", L.f32(z), L.f32(net_out), L.f32(xo), n, d, int(skip_last),
+               L.f32(x_new), L.f32(log_det), L.stream())
+        ctx.save_for_backward(z, net_out)
+        ctx.skip_last, ctx.has_old = bool(skip_last), x_old is not None
+        if want_log_det:
+            return x_new, log_det
+        return x_new, None
+
+    @staticmethod
+    def backward(ctx, gx, gl):
+        z, net_out = ctx.saved_tensors
+        n, d = z.shape
+        gx = torch.zeros_like(z) if gx is None else _c(gx)
+        gl = None if gl is None else _c(gl)
+        dz, dxo = torch.empty_like(z), torch.empty_like(z)
+        dnet = torch.empty_like(net_out)
+        L.call("kg_iaf_update_bwd", L.f32(z), L.f32(net_out), L.f32(gx), L.f32(gl), n, d,
+               int(ctx.skip_last), L.f32(dz), L.f32(dnet), L.f32(dxo), L.stream())
+        return dz, dnet, (dxo if ctx.has_old else None), None, None
+
+
+class ReverseColumnsFn(torch.autograd.Function):
+    """PermuteLayer (kgvae/flow_network.py:18-34): column reversal, its own inverse."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        out = torch.empty_like(x)
+        L.call("kg_reverse_columns", L.f32(x), x.shape[0], x.shape[1], L.f32(out), L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ReverseColumnsFn.apply(g)
+
+
+# ---------------------------------------------------------------------------------------------
+# a9  DistMult + BCE + regulariser
+# ---------------------------------------------------------------------------------------------
+class TripletIndex:
+    """Entity-major and relation-major orderings of one batch of triplets (backward only)."""
+
+    def __init__(self, triplets, n_nodes, n_rels):
+        dev = triplets.device
+        S = triplets.shape[0]
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ent_ptr = torch.empty(n_nodes + 1, **i32)
+        self.ent_pack = torch.empty((max(2 * S, 1), 4), **i32)
+        self.rel_ptr = torch.empty(n_rels + 1, **i32)
+        self.rel_perm = torch.empty(max(S, 1), **i32)
+        ws = L.workspace(L.lib().kg_triplet_index_workspace_bytes(S), dev)
+        L.call("kg_triplet_index", L.i32(triplets), S, n_nodes, n_rels, L.i32(self.ent_ptr),
+               L.i32(self.ent_pack), L.i32(self.rel_ptr), L.i32(self.rel_perm), L.ptr(ws),
+               ws.numel(), L.stream())
+
+
+class DistMultScoreFn(torch.autograd.Function):
+    """score_i = sum_d z[s,d] w[r,d] z[o,d] (+ shift): LinkPredict.calc_score and the
+    flow_log_prob shift of get_loss (kgvae/link_predict.py:57-63,75-76)."""
+
+    @staticmethod
+    def forward(ctx, z, w, triplets, shift):
+        z, w = _c(z), _c(w)
+        S = triplets.shape[0]
+        score = torch.empty(S, dtype=torch.float32, device=z.device)
+        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
+        L.call("kg_distmult_score", L.f32(z), L.f32(w), L.i32(triplets), S, z.shape[1], L.f32(sh),
+               L.f32(score), L.stream())
+        ctx.save_for_backward(z, w, triplets)
+        ctx.shift_shape = None if shift is None else shift.shape
+        return score
+
+    @staticmethod
+    def backward(ctx, g):
+        z, w, triplets = ctx.saved_tensors
+        g = _c(g)
+        S, h = triplets.shape[0], z.shape[1]
+        dz = dw = dshift = None
+        idx = TripletIndex(triplets, z.shape[0], w.shape[0])
+        if ctx.needs_input_grad[0]:
+            dz = torch.empty_like(z)
+            L.call("kg_distmult_bwd_dz", L.f32(z), L.f32(w), L.f32(g), L.i32(idx.ent_ptr),
+                   L.i32(idx.ent_pack), z.shape[0], h, L.f32(dz), L.stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            L.call("kg_distmult_bwd_dw", L.f32(z), L.f32(g), L.i32(triplets), L.i32(idx.rel_perm), S, h,
+                   L.f32(dw), L.stream())
+        if ctx.shift_shape is not None and ctx.needs_input_grad[3]:
+            dshift = _reduce("kg_sum", g).reshape(ctx.shift_shape)
+        return dz, dw, None, dshift
+
+
+class BceLogitsFn(torch.autograd.Function):
+    """F.binary_cross_entropy_with_logits(score, labels), mean reduction (kgvae/link_predict.py:77)."""
+
+    @staticmethod
+    def forward(ctx, score, labels):
+        score, labels = _c(score), _c(labels)
+        n = score.numel()
+        loss = torch.empty((), dtype=torch.float32, device=score.device)
+        dscore = torch.empty_like(score)
+        ws = L.workspace(L.lib().kg_reduce_workspace_bytes(n), score.device)
+        L.call("kg_bce_logits_fwd", L.f32(score), L.f32(labels), n, L.f32(loss), L.f32(dscore),
+               L.ptr(ws), ws.numel(), L.stream())
+        ctx.save_for_backward(dscore)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dscore,) = ctx.saved_tensors
+        return dscore * g, None
+
+
+class MeanSquareFn(torch.autograd.Function):
+    """torch.mean(x.pow(2)) (kgvae/link_predict.py:68-69)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return _reduce("kg_sum_squares", x) / x.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return x * (g * (2.0 / x.numel()))
+
+
+# ---------------------------------------------------------------------------------------------
+# a10  ranks
+# ---------------------------------------------------------------------------------------------
+def distmult_rank(emb, w, a, r, b, shift=None, cand_range=None, filt_ptr=None, filt_idx=None):
+    """0-indexed raw (or filtered) rank of b_i among all entities for queries (a_i, r_i):
+    utils.perturb_and_get_rank + sort_and_rank (kgvae/utils.py:180-221) without the score matrix."""
+    emb, w = _c(emb.detach()), _c(w.detach())
+    M, (V, h) = a.numel(), emb.shape
+    dev = emb.device
+    lo, hi = (0, V) if cand_range is None else cand_range
+    ranks = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    q = torch.empty((max(M, 1), h), dtype=torch.float32, device=dev)
+    ts = torch.empty(max(M, 1), dtype=torch.float32, device=dev)
+    sh = None if shift is None else _c(torch.as_tensor(shift, dtype=torch.float32, device=dev).reshape(1))
+    L.call("kg_distmult_rank", L.f32(emb), L.f32(w), L.i32(a), L.i32(r), L.i32(b), M, V, h, L.f32(sh),
+           int(lo), int(hi), L.i32(filt_ptr), L.i32(filt_idx), L.f32(q), L.f32(ts), L.i32(ranks),
+           L.stream())
+    return ranks[:M]

@@ -1,0 +1,235 @@
+"""Host-side helpers with the reference's names and behaviour (kgvae/utils.py).
+
+* graph construction and sampling stay on the host and follow the reference's legacy global
+  ``np.random`` call order, so sampled indices are bit-identical;
+* evaluation (``calc_mrr`` / ``perturb_and_get_rank``) runs on the GPU through the fused
+  score-and-count kernel - the reference moves the model to the CPU for this step;
+* the probability helpers are kept for the cold paths (``get_mmd``, ``sample_z``); the hot path
+  uses the fused kernels in ``ops``.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .graph import Graph
+
+
+# --------------------------------------------------------------------------------------------
+# graph construction (kgvae/utils.py:20-30,127-155)
+# --------------------------------------------------------------------------------------------
+def get_adj_and_degrees(num_nodes, triplets):
+    """Adjacency lists [[edge id, neighbour], ...] per node and their lengths (utils.py:20-30),
+    built with one stable sort instead of a Python loop over triplets."""
+    triplets = np.asarray(triplets)
+    n = len(triplets)
+    ends = np.concatenate((triplets[:, 0], triplets[:, 2]))
+    other = np.concatenate((triplets[:, 2], triplets[:, 0]))
+    eid = np.concatenate((np.arange(n), np.arange(n)))
+    # the reference appends (i, o) to s's list and (i, s) to o's list for i = 0..n-1 in turn
+    order = np.lexsort((np.concatenate((np.zeros(n), np.ones(n))), eid, ends))
+    degrees = np.bincount(ends, minlength=num_nodes)
+    pairs = np.stack((eid[order], other[order]), axis=1)
+    bounds = np.concatenate(([0], np.cumsum(degrees)))
+    adj_list = [pairs[bounds[v]:bounds[v + 1]] for v in range(num_nodes)]
+    return adj_list, degrees
+
+
+def comp_deg_norm(g):
+    in_deg = g.in_degrees(range(g.number_of_nodes())).float().numpy()
+    with np.errstate(divide="ignore"):
+        norm = 1.0 / in_deg
+    norm[np.isinf(norm)] = 0
+    return norm
+
+
+def build_graph_from_triplets(num_nodes, num_rels, triplets):
+    """Bidirectional graph with reverse relations ``rel + num_rels``, edges in ascending
+    (dst, src, rel) order, and 1/in-degree node norms (utils.py:135-150).  ``np.lexsort``
+    yields the same order as the reference's ``sorted(zip(dst, src, rel))``."""
+    src, rel, dst = (np.asarray(a) for a in triplets)
+    src, dst = np.concatenate((src, dst)), np.concatenate((dst, src))
+    rel = np.concatenate((rel, rel + num_rels))
+    order = np.lexsort((rel, src, dst))
+    src, dst, rel = src[order], dst[order], rel[order]
+    g = Graph()
+    g.add_nodes(num_nodes)
+    g.add_edges(src, dst)
+    return g, rel, comp_deg_norm(g)
+
+
+def build_test_graph(num_nodes, num_rels, edges):
+    src, rel, dst = np.asarray(edges).transpose()
+    return build_graph_from_triplets(num_nodes, num_rels, (src, rel, dst))
+
+
+# --------------------------------------------------------------------------------------------
+# sampling (kgvae/utils.py:33-124,158-171) - global np.random, reference call order
+# --------------------------------------------------------------------------------------------
+def sample_edge_uniform(adj_list, degrees, n_triplets, sample_size):
+    return np.random.choice(np.arange(n_triplets), sample_size, replace=False)
+
+
+def sample_edge_neighborhood(adj_list, degrees, n_triplets, sample_size):
+    """Neighbourhood-expansion sampler (utils.py:33-76): same RNG calls, same picks."""
+    edges = np.zeros(sample_size, dtype=np.int32)
+    sample_counts = np.array(degrees).copy()
+    picked = np.zeros(n_triplets, dtype=bool)
+    seen = np.zeros(len(degrees), dtype=bool)
+    node_ids = np.arange(len(degrees))
+    for i in range(sample_size):
+        weights = sample_counts * seen
+        if np.sum(weights) == 0:
+            weights = np.ones_like(weights)
+            weights[np.where(sample_counts == 0)] = 0
+        chosen_vertex = np.random.choice(node_ids, p=weights / np.sum(weights))
+        chosen_adj = adj_list[chosen_vertex]
+        seen[chosen_vertex] = True
+        while True:
+            edge_number, other_vertex = chosen_adj[np.random.choice(np.arange(chosen_adj.shape[0]))]
+            if not picked[edge_number]:
+                break
+        edges[i] = edge_number
+        picked[edge_number] = True
+        sample_counts[chosen_vertex] -= 1
+        sample_counts[other_vertex] -= 1
+        seen[other_vertex] = True
+    return edges
+
+
+def negative_sampling(pos_samples, num_entity, negative_rate):
+    """Corrupt the subject where u > 0.5, else the object (utils.py:158-171)."""
+    n = len(pos_samples)
+    total = n * negative_rate
+    neg = np.tile(pos_samples, (negative_rate, 1))
+    labels = np.zeros(n * (negative_rate + 1), dtype=np.float32)
+    labels[:n] = 1
+    values = np.random.randint(num_entity, size=total)
+    coin = np.random.uniform(size=total)
+    head = coin > 0.5
+    neg[head, 0] = values[head]
+    neg[~head, 2] = values[~head]
+    return np.concatenate((pos_samples, neg)), labels
+
+
+def generate_sampled_graph_and_labels(triplets, sample_size, split_size, num_rels, adj_list,
+                                      degrees, negative_rate, sampler="uniform"):
+    """Sample edges, relabel nodes, draw negatives, keep ``split_size`` of the edges as graph
+    structure (utils.py:85-124).  Returns (g, uniq_v, rel, norm, samples, labels)."""
+    if sampler == "uniform":
+        picked = sample_edge_uniform(adj_list, degrees, len(triplets), sample_size)
+    elif sampler == "neighbor":
+        picked = sample_edge_neighborhood(adj_list, degrees, len(triplets), sample_size)
+    else:
+        raise ValueError("Sampler type must be either 'uniform' or 'neighbor'.")
+    src, rel, dst = np.asarray(triplets)[picked].transpose()
+    uniq_v, relabeled = np.unique((src, dst), return_inverse=True)
+    src, dst = np.reshape(relabeled, (2, -1))
+    samples, labels = negative_sampling(np.stack((src, rel, dst)).transpose(), len(uniq_v),
+                                        negative_rate)
+    keep = np.random.choice(np.arange(sample_size), size=int(sample_size * split_size), replace=False)
+    g, rel, norm = build_graph_from_triplets(len(uniq_v), num_rels, (src[keep], rel[keep], dst[keep]))
+    return g, uniq_v, rel, norm, samples, labels
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation (kgvae/utils.py:180-221,293-314)
+# --------------------------------------------------------------------------------------------
+def sort_and_rank(score, target):
+    """0-indexed rank of ``target`` in each row of ``score`` (descending).  Same result as the
+    reference's sort + nonzero when scores are distinct; ties go to the lower entity id."""
+    t = target.view(-1, 1)
+    st = score.gather(1, t)
+    col = torch.arange(score.shape[1], device=score.device).view(1, -1)
+    return ((score > st).sum(1) + ((score == st) & (col < t)).sum(1)).view(-1)
+
+
+def perturb_and_get_rank(embedding, w, a, r, b, test_size, batch_size=100, all_batches=True,
+                         flow_log_prob=None, verbose=True, filt=None, cand_range=None):
+    """Rank of ``b`` among all entities for the queries (a, r) (utils.py:187-221).
+
+    The reference scores ``batch_size`` queries at a time through a D x E x V tensor; here all
+    queries go through one fused score-and-count launch (``batch_size`` only bounds the work
+    when ``all_batches`` is False, as in the reference's periodic validation)."""
+    n = int(test_size) if all_batches else min(int(test_size), int(batch_size))
+    dev = embedding.device
+    a32, r32, b32 = (ops.as_i32(t[:n], dev) for t in (a, r, b))
+    fp, fi = (None, None) if filt is None else filt
+    ranks = ops.distmult_rank(embedding, w, a32, r32, b32, shift=flow_log_prob,
+                              cand_range=cand_range, filt_ptr=fp, filt_idx=fi).long()
+    if verbose:
+        rr = ranks.float() + 1.0
+        print("ranked {} queries: MR : {:.6f} |  MRR : {:.6f} | Hit1: {:.6f} | Hit5: {:.6f} | Hit10: {:.6f}".format(
+            n, rr.mean().item(), (1.0 / rr).mean().item(), (rr <= 1).float().mean().item(),
+            (rr <= 5).float().mean().item(), (rr <= 10).float().mean().item()))
+    return ranks
+
+
+def calc_mrr(embedding, w, test_triplets, hits=[], eval_bz=100, all_batches=True, flow_log_prob=None,
+             verbose=True, return_ranks=False):
+    """Raw MRR / Hits@k over both perturbation directions (utils.py:293-314)."""
+    with torch.no_grad():
+        s, r, o = test_triplets[:, 0], test_triplets[:, 1], test_triplets[:, 2]
+        n = test_triplets.shape[0]
+        ranks_s = perturb_and_get_rank(embedding, w, o, r, s, n, eval_bz, all_batches, flow_log_prob, verbose)
+        ranks_o = perturb_and_get_rank(embedding, w, s, r, o, n, eval_bz, all_batches, flow_log_prob, verbose)
+        ranks = torch.cat([ranks_s, ranks_o]) + 1
+        mrr = torch.mean(1.0 / ranks.float())
+        if verbose:
+            print("MRR (raw): {:.6f}".format(mrr.item()))
+            for hit in hits:
+                print("Hits (raw) @ {}: {:.6f}".format(hit, torch.mean((ranks <= hit).float()).item()))
+    return (mrr.item(), ranks) if return_ranks else mrr.item()
+
+
+def build_filter(all_triplets, queries_a, queries_r, num_rels, direction, device):
+    """CSR of known-true candidates per query for filtered ranking (extension; the reference is
+    raw-only).  direction "object": candidates c with (a, r, c) known; "subject": (c, r, a)."""
+    t = np.asarray(all_triplets)
+    key_col, val_col = (0, 2) if direction == "object" else (2, 0)
+    keys = t[:, key_col].astype(np.int64) * num_rels + t[:, 1]
+    order = np.argsort(keys, kind="stable")
+    keys_sorted, vals_sorted = keys[order], t[order, val_col]
+    q = np.asarray(queries_a).astype(np.int64) * num_rels + np.asarray(queries_r)
+    lo = np.searchsorted(keys_sorted, q, side="left")
+    hi = np.searchsorted(keys_sorted, q, side="right")
+    # the kernel subtracts one count per listed candidate, so each list must be duplicate-free
+    lists = [np.unique(vals_sorted[l:h]) for l, h in zip(lo, hi)]
+    ptr = np.concatenate(([0], np.cumsum([len(x) for x in lists]))).astype(np.int32)
+    idx = (np.concatenate(lists) if lists else np.zeros(0)).astype(np.int32)
+    return torch.from_numpy(ptr).to(device), torch.from_numpy(idx).to(device)
+
+
+# --------------------------------------------------------------------------------------------
+# probability helpers (kgvae/utils.py:323-428)
+# --------------------------------------------------------------------------------------------
+def gaussian_parameters(h, dim=-1):
+    m, raw = torch.split(h, h.size(dim) // 2, dim=dim)
+    return m, F.softplus(raw) + 1e-8
+
+
+def sample_gaussian(m, v, repeat=1):
+    if repeat > 1:
+        sd = torch.cat([torch.sqrt(v.squeeze())] * repeat, dim=0)
+        m = torch.cat([m.squeeze()] * repeat, dim=0)
+    else:
+        sd = torch.sqrt(v)
+    return m + torch.randn_like(sd) * sd
+
+
+def log_normal(x, m, v):
+    lp = -(x - m).pow(2) / (2 * v) - v.sqrt().log() - np.log(np.sqrt(2 * np.pi))
+    return lp.sum(-1)
+
+
+def log_sum_exp(x, dim=0):
+    mx = torch.max(x, dim)[0]
+    return mx + (x - mx.unsqueeze(dim).expand_as(x)).exp().sum(dim).log()
+
+
+def log_mean_exp(x, dim):
+    return log_sum_exp(x, dim) - np.log(x.size(dim))
+
+
+def log_normal_mixture(z, m, v):
+    return log_mean_exp(log_normal(z.unsqueeze(1), m, v), dim=-1)

@@ -1,0 +1,224 @@
+/*
+ * kgvae_b200.h - C ABI of the B200-native GCN-VAE link-prediction hot path.
+ *
+ * The reference (karenyang/GCN-VAE) has no FFI layer: its hot path sits behind Python
+ * module calls into PyTorch/DGL.  Each entry point below replaces one of those calls;
+ * the "replaces" line cites the reference interface (file:line under /root/reference).
+ * The Python host side (gcn-vae_b200/ops.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator);
+ *     nothing is allocated or freed across this boundary; workspaces are caller-provided
+ *   - `stream` is the caller's cudaStream_t (as void*); all work is stream-ordered
+ *   - indices are int32, features fp32, row-major, contiguous unless a leading dimension
+ *     is passed
+ *   - return value: 0 on success, negative on error; kg_last_error() gives the message
+ *     (thread-local); no C++ exception crosses the boundary
+ */
+#ifndef KGVAE_B200_H_
+#define KGVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_OK 0
+#define KG_ERR_INVALID -1
+#define KG_ERR_CUDA -2
+#define KG_ERR_WORKSPACE -3
+
+const char* kg_last_error(void);
+int kg_version(void);
+/* device attributes used for grid sizing (SM count etc.); also a liveness check */
+int kg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * a1  graph construction
+ * replaces: utils.build_graph_from_triplets / comp_deg_norm  kgvae/utils.py:127-150
+ *           node_norm_to_edge_norm                           kgvae/link_predict.py:95-100
+ * Input: T triplets (src, rel, dst).  Output: 2T directed edges (reverse edges carry
+ * rel + num_rels) in ascending (dst, src, rel) order - the reference's
+ * sorted(zip(dst, src, rel)) - plus everything the kernels need:
+ *   e_src/e_dst/e_type [2T], row_ptr [N+1] (dst-CSR), node_norm [N] = 1/in_deg (0 if 0),
+ *   fwd_pack [2T] int4 {src, etype, bits(norm[dst]), dst}        (dst-major order)
+ *   col_ptr [N+1], bwd_pack [2T] int4 {dst, etype, bits(norm), edge_id}  (src-major order)
+ *   rel_ptr [2R+1], rel_pack [2T] int4 {src, dst, etype, bits(norm)}     (etype-major)
+ * Limits: N < 2^24, 2R < 2^16.
+ * ---------------------------------------------------------------------------------- */
+size_t kg_graph_build_workspace_bytes(int n_triplets);
+int kg_graph_build(const int32_t* src, const int32_t* rel, const int32_t* dst, int n_triplets,
+                   int num_nodes, int num_rels,
+                   int32_t* e_src, int32_t* e_dst, int32_t* e_type,
+                   int32_t* row_ptr, float* node_norm,
+                   void* fwd_pack, int32_t* col_ptr, void* bwd_pack,
+                   int32_t* rel_ptr, void* rel_pack,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same index structures from an edge list the caller already ordered (the DGLGraph
+ * surface: g.add_edges(src, dst) + etypes + per-edge norm, kgvae/utils.py:141-148).
+ * Edges need not be sorted; the original edge order is kept as the tie-break so the
+ * per-destination summation order equals the reference's edge order. */
+size_t kg_graph_index_workspace_bytes(int n_edges);
+int kg_graph_index(const int32_t* e_src, const int32_t* e_dst, const int32_t* e_type,
+                   const float* e_norm /* [E] or NULL (=1) */, int n_edges, int num_nodes,
+                   int num_etypes,
+                   int32_t* row_ptr, void* fwd_pack, int32_t* col_ptr, void* bwd_pack,
+                   int32_t* rel_ptr, void* rel_pack,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a2  embedding lookup
+ * replaces: EmbeddingLayer.forward   kgvae/model.py:185-191
+ * ---------------------------------------------------------------------------------- */
+int kg_embedding_fwd(const float* table, const int32_t* ids, int n, int dim, float* out, void* stream);
+/* grad_table must be zero-filled by the caller; rows are accumulated (duplicates allowed) */
+int kg_embedding_bwd(const float* grad_out, const int32_t* ids, int n, int dim, float* grad_table,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a3  RelGraphConv, regularizer="bdd" (block-diagonal decomposition)
+ * replaces: dgl.nn.pytorch.RelGraphConv.forward(g, x, etypes, norm), constructed at
+ *           kgvae/model.py:54-59, called at kgvae/model.py:110-111
+ * weight [R, B*si*so] row-major (b, i, o) as in DGL.
+ * ---------------------------------------------------------------------------------- */
+/* derived layouts, rebuilt whenever `weight` changes:
+ *   w_fwd [R, si, B*so]: w_fwd[r][i][b*so+o] = weight[r][b][i][o]
+ *   w_bwd [R, so, B*si]: w_bwd[r][o][b*si+i] = weight[r][b][i][o]                     */
+int kg_bdd_weight_layouts(const float* weight, int num_etypes, int num_bases, int si, int so,
+                          float* w_fwd, float* w_bwd, void* stream);
+/* agg[v, :] = sum_{e: dst_e = v} norm_e * blockdiag(W[etype_e]) * x[src_e, :]   (no atomics) */
+int kg_bdd_aggregate_fwd(const float* x, const int32_t* row_ptr, const void* fwd_pack,
+                         const float* w_fwd, int n_dst, int num_bases, int si, int so,
+                         float* agg, void* stream);
+/* dx[u, :] = sum_{e: src_e = u} norm_e * blockdiag(W[etype_e])^T * dagg[dst_e, :] */
+int kg_bdd_aggregate_bwd_dx(const float* dagg, const int32_t* col_ptr, const void* bwd_pack,
+                            const float* w_bwd, int n_src, int num_bases, int si, int so,
+                            float* dx, void* stream);
+/* dweight[r][b][i][o] += sum_{e: etype_e = r} norm_e * x[src_e][b*si+i] * dagg[dst_e][b*so+o]
+ * dweight must be zero-filled by the caller. */
+int kg_bdd_aggregate_bwd_dw(const float* x, const float* dagg, const void* rel_pack, int n_edges,
+                            int num_bases, int si, int so, float* dweight, void* stream);
+
+/* out = dropout(act(agg + bias + loop)) tail of RelGraphConv.forward; backward of the same.
+ * act: 0 identity, 1 relu.  drop_mask: [n, dim] keep-mask already scaled by 1/(1-p), or NULL. */
+int kg_act_dropout_bwd(const float* grad_out, const float* out, const float* drop_mask, int act,
+                       long long numel, float* grad_pre, void* stream);
+/* column sums of a [rows, cols] matrix (h_bias / MaskedLinear bias gradients); deterministic.
+ * workspace: kg_colsum_workspace_bytes(rows, cols) */
+size_t kg_colsum_workspace_bytes(int rows, int cols);
+int kg_colsum(const float* x, int rows, int cols, float* out, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * dense fp32 GEMM with fused epilogue (self-loop x@loop_weight kgvae/model.py:55,58 via DGL;
+ * MaskedLinear kgvae/flow_network.py:15 and its backward)
+ *   C[M,N] = epilogue( op(A)[M,K] * op(B)[K,N] )
+ *   A(m,k) = A[m*lda + k] if !trans_a else A[k*lda + m];  B(k,n) likewise with ldb.
+ *   epilogue: v = acc (+ bias[n]) (+ addend[m*ldc+n]); if relu v = max(v,0);
+ *             if mask v *= mask[m*ldc+n]; C = v   (accumulate: C += v)
+ * ---------------------------------------------------------------------------------- */
+int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
+                float* C, int ldc, int M, int N, int K,
+                const float* bias, const float* addend, int relu, const float* mask,
+                int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a5  mean/variance heads + reparameterised sample
+ * replaces: utils.gaussian_parameters kgvae/utils.py:323-339, utils.sample_gaussian :342-361
+ * h2 [n, 2h] -> z_mean = h2[:, :h], z_var = softplus(h2[:, h:]) + 1e-8, z = m + eps*sqrt(v)
+ * ---------------------------------------------------------------------------------- */
+int kg_reparam_fwd(const float* h2, const float* eps, int n, int h, float* z_mean, float* z_var,
+                   float* z, void* stream);
+/* dh2 from (dz, dmean, dvar); any of dmean/dvar may be NULL */
+int kg_reparam_bwd(const float* h2, const float* eps, const float* z_var, const float* dz,
+                   const float* dmean, const float* dvar, int n, int h, float* dh2, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a7  single-sample KL estimate against the mixture-of-Gaussians prior
+ * replaces: KGVAE.get_kl kgvae/model.py:82-87 (log_normal :381-398, log_normal_mixture :364-378)
+ * kl_rows[n] = logN(z_n; m_n, v_n) - log( (1/k) sum_i N(z_n; pm_i, pv_i) )   (flow term added
+ * by the caller); resp [n, k] = posterior responsibilities saved for backward.
+ * z_pre [2k, h]: rows 0..k-1 prior means, rows k..2k-1 raw variances (softplus + 1e-8).
+ * prior_ws [3, k, h]: workspace written by fwd (variance, 1/(2 var), log sqrt var), read by bwd.
+ * k <= 16.
+ * ---------------------------------------------------------------------------------- */
+int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z_var, const float* z_pre,
+                  int n, int h, int k, float* prior_ws, float* kl_rows, float* resp, void* stream);
+/* scale = dL/dkl / n.  dz_pre [2k, h] must be zero-filled by the caller. */
+int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z_var, const float* z_pre,
+                  const float* prior_ws, const float* resp, float scale, int n, int h, int k,
+                  float* dz, float* dmean, float* dvar, float* dz_pre, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a6  IAF: element update of one MADE pass
+ * replaces: MADE.forward body kgvae/flow_network.py:91-96
+ * net_out [n, 2d] = (mu | alpha).  x_new[:, j] = z[:, j]*exp(alpha[:, j] + mu[:, j]) for the
+ * updated columns; with skip_last the last column keeps x_old (passes 2..n_hidden+2).
+ * log_det[n] = sum_j alpha[n, j] (only written when log_det != NULL: the last pass).
+ * ---------------------------------------------------------------------------------- */
+int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old, int n, int d,
+                      int skip_last, float* x_new, float* log_det, void* stream);
+int kg_iaf_update_bwd(const float* z, const float* net_out, const float* dx_new,
+                      const float* dlog_det /* [n] or NULL */, int n, int d, int skip_last,
+                      float* dz, float* dnet_out, float* dx_old, void* stream);
+/* column reversal (PermuteLayer kgvae/flow_network.py:28-30); its own inverse and backward */
+int kg_reverse_columns(const float* x, int n, int d, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a9  DistMult decoder + BCE-with-logits + L2 regulariser
+ * replaces: LinkPredict.calc_score kgvae/link_predict.py:57-63, get_loss :71-78,
+ *           regularization_loss :68-69
+ * triplets [S, 3] int32 (s, r, o).  score_i = sum_d z[s,d] w[r,d] z[o,d] + shift
+ * ---------------------------------------------------------------------------------- */
+int kg_distmult_score(const float* z, const float* w, const int32_t* triplets, int n_triplets, int h,
+                      const float* shift /* device scalar or NULL */, float* score, void* stream);
+/* mean BCE-with-logits; also dscore_i = (sigmoid(score_i) - label_i) / S.
+ * partial: workspace of kg_reduce_workspace_bytes(S) bytes; loss_out: 1 float */
+size_t kg_reduce_workspace_bytes(long long n);
+int kg_bce_logits_fwd(const float* score, const float* labels, int n, float* loss_out, float* dscore,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* sum of squares of a flat array -> out[0] (deterministic two-stage reduce) */
+int kg_sum_squares(const float* x, long long n, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int kg_sum(const float* x, long long n, float* out, void* workspace, size_t workspace_bytes,
+           void* stream);
+/* index structures for the backward pass, built once per batch of triplets:
+ *   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, rel, triplet_id, 0}: for entity v, every
+ *     triplet where v is subject (other = object) or object (other = subject)
+ *   rel_ptr [n_rels+1], rel_perm [S]: triplet ids grouped by relation */
+size_t kg_triplet_index_workspace_bytes(int n_triplets);
+int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
+                     int32_t* ent_ptr, void* ent_pack, int32_t* rel_ptr, int32_t* rel_perm,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* dz[v,:] = sum_{(other, r, t) in ent(v)} gscore[t] * w[r,:] * z[other,:]    (no atomics) */
+int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore, const int32_t* ent_ptr,
+                       const void* ent_pack, int n_nodes, int h, float* dz, void* stream);
+/* dw[r,:] += sum_{t: rel_t = r} gscore[t] * z[s_t,:] * z[o_t,:]; dw zero-filled by the caller */
+int kg_distmult_bwd_dw(const float* z, const float* gscore, const int32_t* triplets,
+                       const int32_t* rel_perm, int n_triplets, int h, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * a10  all-entity rank evaluation
+ * replaces: utils.perturb_and_get_rank kgvae/utils.py:187-221 + sort_and_rank :180-184
+ * For each query i: q_i = emb[a_i] * w[r_i]; score_ij = q_i . emb[j] + shift for all j < V;
+ * rank_i = #{j : score_ij > score_i,b_i} + #{j < b_i : score_ij == score_i,b_i}  (0-indexed,
+ * ties by ascending entity id).  The M x V score matrix is never written to memory.
+ * cand_begin/cand_end restrict candidates to an entity shard [begin, end) (multi-GPU: the
+ * per-shard counts add up to the rank).
+ * filt_ptr/filt_idx (optional, may be NULL): CSR of known-true candidates per query that are
+ * removed from the count (filtered setting; the reference itself is raw-only, link_predict.py:7).
+ * queries: workspace [M, h] floats; tscore: workspace [M] floats.
+ * ---------------------------------------------------------------------------------- */
+int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const int32_t* r,
+                     const int32_t* b, int n_queries, int n_entities, int h,
+                     const float* shift /* device scalar or NULL */, int cand_begin, int cand_end,
+                     const int32_t* filt_ptr, const int32_t* filt_idx,
+                     float* queries, float* tscore, int32_t* ranks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGVAE_B200_H_ */

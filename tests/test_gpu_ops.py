@@ -1,0 +1,356 @@
+"""Per-kernel parity: each C-ABI entry point (through ops.py) against the oracle / plain fp32
+torch on the same seeded inputs.  Tolerance 1e-4 relative to the tensor scale (north_star),
+integers bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, RTOL, assert_close
+
+import gcn_vae_b200 as K
+from gcn_vae_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand_graph(seed, n, e, r):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, e)
+    dst = rng.integers(0, max(1, n - 3), e)          # the last nodes stay isolated
+    et = rng.integers(0, r, e)
+    order = np.lexsort((et, src, dst))
+    src, dst, et = src[order], dst[order], et[order]
+    norm = rng.random(e).astype(np.float32) + 0.1
+    return src, dst, et, norm
+
+
+def _index(src, dst, et, norm, n, r):
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(DEV)
+    return ops.graph_index(t(src, torch.int32), t(dst, torch.int32), t(et, torch.int32),
+                           t(norm, torch.float32), n, r)
+
+
+# ------------------------------------------------------------------------------ graph (a1)
+@pytest.mark.parametrize("n,e,r", [(50, 400, 6), (7, 0, 3), (300, 5000, 40), (5, 64, 1)])
+def test_graph_index_integer_exact(n, e, r):
+    src, dst, et, norm = _rand_graph(0, n, e, r)
+    perm = np.random.default_rng(1).permutation(e)       # hand it over unsorted
+    gi = _index(src[perm], dst[perm], et[perm], norm[perm], n, r)
+    s_, d_, t_, w_ = src[perm], dst[perm], et[perm], norm[perm]
+    for ptr, pack, key, cols in ((gi.row_ptr, gi.fwd_pack, d_, (s_, t_, w_.view(np.int32), d_)),
+                                 (gi.col_ptr, gi.bwd_pack, s_, (d_, t_, w_.view(np.int32), np.arange(e))),
+                                 (gi.rel_ptr, gi.rel_pack, t_, (s_, d_, t_, w_.view(np.int32)))):
+        order = np.argsort(key, kind="stable")
+        nbins = r if key is t_ else n
+        want_ptr = np.concatenate(([0], np.cumsum(np.bincount(key, minlength=nbins))))
+        assert np.array_equal(ptr.cpu().numpy(), want_ptr)
+        if e:
+            want = np.stack([c[order] for c in cols], axis=1).astype(np.int32)
+            assert np.array_equal(pack.cpu().numpy()[:e], want)
+
+
+@pytest.mark.parametrize("n,t,r", [(40, 300, 5), (1000, 20000, 237), (6, 1, 2)])
+def test_graph_build_matches_reference_order(n, t, r):
+    rng = np.random.default_rng(2)
+    s, o, rel = rng.integers(0, n, t), rng.integers(0, n, t), rng.integers(0, r, t)
+    want = O.build_graph_from_triplets(n, r, s, rel, o)
+    dv = lambda a: torch.from_numpy(a.astype(np.int32)).to(DEV)
+    gi = ops.graph_build(dv(s), dv(rel), dv(o), n, r)
+    assert np.array_equal(gi.e_src.cpu().numpy(), want["src"])
+    assert np.array_equal(gi.e_dst.cpu().numpy(), want["dst"])
+    assert np.array_equal(gi.e_type.cpu().numpy(), want["etype"])
+    assert np.array_equal(gi.node_norm.cpu().numpy(), want["norm"])          # bit-exact fp32
+    fwd = gi.fwd_pack.cpu().numpy()[:2 * t]
+    assert np.array_equal(fwd[:, 0], want["src"]) and np.array_equal(fwd[:, 1], want["etype"])
+    assert np.array_equal(fwd[:, 2].view(np.float32), want["edge_norm"].reshape(-1))
+    assert np.array_equal(gi.row_ptr.cpu().numpy(),
+                          np.concatenate(([0], np.cumsum(np.bincount(want["dst"], minlength=n)))))
+
+
+# ------------------------------------------------------------------------------ gemm
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (130, 70, 33), (257, 500, 500), (64, 1000, 20), (500, 100, 3000)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_layouts(M, N, K, ta, tb):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    want = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(a.to(DEV), b.to(DEV), out, trans_a=bool(ta), trans_b=bool(tb))
+    assert_close(out, want, 2e-5, f"gemm {M}x{N}x{K} ta={ta} tb={tb}")
+
+
+def test_gemm_epilogue_and_accumulate():
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 200, 90, 75
+    a, b = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    mask = (torch.rand(M, N, generator=g) < 0.8).float() / 0.8
+    want = torch.relu(a @ b + bias + add) * mask
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(a.to(DEV), b.to(DEV), out, bias=bias.to(DEV), addend=add.to(DEV), relu=True, mask=mask.to(DEV))
+    assert_close(out, want, 2e-5, "fused epilogue")
+    base = torch.randn(M, N, generator=g)
+    out2 = base.to(DEV).clone()
+    ops.gemm(a.to(DEV), b.to(DEV), out2, accumulate=True)
+    assert_close(out2, base + a @ b, 2e-5, "accumulate")
+    # K = 0: epilogue only
+    out3 = torch.empty(M, N, device=DEV)
+    ops.gemm(a.to(DEV)[:, :0], b.to(DEV)[:0], out3, bias=bias.to(DEV), addend=add.to(DEV))
+    assert_close(out3, add + bias, 1e-6, "K=0 epilogue")
+    # split-K path with a mask and with accumulate
+    a2, b2 = torch.randn(4000, 60, generator=g), torch.randn(4000, 50, generator=g)
+    m2 = (torch.rand(60, 50, generator=g) < 0.5).float()
+    out4 = torch.ones(60, 50, device=DEV)
+    ops.gemm(a2.to(DEV), b2.to(DEV), out4, trans_a=True, mask=m2.to(DEV), accumulate=True)
+    assert_close(out4, 1 + (a2.t().double() @ b2.double()).float() * m2, 2e-5, "split-K masked accumulate")
+
+
+def test_colsum_and_reductions():
+    g = torch.Generator().manual_seed(1)
+    for rows, cols in [(1, 1), (300, 37), (14541, 100), (0, 5)]:
+        x = torch.randn(rows, cols, generator=g)
+        assert_close(ops.colsum(x.to(DEV)), x.double().sum(0), 2e-5, f"colsum {rows}x{cols}")
+    x = torch.randn(1_000_003, generator=g)
+    assert_close(ops._reduce("kg_sum", x.to(DEV)), x.double().sum(), 1e-4, "sum")
+    assert_close(ops._reduce("kg_sum_squares", x.to(DEV)), (x.double() ** 2).sum(), 1e-5, "sumsq")
+
+
+# ------------------------------------------------------------------------------ embedding (a2)
+def test_embedding_fwd_bwd():
+    g = torch.Generator().manual_seed(2)
+    table = torch.randn(50, 24, generator=g, requires_grad=True)
+    ids = torch.tensor([3, 3, 49, 0, 7, 3])
+    gout = torch.randn(6, 24, generator=g)
+    table[ids].backward(gout)
+    t2 = table.detach().to(DEV).requires_grad_(True)
+    out = ops.EmbeddingFn.apply(t2, ids.to(torch.int32).to(DEV))
+    out.backward(gout.to(DEV))
+    assert torch.equal(out.detach().cpu(), table.detach()[ids])
+    assert_close(t2.grad, table.grad, 1e-6, "embedding grad")
+
+
+# ------------------------------------------------------------------------------ bdd layer (a3)
+@pytest.mark.parametrize("n,e,r,B,si,so,act", [(60, 500, 6, 4, 5, 5, 1), (60, 500, 6, 4, 5, 10, 0),
+                                               (200, 3000, 24, 20, 5, 10, 1), (33, 100, 3, 3, 7, 2, 0),
+                                               (10, 0, 2, 2, 4, 4, 1)])
+def test_bdd_layer_fwd_bwd(n, e, r, B, si, so, act):
+    src, dst, et, norm = _rand_graph(3, n, e, r)
+    g = torch.Generator().manual_seed(n + e)
+    x = torch.randn(n, B * si, generator=g, requires_grad=True)
+    weight = (torch.randn(r, B * si * so, generator=g) * 0.3).requires_grad_(True)
+    loop = (torch.randn(B * si, B * so, generator=g) * 0.2).requires_grad_(True)
+    bias = torch.randn(B * so, generator=g).requires_grad_(True)
+    mask = (torch.rand(n, B * so, generator=g) < 0.8).float() / 0.8
+    gout = torch.randn(n, B * so, generator=g)
+    graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
+    want = O.rgcn_bdd_layer(x, graph, weight, bias, loop, B, torch.relu if act else None, mask)
+    want.backward(gout)
+
+    gi = _index(src, dst, et, norm, n, r)
+    cu = [t.detach().to(DEV).requires_grad_(True) for t in (x, weight, loop, bias)]
+    out = ops.BddConvFn.apply(cu[0], cu[1], cu[2], cu[3], gi, B, act, mask.to(DEV))
+    out.backward(gout.to(DEV))
+    assert_close(out, want, RTOL, "bdd out")
+    for name, a, b in zip(("dx", "dW", "dloop", "dbias"), cu, (x, weight, loop, bias)):
+        assert_close(a.grad, b.grad, RTOL, f"bdd {name}")
+
+
+def test_relgraphconv_module_matches_shim_semantics():
+    """Module-level call with DGL's signature, no self loop / no bias / generic activation."""
+    n, e, r, B = 40, 300, 5, 4
+    src, dst, et, norm = _rand_graph(4, n, e, r)
+    layer = K.RelGraphConv(20, 40, r, "bdd", B, bias=False, activation=torch.tanh, self_loop=False).to(DEV)
+    g = K.Graph()
+    g.add_nodes(n)
+    g.add_edges(src, dst)
+    x = torch.randn(n, 20)
+    out = layer(g, x.to(DEV), torch.from_numpy(et).to(DEV), torch.from_numpy(norm).view(-1, 1).to(DEV))
+    graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
+    want = torch.tanh(O.rgcn_bdd_layer(x, graph, layer.weight.detach().cpu(), torch.zeros(40),
+                                       torch.zeros(20, 40), B))
+    assert_close(out, want, RTOL, "RelGraphConv module")
+    with pytest.raises(ValueError):
+        K.RelGraphConv(500, 500, 36, "bdd", 100)          # DGL: num_bases > num_rels -> num_rels
+
+
+# ------------------------------------------------------------------------------ latent (a5, a7)
+def test_reparam_fwd_bwd():
+    g = torch.Generator().manual_seed(5)
+    n, h = 70, 36
+    h2 = (torch.randn(n, 2 * h, generator=g) * 3).requires_grad_(True)
+    h2.data[0, h] = 25.0                                   # softplus threshold branch
+    eps = torch.randn(n, h, generator=g)
+    m, v = O.gaussian_parameters(h2)
+    z = O.sample_gaussian(m, v, eps)
+    gz, gm, gv = (torch.randn(n, h, generator=g) for _ in range(3))
+    (z * gz + m * gm + v * gv).sum().backward()
+    c = h2.detach().to(DEV).requires_grad_(True)
+    m2, v2, z2 = ops.ReparamFn.apply(c, eps.to(DEV))
+    (z2 * gz.to(DEV) + m2 * gm.to(DEV) + v2 * gv.to(DEV)).sum().backward()
+    assert_close(m2, m, 1e-6, "mean")
+    assert_close(v2, v, 1e-5, "var")
+    assert_close(z2, z, 1e-5, "z")
+    assert_close(c.grad, h2.grad, RTOL, "dh2")
+
+
+@pytest.mark.parametrize("n,h,k", [(50, 20, 3), (130, 100, 10), (9, 500, 16), (40, 33, 1)])
+def test_kl_mog_fwd_bwd(n, h, k):
+    g = torch.Generator().manual_seed(n + h + k)
+    leaf = lambda *s: torch.randn(*s, generator=g).requires_grad_(True)
+    z, m = leaf(n, h), leaf(n, h)
+    v = (torch.rand(n, h, generator=g) + 0.2).requires_grad_(True)
+    z_pre = (torch.randn(1, 2 * k, h, generator=g) * 0.5).requires_grad_(True)
+    want = O.kl_term(z, m, v, z_pre, None)
+    want.backward()
+    cu = [t.detach().to(DEV).requires_grad_(True) for t in (z, m, v, z_pre)]
+    got = ops.KlMogFn.apply(*cu)
+    got.backward()
+    assert_close(got, want, RTOL, "kl")
+    for name, a, b in zip(("dz", "dmean", "dvar", "dz_pre"), cu, (z, m, v, z_pre)):
+        assert_close(a.grad, b.grad, RTOL, f"kl {name}")
+
+
+# ------------------------------------------------------------------------------ IAF (a6)
+def test_made_module_matches_golden(golden):
+    gv = golden("made_block")
+    D, nh, N = (int(x) for x in gv["cfg"])
+    made = K.MADE(D, D, nh)
+    made.load_state_dict({k[len("param/"):]: torch.from_numpy(v) for k, v in gv.items() if k.startswith("param/")})
+    made = made.to(DEV)
+    perm = K.PermuteLayer(D)
+    z = torch.from_numpy(gv["z"]).to(DEV).requires_grad_(True)
+    x, log_det = made(z)
+    xp, zero = perm(x)
+    (xp.pow(2).sum() + log_det.sum()).backward()
+    assert_close(x, gv["x"], RTOL, "made x")
+    assert_close(log_det, gv["log_det"], RTOL, "made log_det")
+    assert_close(xp, gv["x_perm"], RTOL, "permute")
+    assert tuple(zero.shape) == (N, 1) and float(zero.abs().sum()) == 0
+    assert_close(z.grad, gv["z_grad"], RTOL, "made dz")
+    for l in range(nh + 2):
+        assert_close(made.net[2 * l].weight.grad, gv[f"grad/net.{2 * l}.weight"], RTOL, f"made dW{l}")
+        assert_close(made.net[2 * l].bias.grad, gv[f"grad/net.{2 * l}.bias"], RTOL, f"made db{l}")
+    zi, ldi = made.inverse(x.detach())
+    assert_close(zi, gv["inv_z"], RTOL, "inverse z")
+    assert_close(ldi, gv["inv_log_det"], RTOL, "inverse log_det")
+
+
+def test_permute_is_involution():
+    x = torch.randn(17, 9, device=DEV)
+    p = K.PermuteLayer(9)
+    assert torch.equal(p(p(x)[0])[0], x)
+
+
+# ------------------------------------------------------------------------------ decoder (a9)
+@pytest.mark.parametrize("n,h,r,S", [(40, 20, 3, 500), (300, 100, 7, 5000), (25, 33, 2, 64), (10, 8, 2, 0)])
+def test_distmult_loss_fwd_bwd(n, h, r, S):
+    g = torch.Generator().manual_seed(n + S)
+    z = torch.randn(n, h, generator=g).requires_grad_(True)
+    w = torch.randn(r, h, generator=g).requires_grad_(True)
+    shift = torch.randn((), generator=g).requires_grad_(True)
+    rng = np.random.default_rng(S)
+    trip = np.stack([rng.integers(0, n, S), rng.integers(0, r, S), rng.integers(0, n, S)], 1).astype(np.int64)
+    labels = torch.from_numpy((rng.random(S) < 0.3).astype(np.float32))
+    score = O.distmult_score(z, w, trip) + shift
+    cu = [t.detach().to(DEV).requires_grad_(True) for t in (z, w, shift)]
+    got_score = ops.DistMultScoreFn.apply(cu[0], cu[1], torch.from_numpy(trip).to(torch.int32).to(DEV), cu[2])
+    assert_close(got_score, score, RTOL, "score")
+    if S == 0:
+        return
+    want = torch.nn.functional.binary_cross_entropy_with_logits(score, labels)
+    want.backward()
+    got = ops.BceLogitsFn.apply(got_score, labels.to(DEV))
+    got.backward()
+    assert_close(got, want, 1e-5, "bce")
+    for name, a, b in zip(("dz", "dw", "dshift"), cu, (z, w, shift)):
+        assert_close(a.grad, b.grad, RTOL, f"distmult {name}")
+
+
+def test_mean_square():
+    x = torch.randn(300, 50).requires_grad_(True)
+    x.pow(2).mean().backward()
+    c = x.detach().to(DEV).requires_grad_(True)
+    got = ops.MeanSquareFn.apply(c)
+    got.backward()
+    assert_close(got, x.detach().pow(2).mean(), 1e-5, "mean square")
+    assert_close(c.grad, x.grad, 1e-6, "mean square grad")
+
+
+# ------------------------------------------------------------------------------ ranks (a10)
+def _oracle_ranks(emb, w, a, r, b, shift):
+    score = O.eval_scores(emb, w, torch.as_tensor(a), torch.as_tensor(r), shift)
+    return O.rank_of_target(score, torch.as_tensor(b)), O.rank_interval(score, torch.as_tensor(b)), score
+
+
+def test_rank_exact_fixture_bit_exact(golden):
+    gv = golden("rank_exact")
+    emb, w = torch.from_numpy(gv["emb"]), torch.from_numpy(gv["w"])
+    t = torch.from_numpy(gv["test_triples"])
+    _, ranks = K.utils.calc_mrr(emb.to(DEV), w.to(DEV), t.to(DEV), eval_bz=32, verbose=False, return_ranks=True)
+    _, _, want = O.calc_mrr(emb, w, t, eval_bz=32, policy="stable", apply_sigmoid=False)
+    assert torch.equal(ranks.cpu(), want)
+    # and inside the tie interval of the reference's own (sigmoid, unstable-sort) ranks
+    s, r, o = t[:, 0], t[:, 1], t[:, 2]
+    lo_s, hi_s = O.rank_interval(torch.sigmoid(O.eval_scores(emb, w, o, r)), s)
+    lo_o, hi_o = O.rank_interval(torch.sigmoid(O.eval_scores(emb, w, s, r)), o)
+    lo, hi = torch.cat([lo_s, lo_o]), torch.cat([hi_s, hi_o])
+    got0 = ranks.cpu() - 1
+    assert bool(((got0 >= lo) & (got0 <= hi)).all())
+    ref = torch.from_numpy(gv["ref_ranks"])
+    untied = lo == hi
+    assert torch.equal(got0[untied], ref[untied])
+
+
+@pytest.mark.parametrize("V,h,M", [(96, 16, 80), (1000, 100, 300), (14541, 500, 48), (130, 20, 1)])
+def test_rank_dyadic_inputs_bit_exact(V, h, M):
+    """Inputs on a coarse dyadic grid: every partial sum is exact in fp32, so ranks do not
+    depend on accumulation order and must equal the oracle's bit for bit (ties included)."""
+    rng = np.random.default_rng(V + M)
+    emb = torch.from_numpy(rng.integers(-4, 5, size=(V, h)).astype(np.float32) / 4)
+    w = torch.from_numpy(rng.integers(-4, 5, size=(7, h)).astype(np.float32) / 4)
+    a, r, b = rng.integers(0, V, M), rng.integers(0, 7, M), rng.integers(0, V, M)
+    shift = 0.375
+    want, _, _ = _oracle_ranks(emb, w, a, r, b, shift)
+    dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
+    got = ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b), shift=shift)
+    assert torch.equal(got.cpu().long(), want)
+    # entity shards add up (multi-GPU evaluation)
+    parts = [ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b), shift=shift, cand_range=(lo, hi))
+             for lo, hi in ((0, V // 3), (V // 3, V // 3 + 1), (V // 3 + 1, V))]
+    assert torch.equal(sum(p.long() for p in parts).cpu(), want)
+
+
+def test_rank_random_floats_within_tolerance_interval():
+    rng = np.random.default_rng(9)
+    V, h, M = 2000, 500, 100
+    emb = torch.from_numpy(rng.standard_normal((V, h)).astype(np.float32))
+    w = torch.from_numpy(rng.standard_normal((11, h)).astype(np.float32))
+    a, r, b = rng.integers(0, V, M), rng.integers(0, 11, M), rng.integers(0, V, M)
+    dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
+    got = ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b)).cpu().long()
+    score = O.eval_scores(emb.double(), w.double(), torch.as_tensor(a), torch.as_tensor(r))
+    st = score.gather(1, torch.as_tensor(b).view(-1, 1))
+    tol = 1e-4 * score.abs().max()
+    lo = (score > st + tol).sum(1)
+    hi = (score >= st - tol).sum(1) - 1
+    assert bool(((got >= lo) & (got <= hi)).all())
+    exact = O.rank_of_target(score, torch.as_tensor(b))
+    assert int((got != exact).sum()) <= M // 20
+
+
+def test_rank_filtered():
+    rng = np.random.default_rng(10)
+    V, h, M = 400, 32, 60
+    emb = torch.from_numpy(rng.integers(-4, 5, size=(V, h)).astype(np.float32) / 4)
+    w = torch.from_numpy(rng.integers(-4, 5, size=(3, h)).astype(np.float32) / 4)
+    a, r, b = rng.integers(0, V, M), rng.integers(0, 3, M), rng.integers(0, V, M)
+    known = [sorted(set(rng.integers(0, V, rng.integers(0, 40)).tolist()) | {int(b[i])}) for i in range(M)]
+    score = O.eval_scores(emb, w, torch.as_tensor(a), torch.as_tensor(r))
+    want = O.filtered_ranks(score, b, known)
+    ptr = np.concatenate(([0], np.cumsum([len(x) for x in known]))).astype(np.int32)
+    idx = np.concatenate(known).astype(np.int32)
+    dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
+    got = ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b), filt_ptr=dv(ptr), filt_idx=dv(idx))
+    assert torch.equal(got.cpu().long(), want)

@@ -1,0 +1,106 @@
+"""Host-side logic of the package against the oracle and the golden vectors (CPU only)."""
+import numpy as np
+import torch
+
+from helpers import O
+
+import gcn_vae_b200 as K
+
+
+def _train_triples(seed, n_ent, n_rel, n):
+    rng = np.random.default_rng(seed)
+    s = rng.integers(0, n_ent, size=n)
+    o = rng.integers(0, n_ent, size=n)
+    r = rng.integers(0, n_rel, size=n)
+    return np.stack([s, r, o], axis=1).astype(np.int64)
+
+
+def test_sampler_matches_reference_golden(golden):
+    gv = golden("sampling_seed0")
+    n_ent, n_rel, n_train, batch, neg, seed, _ = (int(x) for x in gv["cfg"])
+    train = _train_triples(seed, n_ent, n_rel, n_train)
+    np.random.seed(0)
+    g, uniq_v, rel, norm, samples, labels = K.utils.generate_sampled_graph_and_labels(
+        train, batch, 0.5, n_rel, None, None, neg, "uniform")
+    assert np.array_equal(g._src, gv["g_src"])
+    assert np.array_equal(g._dst, gv["g_dst"])
+    assert np.array_equal(rel, gv["edge_type"])
+    assert np.array_equal(norm.astype(np.float32), gv["node_norm"])
+    assert np.array_equal(uniq_v, gv["node_id"])
+    assert np.array_equal(samples, gv["samples"])
+    assert float(labels.sum()) == float(gv["labels_sum"])
+    en = K.node_norm_to_edge_norm(g, torch.from_numpy(norm).view(-1, 1))
+    assert np.array_equal(en.numpy().reshape(-1), norm[g._dst])
+
+
+def test_graph_build_matches_oracle():
+    t = _train_triples(5, 50, 4, 300)
+    g, rel, norm = K.utils.build_graph_from_triplets(50, 4, (t[:, 0], t[:, 1], t[:, 2]))
+    want = O.build_graph_from_triplets(50, 4, t[:, 0], t[:, 1], t[:, 2])
+    assert np.array_equal(g._src, want["src"]) and np.array_equal(g._dst, want["dst"])
+    assert np.array_equal(rel, want["etype"])
+    assert np.array_equal(norm.astype(np.float32), want["norm"])
+    assert len(g) == 50 and g.number_of_nodes() == 50 and g.number_of_edges() == 600
+    assert np.array_equal(g.in_degrees(range(50)).numpy(), np.bincount(want["dst"], minlength=50))
+
+
+def test_adjacency_lists_follow_reference_order():
+    t = _train_triples(6, 20, 3, 60)
+    t[3] = (4, 1, 4)                      # self loop: appears twice in its list
+    adj, deg = K.utils.get_adj_and_degrees(20, t)
+    ref = [[] for _ in range(20)]
+    for i, (s, _, o) in enumerate(t):     # kgvae/utils.py:24-26
+        ref[s].append([i, o])
+        ref[o].append([i, s])
+    for v in range(20):
+        assert deg[v] == len(ref[v])
+        assert np.array_equal(adj[v].reshape(-1, 2), np.array(ref[v]).reshape(-1, 2))
+
+
+def test_neighbor_sampler_is_reproducible_and_valid():
+    t = _train_triples(8, 40, 3, 200)
+    adj, deg = K.utils.get_adj_and_degrees(40, t)
+    np.random.seed(1)
+    a = K.utils.sample_edge_neighborhood(adj, deg, len(t), 50)
+    np.random.seed(1)
+    b = K.utils.sample_edge_neighborhood(adj, deg, len(t), 50)
+    assert np.array_equal(a, b) and len(set(a.tolist())) == 50
+
+
+def test_state_dict_keys_match_reference(golden):
+    gv = golden("kgvae_tiny_flow3")
+    n_ent, n_rel, h, bases, k, n_flows, _ = (int(x) for x in gv["cfg"])
+    model = K.LinkPredict(K.KGVAE, n_ent, h, n_rel, num_bases=bases, k=k, n_flows=n_flows)
+    want = {key[len("param/"):]: val.shape for key, val in gv.items() if key.startswith("param/")}
+    got = {key: tuple(val.shape) for key, val in model.state_dict().items()}
+    assert set(got) == set(want)
+    for key in want:
+        assert got[key] == tuple(want[key]), key
+    model.load_state_dict({key: torch.from_numpy(gv["param/" + key]) for key in want})
+
+
+def test_made_masks_and_pass_plan(golden):
+    gv = golden("made_block")
+    D, nh, _ = (int(x) for x in gv["cfg"])
+    made = K.MADE(D, D, nh)
+    for l in range(nh + 2):
+        assert np.array_equal(made.net[2 * l].mask.numpy(), gv[f"param/net.{2 * l}.mask"])
+    for i, deg in enumerate(made.m):
+        assert np.array_equal(deg.numpy(), gv[f"deg/{i}"])
+    assert made._covers_last == [True] + [False] * (nh + 1) + [True]
+
+
+def test_synthetic_shapes():
+    d = K.datasets.synthetic_kg("FB15k-237", seed=0, scale=0.01)
+    assert d.num_nodes == 14541 and d.num_rels == 237 and d.train.shape == (2721, 3)
+    assert d.train[:, 1].max() < 237 and d.train[:, [0, 2]].max() < 14541
+    z = K.datasets.synthetic_kg("toy", seed=0, skew=1.0)
+    assert np.bincount(z.train[:, 0]).max() > 5 * len(z.train) / z.num_nodes
+
+
+def test_filter_csr():
+    allt = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 2], [3, 1, 0], [4, 0, 1]])
+    ptr, idx = K.utils.build_filter(allt, [0, 3, 9], [0, 1, 0], 2, "object", "cpu")
+    assert ptr.tolist() == [0, 2, 3, 3] and idx.tolist() == [1, 2, 0]
+    ptr, idx = K.utils.build_filter(allt, [1, 2], [0, 0], 2, "subject", "cpu")
+    assert ptr.tolist() == [0, 2, 3] and idx.tolist() == [0, 4, 0]
