@@ -36,8 +36,8 @@ _SIGNATURES = {
     "kg_reparam_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_kl_mog_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "kg_kl_mog_bwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "kg_iaf_update_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
-    "kg_iaf_update_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "kg_iaf_update_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "kg_iaf_update_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "kg_reverse_columns": (_I, [_P, _I, _I, _P, _P]),
     "kg_distmult_score": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "kg_reduce_workspace_bytes": (_Z, [_L]),

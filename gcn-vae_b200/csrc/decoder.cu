@@ -191,7 +191,7 @@ static size_t triplet_cub_bytes(int S) {
 
 extern "C" size_t kg_triplet_index_workspace_bytes(int n_triplets) {
   int S = n_triplets > 0 ? n_triplets : 1;
-  return 4 * kg_align_up((size_t)2 * S * 4) + 2 * kg_align_up((size_t)S * 4) + triplet_cub_bytes(S) + 1024;
+  return 4 * kg_align_up(((size_t)2 * S + 1) * 4) + 2 * kg_align_up(((size_t)S + 1) * 4) + triplet_cub_bytes(S) + 1024;
 }
 
 extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,

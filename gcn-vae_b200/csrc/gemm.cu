@@ -68,7 +68,7 @@ extern "C" int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B,
                            const float* addend, int relu, const float* mask, int accumulate,
                            void* stream) {
   KG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative size");
-  KG_REQUIRE(A && B && C, "gemm: null operand");
+  KG_REQUIRE(C && (K == 0 || (A && B)), "gemm: null operand");
   if (M == 0 || N == 0) return KG_OK;
   cudaStream_t st = kg_stream(stream);
 

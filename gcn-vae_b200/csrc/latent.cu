@@ -195,10 +195,16 @@ extern "C" int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z
 
 // ------------------------------------------------------------------------------------------
 // a6  IAF element update   (reference kgvae/flow_network.py:91-96)
+//
+// col_mult[j] = how many times column j occurs in the pass's index list.  0: the column keeps
+// x_old.  The reference writes x[:, idx] = z[:, idx] * exp(...) with idx = arange(D) % (D-1) in
+// the middle passes, where column 0 is listed twice: the forward value is unchanged, but
+// autograd's index_put backward hands the column's gradient to BOTH occurrences, so the
+// reference's gradients through that column are doubled.  Reproduced here via the multiplicity.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 iaf_update_fwd_kernel(const float* __restrict__ z, const float* __restrict__ net,
-                      const float* __restrict__ x_old, int n, int d, int skip_last,
+                      const float* __restrict__ x_old, const int* __restrict__ col_mult, int n, int d,
                       float* __restrict__ x_new, float* __restrict__ log_det) {
   const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -210,7 +216,7 @@ iaf_update_fwd_kernel(const float* __restrict__ z, const float* __restrict__ net
     const float al = alpha[j];
     s += al;
     const size_t off = (size_t)row * d + j;
-    if (skip_last && j == d - 1) x_new[off] = x_old[off];
+    if (__ldg(col_mult + j) == 0) x_new[off] = x_old[off];
     else x_new[off] = z[off] * expf(al + mu[j]);                          // flow_network.py:95
   }
   if (log_det) {
@@ -221,21 +227,23 @@ iaf_update_fwd_kernel(const float* __restrict__ z, const float* __restrict__ net
 
 __global__ void iaf_update_bwd_kernel(const float* __restrict__ z, const float* __restrict__ net,
                                       const float* __restrict__ dx_new,
-                                      const float* __restrict__ dlog_det, int n, int d, int skip_last,
+                                      const float* __restrict__ dlog_det,
+                                      const int* __restrict__ col_mult, int n, int d,
                                       float* __restrict__ dz, float* __restrict__ dnet,
                                       float* __restrict__ dx_old) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * d) return;
   const int row = (int)(t / d), j = (int)(t % d);
-  const float g = dx_new[t];
+  const int mult = __ldg(col_mult + j);
   const float gl = dlog_det ? dlog_det[row] : 0.f;
   float* dmu = dnet + (size_t)row * 2 * d;
-  if (skip_last && j == d - 1) {
+  if (mult == 0) {
     dz[t] = 0.f;
     dmu[j] = 0.f;
     dmu[d + j] = gl;
-    dx_old[t] = g;
+    dx_old[t] = dx_new[t];
   } else {
+    const float g = dx_new[t] * (float)mult;
     const float e = expf(net[(size_t)row * 2 * d + d + j] + net[(size_t)row * 2 * d + j]);
     const float gx = g * z[t] * e;
     dz[t] = g * e;
@@ -245,24 +253,24 @@ __global__ void iaf_update_bwd_kernel(const float* __restrict__ z, const float* 
   }
 }
 
-extern "C" int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old, int n, int d,
-                                 int skip_last, float* x_new, float* log_det, void* stream) {
-  KG_REQUIRE(n >= 0 && d > 0, "iaf fwd: bad sizes");
-  KG_REQUIRE(!skip_last || x_old, "iaf fwd: skip_last needs x_old");
+extern "C" int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old,
+                                 const int32_t* col_mult, int n, int d, float* x_new, float* log_det,
+                                 void* stream) {
+  KG_REQUIRE(n >= 0 && d > 0 && col_mult && x_old, "iaf fwd: bad arguments");
   if (n == 0) return KG_OK;
   iaf_update_fwd_kernel<<<kg_div_up((long long)n * 32, kThreads), kThreads, 0, kg_stream(stream)>>>(
-      z, net_out, x_old, n, d, skip_last, x_new, log_det);
+      z, net_out, x_old, col_mult, n, d, x_new, log_det);
   KG_LAUNCH_OK();
   return KG_OK;
 }
 
 extern "C" int kg_iaf_update_bwd(const float* z, const float* net_out, const float* dx_new,
-                                 const float* dlog_det, int n, int d, int skip_last, float* dz,
-                                 float* dnet_out, float* dx_old, void* stream) {
-  KG_REQUIRE(n >= 0 && d > 0, "iaf bwd: bad sizes");
+                                 const float* dlog_det, const int32_t* col_mult, int n, int d,
+                                 float* dz, float* dnet_out, float* dx_old, void* stream) {
+  KG_REQUIRE(n >= 0 && d > 0 && col_mult, "iaf bwd: bad arguments");
   if (n == 0) return KG_OK;
   iaf_update_bwd_kernel<<<kg_div_up((long long)n * d, kThreads), kThreads, 0, kg_stream(stream)>>>(
-      z, net_out, dx_new, dlog_det, n, d, skip_last, dz, dnet_out, dx_old);
+      z, net_out, dx_new, dlog_det, col_mult, n, d, dz, dnet_out, dx_old);
   KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -64,13 +64,8 @@ class MADE(nn.Module):
         degrees += [torch.arange(self.hidden_size) % (D - 1) for _ in range(self.n_hidden + 1)]
         degrees += [torch.arange(D) % D - 1]
         self.m = degrees
-        # per pass: does the column list reach the last column?  (every list must reach all others)
-        self._covers_last = []
-        for cols in degrees:
-            hit = set((cols % D).tolist())
-            if not set(range(D - 1)) <= hit:
-                raise NotImplementedError("MADE: hidden_size must be >= input_size - 1")
-            self._covers_last.append((D - 1) in hit)
+        # per pass: how often each column occurs in the index list (0 = column is not rewritten)
+        self._col_mult = [torch.bincount(cols % D, minlength=D).to(torch.int32) for cols in degrees]
         return [(hi.unsqueeze(-1) >= lo.unsqueeze(0)).float()
                 for lo, hi in zip(degrees[:-1], degrees[1:])]
 
@@ -86,20 +81,17 @@ class MADE(nn.Module):
     def forward(self, z):
         """z -> (x, log_det[N]).  One full pass per entry of ``self.m``: pass p rewrites the
         columns listed in ``self.m[p]`` (all columns for the first and last pass, all but the
-        last column in between) with z * exp(alpha + mu) (flow_network.py:85-98)."""
+        last column - with column 0 listed twice - in between) with z * exp(alpha + mu)
+        (flow_network.py:85-98)."""
         weights = [layer.masked_weight() for layer in self._linears()]
-        x, log_det = None, None
+        if self._col_mult[0].device != z.device:
+            self._col_mult = [m.to(z.device) for m in self._col_mult]
+        x = torch.zeros_like(z)
+        log_det = None
         n_pass = len(self.m)
-        for p, covers_last in enumerate(self._covers_last):
-            if x is None:
-                x_in = torch.zeros_like(z)
-            else:
-                x_in = x
-            out = self._run_net(x_in, weights)
-            last = p + 1 == n_pass
-            x, ld = ops.IafUpdateFn.apply(z, out, x_in, not covers_last, last)
-            if last:
-                log_det = ld
+        for p, mult in enumerate(self._col_mult):
+            out = self._run_net(x, weights)
+            x, log_det = ops.IafUpdateFn.apply(z, out, x, mult, p + 1 == n_pass)
         return x, log_det
 
     def inverse(self, x):

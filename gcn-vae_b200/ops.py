@@ -92,6 +92,14 @@ def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, addend=None, relu=F
     return out
 
 
+def epilogue_only(out, bias=None, addend=None, relu=False, mask=None):
+    """out = mask * act(addend + bias): the GEMM epilogue with an empty product (K = 0)."""
+    M, N = out.shape
+    L.call("kg_gemm_f32", None, 0, 0, None, 0, 0, L.f32(out), N, M, N, 0, L.f32(bias), L.f32(addend),
+           int(relu), L.f32(mask), 0, L.stream())
+    return out
+
+
 def colsum(x):
     rows, cols = x.shape
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
@@ -164,8 +172,8 @@ class BddConvFn(torch.autograd.Function):
         if loop_weight is not None:
             loop_weight = _c(loop_weight)
             gemm(x, loop_weight, out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
-        else:   # K = 0: the GEMM epilogue alone applies bias / activation / dropout
-            gemm(x[:, :0], agg[:0], out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
+        else:
+            epilogue_only(out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
         ctx.save_for_backward(x, weight, loop_weight, out, mask, w_bwd)
         ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
         ctx.has_bias = h_bias is not None
@@ -301,34 +309,31 @@ class LinearFn(torch.autograd.Function):
 
 class IafUpdateFn(torch.autograd.Function):
     """One pass of MADE.forward's update x[:, idx] = z[:, idx] * exp(alpha + mu) and, on request,
-    log_det = sum_j alpha_j (kgvae/flow_network.py:93-96)."""
+    log_det = sum_j alpha_j (kgvae/flow_network.py:93-96).  ``col_mult`` [d] int32 counts how often
+    each column occurs in ``idx`` (0: column keeps ``x_old``; see kg_iaf_update_bwd)."""
 
     @staticmethod
-    def forward(ctx, z, net_out, x_old, skip_last, want_log_det):
-        z, net_out = _c(z), _c(net_out)
+    def forward(ctx, z, net_out, x_old, col_mult, want_log_det):
+        z, net_out, x_old = _c(z), _c(net_out), _c(x_old)
         n, d = z.shape
         x_new = torch.empty_like(z)
         log_det = torch.empty(n, dtype=torch.float32, device=z.device) if want_log_det else None
-        xo = None if x_old is None else _c(x_old)
-        L.call("kg_iaf_update_fwd", L.f32(z), L.f32(net_out), L.f32(xo), n, d, int(skip_last),
+        L.call("kg_iaf_update_fwd", L.f32(z), L.f32(net_out), L.f32(x_old), L.i32(col_mult), n, d,
                L.f32(x_new), L.f32(log_det), L.stream())
-        ctx.save_for_backward(z, net_out)
-        ctx.skip_last, ctx.has_old = bool(skip_last), x_old is not None
-        if want_log_det:
-            return x_new, log_det
-        return x_new, None
+        ctx.save_for_backward(z, net_out, col_mult)
+        return x_new, log_det
 
     @staticmethod
     def backward(ctx, gx, gl):
-        z, net_out = ctx.saved_tensors
+        z, net_out, col_mult = ctx.saved_tensors
         n, d = z.shape
         gx = torch.zeros_like(z) if gx is None else _c(gx)
         gl = None if gl is None else _c(gl)
         dz, dxo = torch.empty_like(z), torch.empty_like(z)
         dnet = torch.empty_like(net_out)
-        L.call("kg_iaf_update_bwd", L.f32(z), L.f32(net_out), L.f32(gx), L.f32(gl), n, d,
-               int(ctx.skip_last), L.f32(dz), L.f32(dnet), L.f32(dxo), L.stream())
-        return dz, dnet, (dxo if ctx.has_old else None), None, None
+        L.call("kg_iaf_update_bwd", L.f32(z), L.f32(net_out), L.f32(gx), L.f32(gl), L.i32(col_mult),
+               n, d, L.f32(dz), L.f32(dnet), L.f32(dxo), L.stream())
+        return dz, dnet, dxo, None, None
 
 
 class ReverseColumnsFn(torch.autograd.Function):

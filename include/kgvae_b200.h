@@ -155,14 +155,18 @@ int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z_var, const
 /* ------------------------------------------------------------------------------------
  * a6  IAF: element update of one MADE pass
  * replaces: MADE.forward body kgvae/flow_network.py:91-96
- * net_out [n, 2d] = (mu | alpha).  x_new[:, j] = z[:, j]*exp(alpha[:, j] + mu[:, j]) for the
- * updated columns; with skip_last the last column keeps x_old (passes 2..n_hidden+2).
+ * net_out [n, 2d] = (mu | alpha).  col_mult [d] int32 = multiplicity of each column in the pass's
+ * index list (flow_network.py:70-77,93): 0 keeps x_old[:, j]; otherwise
+ * x_new[:, j] = z[:, j]*exp(alpha[:, j] + mu[:, j]) and the backward scales the column's gradient by
+ * the multiplicity (autograd's index_put backward feeds every duplicate - the reference lists
+ * column 0 twice in passes 2..n_hidden+2).
  * log_det[n] = sum_j alpha[n, j] (only written when log_det != NULL: the last pass).
  * ---------------------------------------------------------------------------------- */
-int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old, int n, int d,
-                      int skip_last, float* x_new, float* log_det, void* stream);
+int kg_iaf_update_fwd(const float* z, const float* net_out, const float* x_old,
+                      const int32_t* col_mult, int n, int d, float* x_new, float* log_det,
+                      void* stream);
 int kg_iaf_update_bwd(const float* z, const float* net_out, const float* dx_new,
-                      const float* dlog_det /* [n] or NULL */, int n, int d, int skip_last,
+                      const float* dlog_det /* [n] or NULL */, const int32_t* col_mult, int n, int d,
                       float* dz, float* dnet_out, float* dx_old, void* stream);
 /* column reversal (PermuteLayer kgvae/flow_network.py:28-30); its own inverse and backward */
 int kg_reverse_columns(const float* x, int n, int d, float* out, void* stream);

@@ -103,7 +103,12 @@ def test_eval_matches_reference(golden, case):
     # without ties the rank must equal the reference's; fp accumulation order may flip a
     # near-tie (scores closer than 1e-6 relative): allow at most one such query
     assert int((got0[untied] != ref[untied]).sum()) <= 1
-    assert abs(mrr - float(gv["eval_mrr"])) < 2e-3
+    # MRR must lie between the bounds the tie intervals allow (the reference's own value does too)
+    mrr_lo, mrr_hi = float((1.0 / (hi + 1).float()).mean()), float((1.0 / (lo + 1).float()).mean())
+    assert mrr_lo - 1e-6 <= mrr <= mrr_hi + 1e-6
+    assert mrr_lo - 1e-6 <= float(gv["eval_mrr"]) <= mrr_hi + 1e-6
+    if bool(untied.all()):
+        assert abs(mrr - float(gv["eval_mrr"])) < 2e-3
 
 
 def test_fb15k_step_shape_against_oracle():

@@ -87,7 +87,8 @@ def test_made_masks_and_pass_plan(golden):
         assert np.array_equal(made.net[2 * l].mask.numpy(), gv[f"param/net.{2 * l}.mask"])
     for i, deg in enumerate(made.m):
         assert np.array_equal(deg.numpy(), gv[f"deg/{i}"])
-    assert made._covers_last == [True] + [False] * (nh + 1) + [True]
+    mid = [2] + [1] * (D - 2) + [0]
+    assert [m.tolist() for m in made._col_mult] == [[1] * D] + [mid] * (nh + 1) + [[1] * D]
 
 
 def test_synthetic_shapes():
