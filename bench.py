@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the GCN-VAE link-prediction hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the CPU oracle port, host cores
+
+Workload (config.workload = "fb15k237-full", BASELINE.json configs[1]): synthetic FB15k-237-shaped
+KG (14 541 entities, 237 relations, 272 115 train triples), h=500, 100 blocks, 10-component MoG
+prior, dropout 0.2, negative rate 10.  One STEP = one full-graph training step through the
+reference-shaped API: every train triple is sampled (graph_batch_size = 272 115), half become the
+message-passing graph (272 114 directed edges), all 2 993 265 scored triplets go through DistMult +
+BCE; timed region = graph index build + forward + loss + backward + grad clip + Adam.
+`value` = directed message-passing edges processed per second with inputs resident in HBM;
+`e2e` = the same step with every input copied from pinned host memory and the loss read back.
+`eval` = all-entity rank evaluation (both perturbation directions) of the 20 466 test triples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train edges/s (fwd+bwd) + eval triples/s, FB15k-237 shape, 1/2/4/8 B200"
+H, BASES, MOG_K, DROPOUT, NEG = 500, 100, 10, 0.2, 10
+REG, KL = 0.01, 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# shared: synthetic inputs produced by the reference's own sampler path (host, numpy)
+# ------------------------------------------------------------------------------------------------
+def sample_step(utils_mod, data, batch, seed):
+    np.random.seed(seed)
+    return utils_mod.generate_sampled_graph_and_labels(data.train, batch, 0.5, data.num_rels, None, None,
+                                                       NEG, "uniform")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=100, log=None):
+    """Times oracle/kgvae_oracle.py (the CPU restatement of the reference path) on a bounded
+    sample: the reference's default step (20 000 sampled edges of the same graph, h=500, 100
+    blocks) and `eval_queries` test triples in both directions against all 14 541 entities."""
+    from oracle import kgvae_oracle as O
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kg_datasets", os.path.join(ROOT, "gcn-vae_b200", "datasets.py"))
+    datasets = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(datasets)          # synthetic triples only; no kernels, no package import
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    data = datasets.synthetic_kg("FB15k-237", seed=0)
+    params = O.init_params(data.num_nodes, H, data.num_rels, BASES, MOG_K, n_flows, seed=0)
+    for p in params.values():
+        p.requires_grad_(True)
+    times = []
+    for it in range(warmup + steps):
+        np.random.seed(100 + it)
+        graph, node_id, samples, labels = O.generate_sampled_graph_and_labels(
+            data.train, sample_edges, 0.5, data.num_rels, NEG)
+        etype = graph["etype"]
+        n = len(node_id)
+        eps = torch.randn(n, H)
+        masks = tuple((torch.rand(n, w) < 1 - DROPOUT).float() / (1 - DROPOUT) for w in (H, 2 * H))
+        t0 = time.perf_counter()
+        enc = O.kgvae_encode(params, graph, node_id, eps, BASES, n_flows, masks)
+        out = O.kgvae_loss(params, enc, samples, labels, REG, KL, n_flows)
+        out["loss"].backward()
+        dt = time.perf_counter() - t0
+        for p in params.values():
+            p.grad = None
+        if it >= warmup:
+            times.append(dt)
+        if log:
+            log(f"[cpu oracle] step {it}: {dt:.2f}s ({len(etype)} edges, {len(labels)} triplets)")
+    edges = sample_edges  # 2 * (sample_edges / 2) directed edges
+    train_rate = edges / (sum(times) / len(times))
+    # evaluation sample
+    with torch.no_grad():
+        emb = params["encoder.input_layer.embedding.weight"].detach()
+        t = torch.from_numpy(data.test[:eval_queries])
+        t0 = time.perf_counter()
+        O.calc_mrr(emb, params["w_relation"].detach(), t, eval_bz=eval_queries, policy="reference")
+        eval_dt = time.perf_counter() - t0
+    return {"train_edges_per_s": train_rate, "step_s": sum(times) / len(times), "cores": cores,
+            "eval_triples_per_s": eval_queries / eval_dt,
+            "sample": f"reference default step: {sample_edges} sampled edges ({sample_edges * (NEG + 1)} scored "
+                      f"triplets) of the same graph, fwd+loss+bwd, {len(times)} timed steps; eval: "
+                      f"{eval_queries} test triples x 2 directions x 14541 candidates"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_oracle_rates(args.steps, args.warmup, args.n_flows, log=lambda m: print(m, file=sys.stderr))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["train_edges_per_s"], "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fb15k237-full", "n_flows": args.n_flows, "h": H, "bases": BASES},
+        "cpu_baseline": {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"],
+                         "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["train_edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "eval": {"value": r["eval_triples_per_s"], "unit": "triples/s"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(tag, shp):
+    """Algorithmic (compulsory) HBM bytes of one launch of the named op; DESIGN.md section 4."""
+    N, E, S, R2, h = shp["N"], shp["E"], shp["S"], shp["R2"], H
+    if tag.startswith("kg_bdd_aggregate_fwd") or tag.startswith("kg_bdd_aggregate_bwd_dx"):
+        si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
+        fin, fout = (si, so) if "fwd" in tag else (so, si)
+        return E * (4 * BASES * fin + 16) + 4 * N * BASES * fout + 4 * R2 * BASES * si * so
+    if tag.startswith("kg_bdd_aggregate_bwd_dw"):
+        si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
+        return E * (4 * BASES * (si + so) + 16) + 4 * R2 * BASES * si * so
+    if tag == "kg_distmult_score":
+        return S * (3 * 4 * h + 12 + 4)
+    if tag == "kg_distmult_bwd_dz":
+        return 2 * S * (2 * 4 * h + 16 + 4) + 4 * N * h
+    if tag == "kg_distmult_bwd_dw":
+        return S * (2 * 4 * h + 12 + 8) + 4 * shp["R"] * h
+    return None
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    import gcn_vae_b200 as K
+    from gcn_vae_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+
+    data = K.datasets.synthetic_kg("FB15k-237", seed=0)
+    batch = len(data.train) if args.workload == "fb15k237-full" else 20000
+    torch.manual_seed(0)
+    model = K.LinkPredict(K.KGVAE, data.num_nodes, H, data.num_rels, num_bases=BASES, dropout=DROPOUT,
+                          use_cuda=True, reg_param=REG, kl_param=KL, k=MOG_K, n_flows=args.n_flows).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    # ---- the step's inputs: the reference's own host sampler (weak scaling: one sample per rank) --
+    t0 = time.perf_counter()
+    g, node_id, etype, node_norm, samples, labels = sample_step(K.utils, data, batch, seed=rank)
+    log(f"host sampling: {time.perf_counter() - t0:.2f}s; nodes={len(node_id)} edges={len(etype)} triplets={len(labels)}")
+    E, S, N = len(etype), len(labels), len(node_id)
+    pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory()
+    host = {"node_id": pin(node_id, torch.int32), "src": pin(g._src, torch.int32), "dst": pin(g._dst, torch.int32),
+            "etype": pin(etype, torch.int32), "norm": pin(node_norm[g._dst].reshape(-1, 1), torch.float32),
+            "samples": pin(samples, torch.int32), "labels": pin(labels, torch.float32)}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def make_graph(t):
+        gr = K.Graph()
+        gr._n, gr._src, gr._dst = N, g._src, g._dst
+        gr._dev_edges[dev] = (t["src"], t["dst"])
+        return gr
+
+    def step(t):
+        gr = make_graph(t)                                  # fresh graph: the index is rebuilt
+        opt.zero_grad(set_to_none=True)
+        embed = model(gr, t["node_id"].view(-1, 1), t["etype"], t["norm"])
+        loss, _, _, _ = model.get_loss(gr, embed, t["samples"], t["labels"])
+        loss.backward()
+        if world > 1:                                       # replicas: average gradients over NVLink
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    def e2e_step():
+        t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(step(t))                               # D2H read of the loss
+
+    def timed(fn, n_steps):
+        total = 0.0
+        for _ in range(n_steps):
+            flush_buf.fill_(1)                              # L2 flush, outside the timed events
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            total += a.elapsed_time(b)
+        return total
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    model.train()
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sync_all()
+    clocks = ClockSampler(local)
+    L.launches = 0
+    L.profile = {}
+    ms_dev = max_over_ranks(timed(lambda: step(resident), args.steps))
+    launches = L.launches
+    prof, L.profile = L.profile, None
+    sync_all()
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    ms_e2e = max_over_ranks(timed(e2e_step, args.steps))
+    sync_all()
+
+    # ---- evaluation: encoder on the test graph + all-entity ranks -----------------------------
+    model.eval()
+    test = torch.from_numpy(data.test)
+    tg, trel, tnorm = K.utils.build_test_graph(data.num_nodes, data.num_rels, test)
+    t_ids = torch.arange(data.num_nodes, dtype=torch.int32, device=dev).view(-1, 1)
+    t_rel = torch.from_numpy(trel).to(torch.int32).to(dev)
+    t_norm = torch.from_numpy(tnorm[tg._dst].reshape(-1, 1).astype(np.float32)).to(dev)
+    test_host = test.to(torch.int32).pin_memory()
+    test_dev = test_host.to(dev)
+    lo, hi = (data.num_nodes * rank) // world, (data.num_nodes * (rank + 1)) // world
+
+    def eval_ranks(tt):
+        with torch.no_grad():
+            emb = model(tg, t_ids, t_rel, t_norm)
+            s, r, o = tt[:, 0].contiguous(), tt[:, 1].contiguous(), tt[:, 2].contiguous()
+            shift = model._flow_shift()
+            rk = torch.cat([K.ops.distmult_rank(emb, model.w_relation, o, r, s, shift=shift, cand_range=(lo, hi)),
+                            K.ops.distmult_rank(emb, model.w_relation, s, r, o, shift=shift, cand_range=(lo, hi))])
+            if world > 1:                                   # entity-sharded counts add up
+                dist.all_reduce(rk)
+            return rk
+
+    for _ in range(3):
+        eval_ranks(test_dev)
+    sync_all()
+    L.profile = {}
+    ms_eval = max_over_ranks(timed(lambda: eval_ranks(test_dev), args.steps))
+    eval_prof, L.profile = L.profile, None
+    ms_eval_e2e = max_over_ranks(timed(lambda: eval_ranks(test_host.to(dev, non_blocking=True)).cpu(), args.steps))
+    sync_all()
+    clock_info = clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    shp = {"N": N, "E": E, "S": S, "R2": 2 * data.num_rels, "R": data.num_rels}
+    op_ms = {tag: sum(a.elapsed_time(b) for a, b in evs) for tag, evs in prof.items()}
+    op_n = {tag: len(evs) for tag, evs in prof.items()}
+    total_ops = sum(op_ms.values())
+    top = sorted(op_ms.items(), key=lambda kv: -kv[1])
+    for tag, ms in top[:14]:
+        log(f"  {tag:44s} {ms / args.steps:8.3f} ms/step  {100 * ms / total_ops:5.1f}%  x{op_n[tag] // args.steps}")
+    pk = peaks()
+    roof = None
+    for tag, ms in top:
+        ab = algorithmic_bytes(tag, shp)
+        if ab is not None:
+            per_launch_ms = ms / op_n[tag]
+            ach = ab / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": tag, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": ab,
+                    "share_of_step": ms / total_ops,
+                    "regime": "L2-resident gathers (z, h are 29 MB): algorithmic GB/s can exceed HBM peak"}
+            break
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if roof and os.path.exists(traffic_file):
+        roof["traffic"] = json.load(open(traffic_file)).get(roof["kernel"])
+    eval_top = sorted(((t, sum(a.elapsed_time(b) for a, b in e) / len(e)) for t, e in eval_prof.items()),
+                      key=lambda kv: -kv[1])
+    T = len(data.test)
+    rank_ms = dict(eval_top).get("kg_distmult_rank")
+    eval_roof = None
+    if rank_ms:
+        flops = 2.0 * T * (hi - lo) * H
+        eval_roof = {"kernel": "kg_distmult_rank", "bound": "tensor", "achieved": flops / (rank_ms * 1e-3) / 1e12,
+                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": flops / (rank_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+                     "note": "fp32 FMA build (parity mode); peak is the measured bf16 tensor figure"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_rates(2, 1, args.n_flows, log=log)
+        cpu = {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"], "eval_triples_per_s": r["eval_triples_per_s"]}
+
+    total_edges = E * world * args.steps
+    line = {
+        "metric": METRIC, "value": total_edges / (ms_dev * 1e-3), "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "entities": data.num_nodes, "relations": data.num_rels,
+                   "train_triples": len(data.train), "graph_edges": E, "scored_triplets": S, "nodes": N,
+                   "h": H, "bases": BASES, "mog_k": MOG_K, "n_flows": args.n_flows, "negative_rate": NEG,
+                   "parallelism": f"replicas x{world} (grad all-reduce), eval entity-sharded",
+                   "timed": "graph index + fwd + loss + bwd + clip + Adam; per-step CUDA events",
+                   "l2": "flushed between steps (256 MiB write)"},
+        "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "eval": {"value": T * args.steps / (ms_eval * 1e-3), "unit": "triples/s", "test_triples": T,
+                 "candidates": data.num_nodes, "ms": ms_eval / args.steps, "setting": "raw, both directions",
+                 "e2e_value": T * args.steps / (ms_eval_e2e * 1e-3), "roofline": eval_roof},
+        "scored_triplets_per_s": S * world * args.steps / (ms_dev * 1e-3),
+        "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fb15k237-full", choices=["fb15k237-full", "fb15k237-step"])
+    ap.add_argument("--n-flows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

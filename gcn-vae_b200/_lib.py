@@ -70,12 +70,29 @@ def lib():
     return _lib
 
 
-def call(name, *args):
+# kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
+KERNELS_PER_CALL = {
+    "kg_graph_build": 26, "kg_graph_index": 18, "kg_triplet_index": 11, "kg_colsum": 2,
+    "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
+}
+launches = 0          # running count of kernels launched through this binding
+profile = None        # when a dict: name -> [(start_event, end_event), ...] per call
+
+
+def call(name, *args, tag=None):
     """Invoke an int-returning entry point; raise RuntimeError with kg_last_error() on failure."""
+    global launches
     handle = lib()
+    if profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(handle, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {handle.kg_last_error().decode()}")
+    launches += KERNELS_PER_CALL.get(name, 1)
+    if profile is not None:
+        ev1.record()
+        profile.setdefault(tag or name, []).append((ev0, ev1))
 
 
 def ptr(t, dtype=None):

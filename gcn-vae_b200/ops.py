@@ -88,7 +88,8 @@ def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, addend=None, relu=F
     K = a.shape[0] if trans_a else a.shape[1]
     L.call("kg_gemm_f32", L.f32(a), a.shape[1], int(trans_a), L.f32(b), b.shape[1], int(trans_b),
            L.f32(out), out.shape[1], M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask),
-           int(accumulate), L.stream())
+           int(accumulate), L.stream(),
+           tag=f"kg_gemm_f32[{M}x{N}x{K},{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]")
     return out
 
 
@@ -165,7 +166,7 @@ class BddConvFn(torch.autograd.Function):
                L.f32(w_bwd), L.stream())
         agg = torch.empty((n, out_feat), dtype=torch.float32, device=dev)
         L.call("kg_bdd_aggregate_fwd", L.f32(x), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), L.f32(w_fwd),
-               n, num_bases, si, so, L.f32(agg), L.stream())
+               n, num_bases, si, so, L.f32(agg), L.stream(), tag=f"kg_bdd_aggregate_fwd[{si}x{so}]")
         out = torch.empty_like(agg)
         bias = None if h_bias is None else _c(h_bias)
         mask = None if drop_mask is None else _c(drop_mask)
@@ -192,13 +193,13 @@ class BddConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             L.call("kg_bdd_aggregate_bwd_dx", L.f32(gpre), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
-                   L.f32(w_bwd), n, B, si, so, L.f32(dx), L.stream())
+                   L.f32(w_bwd), n, B, si, so, L.f32(dx), L.stream(), tag=f"kg_bdd_aggregate_bwd_dx[{si}x{so}]")
             if loop_weight is not None:
                 gemm(gpre, loop_weight, dx, trans_b=True, accumulate=True)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(weight)
             L.call("kg_bdd_aggregate_bwd_dw", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges,
-                   B, si, so, L.f32(dw), L.stream())
+                   B, si, so, L.f32(dw), L.stream(), tag=f"kg_bdd_aggregate_bwd_dw[{si}x{so}]")
         if loop_weight is not None and ctx.needs_input_grad[2]:
             dloop = torch.empty_like(loop_weight)
             gemm(x, gpre, dloop, trans_a=True)
