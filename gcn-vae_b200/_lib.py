@@ -48,7 +48,8 @@ _SIGNATURES = {
     "kg_triplet_index": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "kg_distmult_bwd_dz": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
-    "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "kg_distmult_rank_workspace_bytes": (_Z, [_I, _I, _I]),
+    "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _Z, _P, _P, _P]),
 }
 
 _lib = None

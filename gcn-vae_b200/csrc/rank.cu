@@ -1,129 +1,465 @@
-// a10: all-entity rank evaluation.
+// a10: all-entity rank evaluation on the 5th-generation tensor cores.
 // Replaces utils.perturb_and_get_rank + sort_and_rank (reference kgvae/utils.py:180-221): the
 // reference materialises a D x E x V outer-product tensor (11.6 GB per 400-query batch at
 // FB15k-237 shape), reduces it to an E x V score matrix, applies sigmoid and fully sorts every
-// row to find one position.  Here the score tile lives only in registers: the GEMM epilogue
-// compares each candidate's score with the target's and counts, so only int32 ranks[M] reach HBM.
+// row to find one position.  Here the M x V score matrix only ever exists as 128 x 256 fp32
+// tiles in tensor memory; the epilogue counts, per query, the candidates that beat the target,
+// so only int32 ranks[M] reach HBM.
 //
-// Tie policy: rank = #{score > target} + #{score == target and id < target id}.
-// Comparing logits instead of sigmoid(logits) refines the reference's order (sigmoid is
-// monotone), so the result always lies inside the reference's tie interval and is identical
-// when the reference has no ties.  The target's own score is recomputed by score_chain() with
-// the same fmaf order as the tile kernel, hence bit-identical to the tile's value.
-#include "gemm_tile.cuh"
+// Definition of the score (the "canonical" fp32 value every comparison is decided on):
+//   q_i = emb[a_i] * w[r_i]                        (one fp32 multiply per element, utils.py:200)
+//   dot(q, e) = butterfly_sum_l( chain_{k = l, l+32, ...} fmaf(q[k], e[k], .) )   (lane l of a warp)
+//   score_ij = dot(q_i, emb[j]) + shift            (utils.py:204-207)
+//   rank_i = #{j : score_ij > score_i,b_i} + #{j < b_i : score_ij == score_i,b_i}      
+// Comparing logits instead of sigmoid(logits) refines the reference's order (sigmoid is monotone),
+// so the result always lies inside the reference's tie interval and equals it when the
+// reference has no ties.
+//
+// How the tensor cores are used without giving up the fp32 decision: both operands are split
+// into two fp16 terms (x * 2^s = hi + lo, s a per-row power of two), and the tile accumulates
+// lo*hi + hi*lo + hi*hi in fp32 (tcgen05.mma kind::f16, operands TMA-staged in 128B-swizzled
+// shared memory, accumulators double-buffered in TMEM).  The epilogue treats that value as a
+// FILTER: a candidate whose tensor-core score differs from the target's canonical score by more
+// than  mu * |q| * |e| + eps  is decided immediately; the few that fall inside the band
+// (about 5e-4 of all pairs on Gaussian data, and every exact tie) are re-scored with dot()
+// above by the same warp.  mu = 2^-15 is > 10x the worst deviation the split product showed
+// against dot() (tests/test_gpu_ops.py::test_rank_filter_margin).
+#include "tc05.cuh"
 
-using namespace kg_gemm;
+using namespace tc05;
 
-__global__ void build_queries(const float* __restrict__ emb, const float* __restrict__ w,
-                              const int* __restrict__ a, const int* __restrict__ r, int M, int h,
-                              float* __restrict__ q) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)M * h) return;
-  int i = (int)(idx / h), d = (int)(idx % h);
-  q[idx] = emb[(size_t)a[i] * h + d] * w[(size_t)r[i] * h + d];   // utils.py:200
-}
+namespace {
 
-// same accumulation order as kg_gemm::mainloop: one fmaf chain over ascending k
-__device__ __forceinline__ float score_chain(const float* __restrict__ q, const float* __restrict__ e, int h) {
+constexpr int BM = 128, BN = 256, BK = 64;           // CTA tile; BK fp16 elements = one 128-byte row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 128 + 2 * BN * 8 + 4 * (BN / 32) * 32 * 4;
+constexpr float kMu = 3.0517578125e-05f;               // 2^-15
+constexpr float kEps = 4.76837158203125e-07f;         // 2^-21
+
+__device__ __forceinline__ float warp_dot(const float* __restrict__ q, const float* __restrict__ e, int h,
+                                          int lane) {
   float acc = 0.f;
-  for (int k = 0; k < h; ++k) acc = fmaf(q[k], e[k], acc);
+  for (int k = lane; k < h; k += 32) acc = fmaf(__ldg(q + k), __ldg(e + k), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   return acc;
 }
 
-__global__ void target_scores(const float* __restrict__ q, const float* __restrict__ emb,
-                              const int* __restrict__ b, int M, int h, const float* __restrict__ shift_p,
-                              float* __restrict__ ts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  const float shift = shift_p ? __ldg(shift_p) : 0.f;
-  ts[i] = score_chain(q + (size_t)i * h, emb + (size_t)b[i] * h, h) + shift;   // utils.py:206-207
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
-rank_count_kernel(TileLoader<true> la, TileLoader<true> lb, int K, const float* __restrict__ ts,
-                  const int* __restrict__ tgt, const float* __restrict__ shift_p, int M, int cand_begin,
-                  int cand_end, int* __restrict__ ranks) {
-  __shared__ Smem sm;
-  const float shift = shift_p ? __ldg(shift_p) : 0.f;
-  const int m0 = blockIdx.y * BM, n0 = cand_begin + blockIdx.x * BN;
-  float acc[8][8];
-  mainloop<true, true>(la, lb, m0, n0, 0, K, sm, acc);
+// power-of-two scale that puts max|x| into [2^14, 2^15)
+__device__ __forceinline__ float split_scale(float amax) {
+  if (!(amax > 0.f)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  e = 15 - e;
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  return ldexpf(1.f, e);
+}
 
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+__device__ __forceinline__ void split_store(float x, float s, __half* hi_p, __half* lo_p) {
+  const float xs = x * s;
+  const __half hi = __float2half_rn(xs);
+  *hi_p = hi;
+  *lo_p = __float2half_rn(xs - __half2float(hi));
+}
+
+// one warp per candidate row n (shard-relative): fp16 split of emb[cand_begin + n] and column record
+__global__ void __launch_bounds__(256)
+entity_prep(const float* __restrict__ emb, int cand_begin, int n_cand, int n_cols, int h, int Kp,
+            __half* __restrict__ bcat, float2* __restrict__ colp) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= n_cols) return;
+  if (n >= n_cand) {                                    // tile overhang: masked out
+    if (lane == 0) colp[n] = make_float2(0.f, __int_as_float(0x7fc00000));
+    return;
+  }
+  const float* e = emb + (size_t)(cand_begin + n) * h;
+  float amax = 0.f, ss = 0.f;
+  for (int k = lane; k < h; k += 32) {
+    const float x = __ldg(e + k);
+    amax = fmaxf(amax, fabsf(x));
+    ss = fmaf(x, x, ss);
+  }
+  amax = warp_max(amax);
+  ss = kg_warp_sum(ss);
+  const float s = split_scale(amax);
+  __half* row = bcat + (size_t)n * 2 * Kp;
+  for (int k = lane; k < Kp; k += 32) {
+    if (k < h) split_store(__ldg(e + k), s, row + k, row + Kp + k);
+    else { row[k] = __float2half_rn(0.f); row[Kp + k] = __float2half_rn(0.f); }
+  }
+  if (lane == 0) colp[n] = make_float2(1.f / s, sqrtf(ss) * 1.000002f);
+}
+
+// one warp per query: canonical q (fp32), its fp16 split, the target's canonical score and the
+// row record {A, B, C, t}:  candidate j is decided by  d = sq*(q.e_j)_tc - A  against  B*|e_j| + C
+__global__ void __launch_bounds__(256)
+query_prep(const float* __restrict__ emb, const float* __restrict__ w, const int* __restrict__ a,
+           const int* __restrict__ r, const int* __restrict__ b, int M, int h, int Kp,
+           const float* __restrict__ shift_p, float* __restrict__ q32, __half* __restrict__ acat,
+           float4* __restrict__ rowp, float* __restrict__ sqv) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float shift = shift_p ? __ldg(shift_p) : 0.f;
+  const float* ea = emb + (size_t)__ldg(a + m) * h;
+  const float* wr = w + (size_t)__ldg(r + m) * h;
+  const float* eb = emb + (size_t)__ldg(b + m) * h;
+  float* q = q32 + (size_t)m * h;
+  float amax = 0.f, ss = 0.f, acc = 0.f;
+  for (int k = lane; k < h; k += 32) {
+    const float x = __ldg(ea + k) * __ldg(wr + k);       // utils.py:200
+    q[k] = x;
+    amax = fmaxf(amax, fabsf(x));
+    ss = fmaf(x, x, ss);
+    acc = fmaf(x, __ldg(eb + k), acc);                   // same chain as warp_dot
+  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + tile_row(ty, i);
-    int cnt = 0;
-    if (m < M) {
-      const float t = __ldg(ts + m);
-      const int tid = __ldg(tgt + m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = n0 + tile_col(tx, j);
-        const float s = acc[i][j] + shift;
-        if (n < cand_end && (s > t || (s == t && n < tid))) ++cnt;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  amax = warp_max(amax);
+  ss = kg_warp_sum(ss);
+  const float s = split_scale(amax);
+  __half* row = acat + (size_t)m * 2 * Kp;
+  for (int k = lane; k < Kp; k += 32) {
+    if (k < h) split_store(q[k], s, row + k, row + Kp + k);
+    else { row[k] = __float2half_rn(0.f); row[Kp + k] = __float2half_rn(0.f); }
+  }
+  if (lane == 0) {
+    const float t = acc + shift;                         // utils.py:206-207
+    rowp[m] = make_float4(s * (t - shift), s * kMu * sqrtf(ss) * 1.000002f,
+                          s * (kEps * (fabsf(shift) + fabsf(t)) + 1e-37f), t);
+    sqv[m] = s;
+  }
+}
+
+struct RankArgs {
+  const float* q32;
+  const float* emb;
+  const float4* rowp;
+  const float2* colp;
+  const int* tgt;
+  const float* shift;
+  int* ranks;
+  const float* sqv;      // per-query scale (only read when dump != nullptr)
+  float* dump;           // test hook: tensor-core scores [M, n_cand] (nullptr in production)
+  int M, h, Kp, cand_begin, n_cand, m_tiles, n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, RankArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                     // TMA -> MMA
+  uint64_t* empty = bars + STAGES;           // MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;       // MMA -> epilogue   [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // epilogue -> MMA   [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float2* colp_s = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 128);          // [2][BN]
+  uint32_t* amb_s = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 128 + 2 * BN * 8);  // [4][BN/32][32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull + i, 1);
+      mbar_init(tempty + i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total = p.m_tiles * p.n_tiles;
+  const int k_steps = p.Kp / BK;             // per product term
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+        for (int term = 0; term < 3; ++term) {
+          // small terms first: lo*hi, hi*lo, then hi*hi   (hi at column 0, lo at column Kp)
+          const int a_off = term == 0 ? p.Kp : 0, b_off = term == 1 ? p.Kp : 0;
+          for (int ks = 0; ks < k_steps; ++ks) {
+            mbar_wait(empty + stage, phase ^ 1);
+            uint8_t* st = smem + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
+            tma_load_2d(st, &tm_a, full + stage, a_off + ks * BK, m0);
+            tma_load_2d(st + A_BYTES, &tm_b, full + stage, b_off + ks * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
-    // the 16 threads that share this row are one half-warp
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty + buf, ((it >> 1) & 1) ^ 1);
+        fence_after_thread_sync();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int ks = 0; ks < 3 * k_steps; ++ks) {
+          mbar_wait(full + stage, phase);
+          fence_after_thread_sync();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = smem_desc_k_sw128(sa), db = smem_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (tx == 0 && m < M && cnt) atomicAdd(ranks + m, cnt);
+          for (int k = 0; k < BK / 16; ++k)   // 16 fp16 = 32 bytes per MMA: +2 in the (>>4) address field
+            mma_f16_ss(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+          mma_commit(empty + stage);          // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tfull + buf);              // accumulator complete
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (warps 2..5)
+    const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad + 32)
+    const int etid = threadIdx.x - 64;        // 0..127 among the epilogue threads
+    const float shift = p.shift ? __ldg(p.shift) : 0.f;
+    uint32_t* my_amb = amb_s + (quad * (BN / 32)) * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      const int m = m0 + quad * 32 + lane;
+      // column records of this tile -> shared memory (double-buffered: one barrier per tile)
+      float4* cs4 = reinterpret_cast<float4*>(colp_s + buf * BN);
+      cs4[etid] = __ldg(reinterpret_cast<const float4*>(p.colp + n0) + etid);
+      float4 rp = make_float4(0.f, __int_as_float(0x7fc00000), 0.f, 0.f);
+      int tg = -1;
+      if (m < p.M) {
+        rp = __ldg(p.rowp + m);
+        tg = __ldg(p.tgt + m);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull + buf, (it >> 1) & 1);
+      fence_after_thread_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+      int cnt = 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v0);
+        tmem_ld_32x32b_x32(taddr + c * 32 + 32, v1);
+        tmem_ld_wait();
+        const float4* cp = cs4 + c * 16;
+        uint32_t mask0 = 0, mask1 = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float4 ca = cp[j >> 1], cb = cp[16 + (j >> 1)];   // {1/se, |e|} x 2 columns (broadcast)
+          const float d0 = fmaf(__uint_as_float(v0[j]), ca.x, -rp.x), c0 = fmaf(rp.y, ca.y, rp.z);
+          const float d1 = fmaf(__uint_as_float(v0[j + 1]), ca.z, -rp.x), c1 = fmaf(rp.y, ca.w, rp.z);
+          const float d2 = fmaf(__uint_as_float(v1[j]), cb.x, -rp.x), c2 = fmaf(rp.y, cb.y, rp.z);
+          const float d3 = fmaf(__uint_as_float(v1[j + 1]), cb.z, -rp.x), c3 = fmaf(rp.y, cb.w, rp.z);
+          cnt += (d0 > c0) + (d1 > c1) + (d2 > c2) + (d3 > c3);
+          if (fabsf(d0) <= c0) mask0 |= 1u << j;
+          if (fabsf(d1) <= c1) mask0 |= 2u << j;
+          if (fabsf(d2) <= c2) mask1 |= 1u << j;
+          if (fabsf(d3) <= c3) mask1 |= 2u << j;
+        }
+        my_amb[c * 32] = mask0;
+        my_amb[(c + 1) * 32] = mask1;
+        if (p.dump && m < p.M) {                           // test hook: the filter's view of the scores
+          const float inv_sq = 1.f / __ldg(p.sqv + m);
+          for (int j = 0; j < 64; ++j) {
+            const int n = n0 + c * 32 + j;
+            const float acc = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+            if (n < p.n_cand) p.dump[(size_t)m * p.n_cand + n] = acc * __ldg(&p.colp[n].x) * inv_sq;
+          }
+        }
+      }
+      fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + buf);            // TMEM buffer may be overwritten
+      // undecided pairs: canonical fp32 score, whole warp per pair
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const uint32_t mine = my_amb[c * 32];
+        unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+        while (any) {
+          const int src = __ffs(any) - 1;
+          any &= any - 1;
+          uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
+          const int mr = __shfl_sync(0xffffffffu, m, src);
+          const float t = __shfl_sync(0xffffffffu, rp.w, src);
+          const int tgs = __shfl_sync(0xffffffffu, tg, src);
+          const float* qrow = p.q32 + (size_t)mr * p.h;
+          int extra = 0;
+          if (p.h <= 512) {
+            float qv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qv[i] = lane + 32 * i < p.h ? __ldg(qrow + lane + 32 * i) : 0.f;
+            while (bits) {
+              const int j = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int n = p.cand_begin + n0 + c * 32 + j;
+              const float* erow = p.emb + (size_t)n * p.h;
+              float ev[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ev[i] = lane + 32 * i < p.h ? __ldg(erow + lane + 32 * i) : 0.f;
+              float acc = 0.f;                              // same chain as warp_dot (zero terms are exact no-ops)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc = fmaf(qv[i], ev[i], acc);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+              const float sc = acc + shift;
+              extra += (sc > t || (sc == t && n < tgs)) ? 1 : 0;
+            }
+          } else {
+            while (bits) {
+              const int j = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int n = p.cand_begin + n0 + c * 32 + j;
+              const float sc = warp_dot(qrow, p.emb + (size_t)n * p.h, p.h, lane) + shift;
+              extra += (sc > t || (sc == t && n < tgs)) ? 1 : 0;
+            }
+          }
+          if (lane == src) cnt += extra;
+        }
+      }
+      if (m < p.M && cnt) atomicAdd(p.ranks + m, cnt);
+    }
+  }
+
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_thread_sync();
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
-// filtered setting: take back every known-true candidate that was counted
-__global__ void filter_correction(const float* __restrict__ q, const float* __restrict__ emb,
-                                  const float* __restrict__ ts, const int* __restrict__ tgt,
-                                  const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
-                                  int M, int h, const float* __restrict__ shift_p, int cand_begin,
-                                  int cand_end, int* __restrict__ ranks) {
+// filtered setting: take back every known-true candidate that was counted (warp per query)
+__global__ void __launch_bounds__(256)
+filter_correction(const float* __restrict__ q32, const float* __restrict__ emb, const float4* __restrict__ rowp,
+                  const int* __restrict__ tgt, const int* __restrict__ filt_ptr,
+                  const int* __restrict__ filt_idx, int M, int h, const float* __restrict__ shift_p,
+                  int cand_begin, int cand_end, int* __restrict__ ranks) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
   const float shift = shift_p ? __ldg(shift_p) : 0.f;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const float t = ts[warp];
-  const int tid = tgt[warp];
+  const float t = __ldg(&rowp[m].w);
+  const int tid = __ldg(tgt + m);
   int cnt = 0;
-  for (int p = filt_ptr[warp] + lane; p < filt_ptr[warp + 1]; p += 32) {
-    const int j = filt_idx[p];
+  for (int pidx = __ldg(filt_ptr + m); pidx < __ldg(filt_ptr + m + 1); ++pidx) {
+    const int j = __ldg(filt_idx + pidx);
     if (j == tid || j < cand_begin || j >= cand_end) continue;
-    const float s = score_chain(q + (size_t)warp * h, emb + (size_t)j * h, h) + shift;
-    if (s > t || (s == t && j < tid)) ++cnt;
+    const float s = warp_dot(q32 + (size_t)m * h, emb + (size_t)j * h, h, lane) + shift;
+    cnt += (s > t || (s == t && j < tid)) ? 1 : 0;
   }
-  cnt = kg_warp_sum_int(cnt);
-  if (lane == 0 && cnt) atomicSub(ranks + warp, cnt);
+  if (lane == 0 && cnt) atomicSub(ranks + m, cnt);
+}
+
+struct Layout {
+  size_t q32, acat, bcat, rowp, colp, sqv, total;
+  int Kp, n_tiles, m_tiles;
+};
+
+Layout layout(int M, int n_cand, int h) {
+  Layout L;
+  L.Kp = kg_div_up(h, BK) * BK;
+  L.m_tiles = kg_div_up(M, BM);
+  L.n_tiles = kg_div_up(n_cand, BN);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += kg_align_up(bytes, 1024); return o; };
+  L.q32 = take((size_t)M * h * sizeof(float));
+  L.acat = take((size_t)M * 2 * L.Kp * sizeof(__half));
+  L.bcat = take((size_t)(n_cand > 0 ? n_cand : 1) * 2 * L.Kp * sizeof(__half));
+  L.rowp = take((size_t)M * sizeof(float4));
+  L.colp = take((size_t)(L.n_tiles > 0 ? L.n_tiles : 1) * BN * sizeof(float2));
+  L.sqv = take((size_t)M * sizeof(float));
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+extern "C" size_t kg_distmult_rank_workspace_bytes(int n_queries, int n_candidates, int h) {
+  if (n_queries <= 0 || h <= 0) return 1024;
+  return layout(n_queries, n_candidates > 0 ? n_candidates : 0, h).total + 1024;
 }
 
 extern "C" int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const int32_t* r,
                                 const int32_t* b, int n_queries, int n_entities, int h, const float* shift,
                                 int cand_begin, int cand_end, const int32_t* filt_ptr,
-                                const int32_t* filt_idx, float* queries, float* tscore,
-                                int32_t* ranks, void* stream) {
+                                const int32_t* filt_idx, void* workspace, size_t workspace_bytes,
+                                int32_t* ranks, float* tc_scores, void* stream) {
   KG_REQUIRE(n_queries >= 0 && n_entities > 0 && h > 0, "rank: bad sizes");
   KG_REQUIRE(0 <= cand_begin && cand_begin <= cand_end && cand_end <= n_entities, "rank: bad candidate shard");
   KG_REQUIRE((filt_ptr == nullptr) == (filt_idx == nullptr), "rank: filter needs both ptr and idx");
   cudaStream_t st = kg_stream(stream);
-  const int M = n_queries;
+  const int M = n_queries, n_cand = cand_end - cand_begin;
   if (M == 0) return KG_OK;
   KG_CUDA(cudaMemsetAsync(ranks, 0, sizeof(int) * M, st));
-  build_queries<<<kg_div_up((long long)M * h, 256), 256, 0, st>>>(emb, w, a, r, M, h, queries);
+  const Layout L = layout(M, n_cand, h);
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
+  if (!workspace || base + L.total > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes)
+    return kg_fail(KG_ERR_WORKSPACE, "rank: workspace too small (%zu needed)", L.total + 1024);
+  char* ws = reinterpret_cast<char*>(base);
+  float* q32 = reinterpret_cast<float*>(ws + L.q32);
+  __half* acat = reinterpret_cast<__half*>(ws + L.acat);
+  __half* bcat = reinterpret_cast<__half*>(ws + L.bcat);
+  float4* rowp = reinterpret_cast<float4*>(ws + L.rowp);
+  float2* colp = reinterpret_cast<float2*>(ws + L.colp);
+  float* sqv = reinterpret_cast<float*>(ws + L.sqv);
+
+  query_prep<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(emb, w, a, r, b, M, h, L.Kp, shift, q32, acat, rowp, sqv);
   KG_LAUNCH_OK();
-  target_scores<<<kg_div_up(M, 128), 128, 0, st>>>(queries, emb, b, M, h, shift, tscore);
+  if (n_cand == 0) return KG_OK;
+  const int n_cols = L.n_tiles * BN;
+  entity_prep<<<kg_div_up((long long)n_cols * 32, 256), 256, 0, st>>>(emb, cand_begin, n_cand, n_cols, h, L.Kp, bcat, colp);
   KG_LAUNCH_OK();
-  if (cand_end > cand_begin) {
-    TileLoader<true> la;
-    la.ptr = queries; la.ld = h; la.rows = M; la.K = h;
-    la.vec = ((reinterpret_cast<uintptr_t>(queries) & 15) == 0) && (h % 4 == 0);
-    TileLoader<true> lb;
-    lb.ptr = emb; lb.ld = h; lb.rows = cand_end; lb.K = h;
-    lb.vec = ((reinterpret_cast<uintptr_t>(emb) & 15) == 0) && (h % 4 == 0);
-    dim3 grid(kg_div_up(cand_end - cand_begin, BN), kg_div_up(M, BM));
-    rank_count_kernel<<<grid, THREADS, 0, st>>>(la, lb, h, tscore, b, shift, M, cand_begin, cand_end, ranks);
+
+  CUtensorMap tm_a, tm_b;
+  const uint64_t row_bytes = (uint64_t)2 * L.Kp * sizeof(__half);
+  int rc = make_tensor_map_2d_b16(&tm_a, acat, M, 2 * L.Kp, row_bytes, BM);
+  if (rc != KG_OK) return rc;
+  rc = make_tensor_map_2d_b16(&tm_b, bcat, n_cand, 2 * L.Kp, row_bytes, BN);
+  if (rc != KG_OK) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    KG_CUDA(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  RankArgs args;
+  args.q32 = q32; args.emb = emb; args.rowp = rowp; args.colp = colp; args.tgt = b; args.shift = shift;
+  args.ranks = ranks; args.sqv = sqv; args.dump = tc_scores;
+  args.M = M; args.h = h; args.Kp = L.Kp; args.cand_begin = cand_begin; args.n_cand = n_cand;
+  args.m_tiles = L.m_tiles; args.n_tiles = L.n_tiles;
+  const int total = L.m_tiles * L.n_tiles;
+  const int grid = total < kg_sm_count() ? total : kg_sm_count();
+  rank_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, args);
+  KG_LAUNCH_OK();
+  if (filt_ptr) {
+    filter_correction<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(
+        q32, emb, rowp, b, filt_ptr, filt_idx, M, h, shift, cand_begin, cand_end, ranks);
     KG_LAUNCH_OK();
-    if (filt_ptr) {
-      filter_correction<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(
-          queries, emb, tscore, b, filt_ptr, filt_idx, M, h, shift, cand_begin, cand_end, ranks);
-      KG_LAUNCH_OK();
-    }
   }
   return KG_OK;
 }

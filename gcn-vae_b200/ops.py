@@ -447,18 +447,18 @@ class MeanSquareFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # a10  ranks
 # ---------------------------------------------------------------------------------------------
-def distmult_rank(emb, w, a, r, b, shift=None, cand_range=None, filt_ptr=None, filt_idx=None):
+def distmult_rank(emb, w, a, r, b, shift=None, cand_range=None, filt_ptr=None, filt_idx=None, tc_scores=None):
     """0-indexed raw (or filtered) rank of b_i among all entities for queries (a_i, r_i):
-    utils.perturb_and_get_rank + sort_and_rank (kgvae/utils.py:180-221) without the score matrix."""
+    utils.perturb_and_get_rank + sort_and_rank (kgvae/utils.py:180-221) without the score matrix.
+    ``tc_scores`` (tests only): [M, hi - lo] fp32 tensor that receives the tensor-core scores."""
     emb, w = _c(emb.detach()), _c(w.detach())
     M, (V, h) = a.numel(), emb.shape
     dev = emb.device
     lo, hi = (0, V) if cand_range is None else cand_range
     ranks = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    q = torch.empty((max(M, 1), h), dtype=torch.float32, device=dev)
-    ts = torch.empty(max(M, 1), dtype=torch.float32, device=dev)
+    ws = L.workspace(L.lib().kg_distmult_rank_workspace_bytes(M, int(hi) - int(lo), h), dev)
     sh = None if shift is None else _c(torch.as_tensor(shift, dtype=torch.float32, device=dev).reshape(1))
     L.call("kg_distmult_rank", L.f32(emb), L.f32(w), L.i32(a), L.i32(r), L.i32(b), M, V, h, L.f32(sh),
-           int(lo), int(hi), L.i32(filt_ptr), L.i32(filt_idx), L.f32(q), L.f32(ts), L.i32(ranks),
-           L.stream())
+           int(lo), int(hi), L.i32(filt_ptr), L.i32(filt_idx), L.ptr(ws), ws.numel(), L.i32(ranks),
+           L.f32(tc_scores), L.stream())
     return ranks[:M]

@@ -209,18 +209,24 @@ int kg_distmult_bwd_dw(const float* z, const float* gscore, const int32_t* tripl
  * replaces: utils.perturb_and_get_rank kgvae/utils.py:187-221 + sort_and_rank :180-184
  * For each query i: q_i = emb[a_i] * w[r_i]; score_ij = q_i . emb[j] + shift for all j < V;
  * rank_i = #{j : score_ij > score_i,b_i} + #{j < b_i : score_ij == score_i,b_i}  (0-indexed,
- * ties by ascending entity id).  The M x V score matrix is never written to memory.
+ * ties by ascending entity id).  The M x V score matrix is never written to memory: it lives
+ * as 128 x 256 tiles in tensor memory (tcgen05.mma on a two-term fp16 split of both operands)
+ * and the epilogue counts; pairs the tensor-core value cannot decide are re-scored in fp32.
  * cand_begin/cand_end restrict candidates to an entity shard [begin, end) (multi-GPU: the
  * per-shard counts add up to the rank).
  * filt_ptr/filt_idx (optional, may be NULL): CSR of known-true candidates per query that are
  * removed from the count (filtered setting; the reference itself is raw-only, link_predict.py:7).
- * queries: workspace [M, h] floats; tscore: workspace [M] floats.
+ * workspace: kg_distmult_rank_workspace_bytes(n_queries, cand_end - cand_begin, h) bytes.
+ * tc_scores: NULL in production; a test hook that receives the tensor-core scores
+ *            [n_queries, cand_end - cand_begin] the filter saw.
  * ---------------------------------------------------------------------------------- */
+size_t kg_distmult_rank_workspace_bytes(int n_queries, int n_candidates, int h);
 int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const int32_t* r,
                      const int32_t* b, int n_queries, int n_entities, int h,
                      const float* shift /* device scalar or NULL */, int cand_begin, int cand_end,
                      const int32_t* filt_ptr, const int32_t* filt_idx,
-                     float* queries, float* tscore, int32_t* ranks, void* stream);
+                     void* workspace, size_t workspace_bytes, int32_t* ranks, float* tc_scores,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -340,6 +340,36 @@ def test_rank_random_floats_within_tolerance_interval():
     assert int((got != exact).sum()) <= M // 20
 
 
+@pytest.mark.parametrize("kind", ["gaussian", "positive", "tiny_rows"])
+def test_rank_filter_margin(kind):
+    """The tensor-core (two-term fp16 split) score that the rank kernel uses as a filter must stay
+    far inside the band mu*|q|*|e| (mu = 2^-15) that is re-scored in fp32, and the ranks must
+    equal the fp64 ranks except for candidates closer to the target than fp32 can resolve."""
+    rng = np.random.default_rng(21)
+    V, h, M = 3000, 500, 300
+    emb = rng.standard_normal((V, h)).astype(np.float32)
+    w = rng.standard_normal((5, h)).astype(np.float32)
+    if kind == "positive":                      # all terms of one sign: worst case for accumulation error
+        emb, w = np.abs(emb), np.abs(w)
+    if kind == "tiny_rows":                     # rows of very different magnitude: per-row scaling
+        emb *= np.exp2(rng.integers(-40, 20, size=(V, 1))).astype(np.float32)
+    emb, w = torch.from_numpy(emb), torch.from_numpy(w)
+    a, r, b = rng.integers(0, V, M), rng.integers(0, 5, M), rng.integers(0, V, M)
+    dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
+    tc = torch.full((M, V), float("nan"), device=DEV)
+    got = ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b), tc_scores=tc).cpu().long()
+    q = (emb[a] * w[r])
+    exact = q.double() @ emb.double().T
+    scale = q.double().norm(dim=1, keepdim=True) * emb.double().norm(dim=1).view(1, -1)
+    dev_tc = ((tc.cpu().double() - exact).abs() / scale).max().item()
+    assert dev_tc < 2.0 ** -15 / 10, dev_tc
+    st = exact.gather(1, torch.as_tensor(b).view(-1, 1))
+    tol = 2.0 ** -20 * scale                    # what an fp32 dot product can resolve
+    lo = (exact > st + tol).sum(1)
+    hi = (exact >= st - tol).sum(1) - 1
+    assert bool(((got >= lo) & (got <= hi)).all())
+
+
 def test_rank_filtered():
     rng = np.random.default_rng(10)
     V, h, M = 400, 32, 60
