@@ -31,7 +31,8 @@ _SIGNATURES = {
     "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),
     "kg_colsum_workspace_bytes": (_Z, [_I, _I]),
     "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
-    "kg_gemm_f32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "kg_gemm_f32_workspace_bytes": (_Z, [_I, _I, _I]),
+    "kg_gemm_f32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _Z, _P]),
     "kg_reparam_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "kg_reparam_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_kl_mog_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

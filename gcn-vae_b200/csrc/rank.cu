@@ -24,17 +24,13 @@
 // (about 5e-4 of all pairs on Gaussian data, and every exact tie) are re-scored with dot()
 // above by the same warp.  mu = 2^-15 is > 10x the worst deviation the split product showed
 // against dot() (tests/test_gpu_ops.py::test_rank_filter_margin).
-#include "tc05.cuh"
+#include "split_pipe.cuh"
 
-using namespace tc05;
+using namespace splitpipe;
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;           // CTA tile; BK fp16 elements = one 128-byte row
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 128 + 2 * BN * 8 + 4 * (BN / 32) * 32 * 4;
+constexpr int SMEM_BYTES = PIPE_SMEM + 1024 + 2 * BN * 8 + 4 * (BN / 32) * 32 * 4;   // + colp_s, amb_s
 constexpr float kMu = 3.0517578125e-05f;               // 2^-15
 constexpr float kEps = 4.76837158203125e-07f;         // 2^-21
 
@@ -45,29 +41,6 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ q, const flo
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   return acc;
-}
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// power-of-two scale that puts max|x| into [2^14, 2^15)
-__device__ __forceinline__ float split_scale(float amax) {
-  if (!(amax > 0.f)) return 1.f;
-  int e;
-  frexpf(amax, &e);
-  e = 15 - e;
-  e = e > 100 ? 100 : (e < -100 ? -100 : e);
-  return ldexpf(1.f, e);
-}
-
-__device__ __forceinline__ void split_store(float x, float s, __half* hi_p, __half* lo_p) {
-  const float xs = x * s;
-  const __half hi = __float2half_rn(xs);
-  *hi_p = hi;
-  *lo_p = __float2half_rn(xs - __half2float(hi));
 }
 
 // one warp per candidate row n (shard-relative): fp16 split of emb[cand_begin + n] and column record
@@ -154,88 +127,17 @@ struct RankArgs {
 __global__ void __launch_bounds__(THREADS, 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, RankArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                     // TMA -> MMA
-  uint64_t* empty = bars + STAGES;           // MMA -> TMA
-  uint64_t* tfull = bars + 2 * STAGES;       // MMA -> epilogue   [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // epilogue -> MMA   [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float2* colp_s = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 128);          // [2][BN]
-  uint32_t* amb_s = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 128 + 2 * BN * 8);  // [4][BN/32][32]
-
+  const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b);
+  float2* colp_s = reinterpret_cast<float2*>(P.scratch);                       // [2][BN]
+  uint32_t* amb_s = reinterpret_cast<uint32_t*>(P.scratch + 2 * BN * 8);       // [4][BN/32][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull + i, 1);
-      mbar_init(tempty + i, 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
-  fence_before_thread_sync();
-  __syncthreads();
-  fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int total = p.m_tiles * p.n_tiles;
-  const int k_steps = p.Kp / BK;             // per product term
+  const TileMap tmap{p.m_tiles, p.n_tiles, 1, p.Kp / BK, p.Kp / BK};
+  const int total = tmap.total();
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
-        for (int term = 0; term < 3; ++term) {
-          // small terms first: lo*hi, hi*lo, then hi*hi   (hi at column 0, lo at column Kp)
-          const int a_off = term == 0 ? p.Kp : 0, b_off = term == 1 ? p.Kp : 0;
-          for (int ks = 0; ks < k_steps; ++ks) {
-            mbar_wait(empty + stage, phase ^ 1);
-            uint8_t* st = smem + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
-            tma_load_2d(st, &tm_a, full + stage, a_off + ks * BK, m0);
-            tma_load_2d(st + A_BYTES, &tm_b, full + stage, b_off + ks * BK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
+    pipe_producer(P, &tm_a, &tm_b, tmap, p.Kp);
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(tempty + buf, ((it >> 1) & 1) ^ 1);
-        fence_after_thread_sync();
-        const uint32_t tacc = tmem_base + buf * BN;
-        for (int ks = 0; ks < 3 * k_steps; ++ks) {
-          mbar_wait(full + stage, phase);
-          fence_after_thread_sync();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = smem_desc_k_sw128(sa), db = smem_desc_k_sw128(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // 16 fp16 = 32 bytes per MMA: +2 in the (>>4) address field
-            mma_f16_ss(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
-          mma_commit(empty + stage);          // frees the smem stage once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        mma_commit(tfull + buf);              // accumulator complete
-      }
-    }
+    pipe_mma(P, tmap);
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5)
     const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad + 32)
@@ -256,10 +158,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         rp = __ldg(p.rowp + m);
         tg = __ldg(p.tgt + m);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(tfull + buf, (it >> 1) & 1);
-      fence_after_thread_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+      epi_barrier();
+      const uint32_t taddr = epi_acquire(P, it);
       int cnt = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c += 2) {
@@ -293,9 +193,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       }
-      fence_before_thread_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + buf);            // TMEM buffer may be overwritten
+      epi_release(P, it);                                  // TMEM buffer may be overwritten
       // undecided pairs: canonical fp32 score, whole warp per pair
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -346,12 +244,7 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   }
 
-  fence_before_thread_sync();
-  __syncthreads();
-  if (warp == 2) {
-    fence_after_thread_sync();
-    tmem_dealloc<512>(tmem_base);
-  }
+  pipe_teardown(P);
 }
 
 // filtered setting: take back every known-true candidate that was counted (warp per query)

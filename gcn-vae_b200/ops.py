@@ -86,9 +86,11 @@ def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, addend=None, relu=F
     """out[M,N] (+)= epilogue(op(a) @ op(b)); a, b, out 2-D contiguous fp32."""
     M, N = out.shape
     K = a.shape[0] if trans_a else a.shape[1]
+    nbytes = L.lib().kg_gemm_f32_workspace_bytes(M, N, K)
+    ws = L.workspace(nbytes, out.device) if nbytes else None
     L.call("kg_gemm_f32", L.f32(a), a.shape[1], int(trans_a), L.f32(b), b.shape[1], int(trans_b),
            L.f32(out), out.shape[1], M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask),
-           int(accumulate), L.stream(),
+           int(accumulate), L.ptr(ws), nbytes, L.stream(),
            tag=f"kg_gemm_f32[{M}x{N}x{K},{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]")
     return out
 
@@ -97,7 +99,7 @@ def epilogue_only(out, bias=None, addend=None, relu=False, mask=None):
     """out = mask * act(addend + bias): the GEMM epilogue with an empty product (K = 0)."""
     M, N = out.shape
     L.call("kg_gemm_f32", None, 0, 0, None, 0, 0, L.f32(out), N, M, N, 0, L.f32(bias), L.f32(addend),
-           int(relu), L.f32(mask), 0, L.stream())
+           int(relu), L.f32(mask), 0, None, 0, L.stream())
     return out
 
 

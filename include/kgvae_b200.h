@@ -119,11 +119,15 @@ int kg_colsum(const float* x, int rows, int cols, float* out, void* workspace, s
  *   A(m,k) = A[m*lda + k] if !trans_a else A[k*lda + m];  B(k,n) likewise with ldb.
  *   epilogue: v = acc (+ bias[n]) (+ addend[m*ldc+n]); if relu v = max(v,0);
  *             if mask v *= mask[m*ldc+n]; C = v   (accumulate: C += v)
+ * Products with M, N >= 64, K >= 32 and M*N*K >= 2^22 run on the tensor cores (tcgen05,
+ * two-term fp16 split of both operands, fp32 accumulate: fp32-accurate); they need
+ * kg_gemm_f32_workspace_bytes(M, N, K) bytes of workspace (0 for the small-product FMA kernel).
  * ---------------------------------------------------------------------------------- */
+size_t kg_gemm_f32_workspace_bytes(int M, int N, int K);
 int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
                 float* C, int ldc, int M, int N, int K,
                 const float* bias, const float* addend, int relu, const float* mask,
-                int accumulate, void* stream);
+                int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a5  mean/variance heads + reparameterised sample

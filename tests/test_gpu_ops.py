@@ -8,6 +8,7 @@ import torch
 from helpers import O, RTOL, assert_close
 
 import gcn_vae_b200 as K
+from gcn_vae_b200 import _lib as L
 from gcn_vae_b200 import ops
 
 pytestmark = pytest.mark.gpu
@@ -105,6 +106,39 @@ def test_gemm_epilogue_and_accumulate():
     out4 = torch.ones(60, 50, device=DEV)
     ops.gemm(a2.to(DEV), b2.to(DEV), out4, trans_a=True, mask=m2.to(DEV), accumulate=True)
     assert_close(out4, 1 + (a2.t().double() @ b2.double()).float() * m2, 2e-5, "split-K masked accumulate")
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(14541, 500, 500, 0, 0), (14541, 500, 1000, 0, 1), (500, 1000, 14541, 1, 0),
+                                          (300, 260, 4100, 1, 1), (1000, 500, 700, 0, 1), (129, 257, 200, 0, 0)])
+def test_gemm_tensor_core_path(M, N, K, ta, tb):
+    """Shapes that run on tcgen05 (two-term fp16 split): fp32-level accuracy against fp64, with
+    rows of very different magnitude (per-row scaling), the fused epilogue, and split-K."""
+    assert L.lib().kg_gemm_f32_workspace_bytes(M, N, K) > 0
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    ra = torch.exp2(torch.randint(-12, 12, (M,), generator=g).float())
+    rb = torch.exp2(torch.randint(-12, 12, (N,), generator=g).float())
+    a = a * (ra.view(1, -1) if ta else ra.view(-1, 1))
+    b = b * (rb.view(-1, 1) if tb else rb.view(1, -1))
+    A64, B64 = (a.t() if ta else a).double(), (b.t() if tb else b).double()
+    want = A64 @ B64
+    bound = A64.norm(dim=1, keepdim=True) * B64.norm(dim=0, keepdim=True)     # |a_m| |b_n|
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(a.to(DEV), b.to(DEV), out, trans_a=bool(ta), trans_b=bool(tb))
+    err = ((out.cpu().double() - want).abs() / bound).max().item()
+    assert err < 2e-6, err                      # fp32 FMA chains sit at ~1e-7..1e-6 of |a||b| as well
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    mask = (torch.rand(M, N, generator=g) < 0.8).float() / 0.8
+    base = torch.randn(M, N, generator=g)
+    out2 = base.to(DEV).clone()
+    ops.gemm(a.to(DEV), b.to(DEV), out2, trans_a=bool(ta), trans_b=bool(tb), bias=bias.to(DEV),
+             addend=add.to(DEV), relu=True, mask=mask.to(DEV), accumulate=True)
+    term = torch.relu(want + bias.double() + add.double()) * mask.double()
+    want2 = base.double() + term
+    scale2 = bound + base.double().abs() + term.abs() + bias.double().abs() + add.double().abs()
+    err2 = ((out2.cpu().double() - want2).abs() / scale2).max().item()
+    assert err2 < 2e-6, err2
 
 
 def test_colsum_and_reductions():
