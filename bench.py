@@ -165,13 +165,12 @@ class ClockSampler:
 def algorithmic_bytes(tag, shp):
     """Algorithmic (compulsory) HBM bytes of one launch of the named op; DESIGN.md section 4."""
     N, E, S, R2, h = shp["N"], shp["E"], shp["S"], shp["R2"], H
-    if tag.startswith("kg_bdd_aggregate_fwd") or tag.startswith("kg_bdd_aggregate_bwd_dx"):
+    if tag.startswith("kg_bdd_rel_fwd"):                # SURVEY 8(d): per edge 4*in + 12, per node 4*out, weights once
         si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
-        fin, fout = (si, so) if "fwd" in tag else (so, si)
-        return E * (4 * BASES * fin + 16) + 4 * N * BASES * fout + 4 * R2 * BASES * si * so
-    if tag.startswith("kg_bdd_aggregate_bwd_dw"):
+        return E * (4 * BASES * si + 16) + 4 * N * BASES * so + 4 * R2 * BASES * si * so
+    if tag.startswith("kg_bdd_rel_bwd"):                # per edge 4*(in+out) + 12, per node 4*in (dx), weights r+w
         si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
-        return E * (4 * BASES * (si + so) + 16) + 4 * R2 * BASES * si * so
+        return E * (4 * BASES * (si + so) + 16) + 4 * N * BASES * si + 2 * 4 * R2 * BASES * si * so
     if tag == "kg_distmult_score":
         return S * (3 * 4 * h + 12 + 4)
     if tag == "kg_distmult_bwd_dz":

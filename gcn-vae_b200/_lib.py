@@ -25,9 +25,8 @@ _SIGNATURES = {
     "kg_embedding_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_embedding_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_bdd_weight_layouts": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
-    "kg_bdd_aggregate_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "kg_bdd_aggregate_bwd_dx": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "kg_bdd_aggregate_bwd_dw": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
+    "kg_bdd_rel_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),
     "kg_colsum_workspace_bytes": (_Z, [_I, _I]),
     "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),

@@ -166,9 +166,9 @@ class BddConvFn(torch.autograd.Function):
         w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
         L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
                L.f32(w_bwd), L.stream())
-        agg = torch.empty((n, out_feat), dtype=torch.float32, device=dev)
-        L.call("kg_bdd_aggregate_fwd", L.f32(x), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), L.f32(w_fwd),
-               n, num_bases, si, so, L.f32(agg), L.stream(), tag=f"kg_bdd_aggregate_fwd[{si}x{so}]")
+        agg = torch.zeros((n, out_feat), dtype=torch.float32, device=dev)
+        L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_fwd), num_bases, si, so,
+               L.f32(agg), L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
         out = torch.empty_like(agg)
         bias = None if h_bias is None else _c(h_bias)
         mask = None if drop_mask is None else _c(drop_mask)
@@ -192,16 +192,15 @@ class BddConvFn(torch.autograd.Function):
         L.call("kg_act_dropout_bwd", L.f32(g), L.f32(out), L.f32(mask), ctx.act, out.numel(),
                L.f32(gpre), L.stream())
         dx = dw = dloop = dbias = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            L.call("kg_bdd_aggregate_bwd_dx", L.f32(gpre), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
-                   L.f32(w_bwd), n, B, si, so, L.f32(dx), L.stream(), tag=f"kg_bdd_aggregate_bwd_dx[{si}x{so}]")
-            if loop_weight is not None:
-                gemm(gpre, loop_weight, dx, trans_b=True, accumulate=True)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
             dw = torch.zeros_like(weight)
-            L.call("kg_bdd_aggregate_bwd_dw", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges,
-                   B, si, so, L.f32(dw), L.stream(), tag=f"kg_bdd_aggregate_bwd_dw[{si}x{so}]")
+            L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_bwd),
+                   B, si, so, L.f32(dx), L.f32(dw), L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
+            if dx is not None and loop_weight is not None:
+                gemm(gpre, loop_weight, dx, trans_b=True, accumulate=True)
+            if not ctx.needs_input_grad[1]:
+                dw = None
         if loop_weight is not None and ctx.needs_input_grad[2]:
             dloop = torch.empty_like(loop_weight)
             gemm(x, gpre, dloop, trans_a=True)

@@ -89,18 +89,16 @@ int kg_embedding_bwd(const float* grad_out, const int32_t* ids, int n, int dim, 
  *   w_bwd [R, so, B*si]: w_bwd[r][o][b*si+i] = weight[r][b][i][o]                     */
 int kg_bdd_weight_layouts(const float* weight, int num_etypes, int num_bases, int si, int so,
                           float* w_fwd, float* w_bwd, void* stream);
-/* agg[v, :] = sum_{e: dst_e = v} norm_e * blockdiag(W[etype_e]) * x[src_e, :]   (no atomics) */
-int kg_bdd_aggregate_fwd(const float* x, const int32_t* row_ptr, const void* fwd_pack,
-                         const float* w_fwd, int n_dst, int num_bases, int si, int so,
-                         float* agg, void* stream);
-/* dx[u, :] = sum_{e: src_e = u} norm_e * blockdiag(W[etype_e])^T * dagg[dst_e, :] */
-int kg_bdd_aggregate_bwd_dx(const float* dagg, const int32_t* col_ptr, const void* bwd_pack,
-                            const float* w_bwd, int n_src, int num_bases, int si, int so,
-                            float* dx, void* stream);
-/* dweight[r][b][i][o] += sum_{e: etype_e = r} norm_e * x[src_e][b*si+i] * dagg[dst_e][b*so+o]
- * dweight must be zero-filled by the caller. */
-int kg_bdd_aggregate_bwd_dw(const float* x, const float* dagg, const void* rel_pack, int n_edges,
-                            int num_bases, int si, int so, float* dweight, void* stream);
+/* Message passing (rgcn_bdd_rel.cu): edges walked in (etype, dst) order - rel_pack - so the
+ * block weights of a relation stay in shared memory for a run of edges; messages are accumulated
+ * with vector reductions.  agg / dx / dweight must be zero-filled by the caller; dx may be NULL.
+ *   fwd:  agg[dst] += norm * blockdiag(W[etype]) x[src]
+ *   bwd:  dx[src] += norm * blockdiag(W[etype])^T dagg[dst];  dweight[etype] += norm * x[src] (x) dagg[dst] */
+int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges, const float* w_fwd,
+                   int num_bases, int si, int so, float* agg, void* stream);
+int kg_bdd_rel_bwd(const float* x, const float* dagg, const void* rel_pack, int n_edges,
+                   const float* w_bwd, int num_bases, int si, int so, float* dx, float* dweight,
+                   void* stream);
 
 /* out = dropout(act(agg + bias + loop)) tail of RelGraphConv.forward; backward of the same.
  * act: 0 identity, 1 relu.  drop_mask: [n, dim] keep-mask already scaled by 1/(1-p), or NULL. */
