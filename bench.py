@@ -171,12 +171,10 @@ def algorithmic_bytes(tag, shp):
     if tag.startswith("kg_bdd_rel_bwd"):                # per edge 4*(in+out) + 12, per node 4*in (dx), weights r+w
         si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
         return E * (4 * BASES * (si + so) + 16) + 4 * N * BASES * si + 2 * 4 * R2 * BASES * si * so
-    if tag == "kg_distmult_score":
-        return S * (3 * 4 * h + 12 + 4)
-    if tag == "kg_distmult_bwd_dz":
+    if tag == "kg_distmult_bce_fwd":                    # 3 rows + record per triplet; g out; dw once
+        return S * (3 * 4 * h + 16 + 4 + 4) + 4 * shp["R"] * h
+    if tag == "kg_distmult_bwd_dz":                     # each triplet seen from both ends: w row + other row + record
         return 2 * S * (2 * 4 * h + 16 + 4) + 4 * N * h
-    if tag == "kg_distmult_bwd_dw":
-        return S * (2 * 4 * h + 12 + 8) + 4 * shp["R"] * h
     return None
 
 

@@ -45,9 +45,11 @@ _SIGNATURES = {
     "kg_sum_squares": (_I, [_P, _L, _P, _P, _Z, _P]),
     "kg_sum": (_I, [_P, _L, _P, _P, _Z, _P]),
     "kg_triplet_index_workspace_bytes": (_Z, [_I]),
-    "kg_triplet_index": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_triplet_index": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "kg_distmult_bce_workspace_bytes": (_Z, [_I]),
+    "kg_distmult_bce_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "kg_distmult_bwd_dz": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
-    "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_rank_workspace_bytes": (_Z, [_I, _I, _I]),
     "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _Z, _P, _P, _P]),
 }
@@ -73,7 +75,7 @@ def lib():
 
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
-    "kg_graph_build": 26, "kg_graph_index": 18, "kg_triplet_index": 11, "kg_colsum": 2,
+    "kg_graph_build": 26, "kg_graph_index": 18, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2,
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
 }
 launches = 0          # running count of kernels launched through this binding

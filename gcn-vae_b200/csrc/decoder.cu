@@ -150,19 +150,29 @@ extern "C" int kg_sum(const float* x, long long n, float* out, void* workspace, 
 }
 
 // ------------------------------------------------------------------------------------------
-// triplet index for the backward pass
+// triplet index: the two orderings the decoder kernels walk (integer work: CUB radix sort, no atomics)
+//   rs_rec  [S]  int4 {s, r, o, t}        sorted by (r, s): runs share w[r] and z[s]
+//   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, r, t, 0} sorted by (entity, r): for entity v every
+//           triplet where v is subject (other = object) or object (other = subject)
 // ------------------------------------------------------------------------------------------
-__global__ void triplet_keys(const int* __restrict__ trip, int S, int* ent_key, int* ent_val,
-                             int* rel_key, int* rel_val, int* ent_cnt, int* rel_cnt) {
+__global__ void triplet_keys(const int* __restrict__ trip, int S, int nb, int rb,
+                             unsigned long long* rs_key, int* rs_val, unsigned long long* ent_key, int* ent_val) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S) return;
-  const int s = trip[3 * (size_t)t], r = trip[3 * (size_t)t + 1], o = trip[3 * (size_t)t + 2];
-  ent_key[t] = s;      ent_val[t] = t;         // subject side
-  ent_key[S + t] = o;  ent_val[S + t] = S + t; // object side
-  rel_key[t] = r;      rel_val[t] = t;
-  atomicAdd(ent_cnt + s, 1);
-  atomicAdd(ent_cnt + o, 1);
-  atomicAdd(rel_cnt + r, 1);
+  const unsigned long long s = (unsigned)trip[3 * (size_t)t], r = (unsigned)trip[3 * (size_t)t + 1],
+                           o = (unsigned)trip[3 * (size_t)t + 2];
+  rs_key[t] = (r << nb) | s;
+  rs_val[t] = t;
+  ent_key[t] = (s << rb) | r;      ent_val[t] = t;          // subject side
+  ent_key[S + t] = (o << rb) | r;  ent_val[S + t] = S + t;  // object side
+}
+
+__global__ void fill_rs_rec(const int* __restrict__ trip, const int* __restrict__ sorted_val, int S,
+                            int4* __restrict__ rec) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const int t = sorted_val[k];
+  rec[k] = make_int4(trip[3 * (size_t)t], trip[3 * (size_t)t + 1], trip[3 * (size_t)t + 2], t);
 }
 
 __global__ void fill_ent_pack(const int* __restrict__ trip, const int* __restrict__ sorted_val, int S,
@@ -175,6 +185,21 @@ __global__ void fill_ent_pack(const int* __restrict__ trip, const int* __restric
   pack[k] = make_int4(other, trip[3 * (size_t)t + 1], t, 0);
 }
 
+// ptr[v] = first position whose key has entity >= v (keys sorted ascending)
+__global__ void ent_lower_bound(const unsigned long long* __restrict__ keys, int n, int rb, int n_nodes,
+                                int* __restrict__ ptr) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n_nodes) return;
+  const unsigned long long want = (unsigned long long)v << rb;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(keys + mid) < want) lo = mid + 1;
+    else hi = mid;
+  }
+  ptr[v] = lo;
+}
+
 static int bits_for(int n) {
   int b = 1;
   while (b < 31 && (1ll << b) < (long long)n) ++b;
@@ -182,60 +207,281 @@ static int bits_for(int n) {
 }
 
 static size_t triplet_cub_bytes(int S) {
-  size_t a = 0, c = 0;
-  cub::DeviceRadixSort::SortPairs((void*)nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr,
-                                  (int*)nullptr, 2 * S);
-  cub::DeviceScan::ExclusiveSum((void*)nullptr, c, (int*)nullptr, (int*)nullptr, (1 << 24) + 1);
-  return kg_align_up((a > c ? a : c) + 256);
+  size_t a = 0;
+  cub::DeviceRadixSort::SortPairs((void*)nullptr, a, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (int*)nullptr, (int*)nullptr, 2 * S);
+  return kg_align_up(a + 256);
 }
 
 extern "C" size_t kg_triplet_index_workspace_bytes(int n_triplets) {
   int S = n_triplets > 0 ? n_triplets : 1;
-  return 4 * kg_align_up(((size_t)2 * S + 1) * 4) + 2 * kg_align_up(((size_t)S + 1) * 4) + triplet_cub_bytes(S) + 1024;
+  return 2 * kg_align_up(((size_t)2 * S + 1) * 8) + 2 * kg_align_up(((size_t)2 * S + 1) * 4) +
+         2 * kg_align_up(((size_t)S + 1) * 8) + 2 * kg_align_up(((size_t)S + 1) * 4) + triplet_cub_bytes(S) + 1024;
 }
 
 extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
-                                int32_t* ent_ptr, void* ent_pack, int32_t* rel_ptr, int32_t* rel_perm,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                void* rs_rec, int32_t* ent_ptr, void* ent_pack, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   KG_REQUIRE(n_triplets >= 0 && n_nodes > 0 && n_rels > 0, "triplet index: bad sizes");
-  KG_REQUIRE(n_nodes < (1 << 24), "triplet index: n_nodes < 2^24");
+  KG_REQUIRE(n_nodes < (1 << 24) && n_rels < (1 << 16), "triplet index: n_nodes < 2^24, n_rels < 2^16");
   cudaStream_t st = kg_stream(stream);
   const int S = n_triplets;
-  KG_CUDA(cudaMemsetAsync(ent_ptr, 0, sizeof(int) * (n_nodes + 1), st));
-  KG_CUDA(cudaMemsetAsync(rel_ptr, 0, sizeof(int) * (n_rels + 1), st));
+  if (S == 0) {
+    KG_CUDA(cudaMemsetAsync(ent_ptr, 0, sizeof(int) * (n_nodes + 1), st));
+    return KG_OK;
+  }
   KgArena ws(workspace, workspace_bytes);
-  int* ek_in = ws.take<int>(2 * (size_t)S + 1);
-  int* ek_out = ws.take<int>(2 * (size_t)S + 1);
+  unsigned long long* ek_in = ws.take<unsigned long long>(2 * (size_t)S + 1);
+  unsigned long long* ek_out = ws.take<unsigned long long>(2 * (size_t)S + 1);
   int* ev_in = ws.take<int>(2 * (size_t)S + 1);
   int* ev_out = ws.take<int>(2 * (size_t)S + 1);
-  int* rk_in = ws.take<int>((size_t)S + 1);
+  unsigned long long* rk_in = ws.take<unsigned long long>((size_t)S + 1);
+  unsigned long long* rk_out = ws.take<unsigned long long>((size_t)S + 1);
   int* rv_in = ws.take<int>((size_t)S + 1);
-  size_t temp_bytes = triplet_cub_bytes(S > 0 ? S : 1);
+  int* rv_out = ws.take<int>((size_t)S + 1);
+  size_t temp_bytes = triplet_cub_bytes(S);
   void* temp = ws.take<char>(temp_bytes);
-  if (!ek_in || !ek_out || !ev_in || !ev_out || !rk_in || !rv_in || !temp)
+  if (!ek_in || !ek_out || !ev_in || !ev_out || !rk_in || !rk_out || !rv_in || !rv_out || !temp)
     return kg_fail(KG_ERR_WORKSPACE, "triplet index: workspace too small");
-  if (S > 0) {
-    triplet_keys<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, ek_in, ev_in, rk_in, rv_in, ent_ptr, rel_ptr);
-    KG_LAUNCH_OK();
-  }
+  const int nb = bits_for(n_nodes), rb = bits_for(n_rels);
+  triplet_keys<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, nb, rb, rk_in, rv_in, ek_in, ev_in);
+  KG_LAUNCH_OK();
   size_t tb = temp_bytes;
-  KG_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, ent_ptr, ent_ptr, n_nodes + 1, st));
-  tb = temp_bytes;
-  KG_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, rel_ptr, rel_ptr, n_rels + 1, st));
-  if (S == 0) return KG_OK;
-  tb = temp_bytes;
-  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, 2 * S, 0, bits_for(n_nodes), st));
+  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, 2 * S, 0, nb + rb, st));
   fill_ent_pack<<<kg_div_up(2LL * S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
   KG_LAUNCH_OK();
+  ent_lower_bound<<<kg_div_up(n_nodes + 1, kThreads), kThreads, 0, st>>>(ek_out, 2 * S, rb, n_nodes, ent_ptr);
+  KG_LAUNCH_OK();
   tb = temp_bytes;
-  // relation grouping: reuse ek_out as the (unused) sorted-key output
-  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, rk_in, ek_out, rv_in, rel_perm, S, 0, bits_for(n_rels), st));
+  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, rk_in, rk_out, rv_in, rv_out, S, 0, nb + rb, st));
+  fill_rs_rec<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, rv_out, S, reinterpret_cast<int4*>(rs_rec));
+  KG_LAUNCH_OK();
   return KG_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// dz[v, :] = sum over the entity-major index of gscore[t] * w[r, :] * z[other, :]
-// one thread per (entity, VEC consecutive columns); no atomics
+// (r, s)-ordered pass over the triplets, one warp per chunk of kChunkT consecutive records.
+//   FUSED : score_t = sum_d (z[s,d] w[r,d]) z[o,d] + shift; BCE-with-logits term; g_t = (sigmoid - y) / S;
+//           dw[r,:] += g_t z[s,:] z[o,:]          (link_predict.py:57-63,74-77 and their backward into w)
+//   !FUSED: g_t given; dw only
+// A lane keeps its float4 slots of w[r] and z[s] in registers while the run lasts, streams z[o]
+// (2 KB, coalesced), and flushes the dw accumulators with vector reductions when r changes.
+// ------------------------------------------------------------------------------------------
+static constexpr int kChunkT = 32;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int NV, bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, const int4* __restrict__ rec,
+                   const float* __restrict__ labels, const float* __restrict__ g_in,
+                   const float* __restrict__ shift_p, int S, int h, float inv_S, float* __restrict__ score_out,
+                   float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ loss_part,
+                   float* __restrict__ gsum_part) {
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int k0 = warp * kChunkT;
+  if (k0 >= S) return;
+  const int k1 = min(S, k0 + kChunkT), nvec = h >> 2;
+  const float shift = (FUSED && shift_p) ? __ldg(shift_p) : 0.f;
+  float4 zs[NV], wr[NV], acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cs = -1, cr = -1;
+  float loss = 0.f, gsum = 0.f;
+  int4 rc = __ldg(rec + k0);
+  for (int k = k0; k < k1; ++k) {
+    const int4 nxt = k + 1 < k1 ? __ldg(rec + k + 1) : rc;      // prefetch the next record
+    if (rc.y != cr) {
+      if (cr >= 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nvec) red_add_v4(dw + (size_t)cr * h + 4 * c, acc[i]);
+          acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      cr = rc.y;
+      cs = -1;
+      if (FUSED) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + 32 * i;
+          wr[i] = c < nvec ? __ldg(reinterpret_cast<const float4*>(w + (size_t)cr * h) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    if (rc.x != cs) {
+      cs = rc.x;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        zs[i] = c < nvec ? __ldg(reinterpret_cast<const float4*>(z + (size_t)cs * h) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 zo[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      zo[i] = c < nvec ? __ldg(reinterpret_cast<const float4*>(z + (size_t)rc.z * h) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float g;
+    if (FUSED) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        dot = fmaf(zs[i].x * wr[i].x, zo[i].x, dot);
+        dot = fmaf(zs[i].y * wr[i].y, zo[i].y, dot);
+        dot = fmaf(zs[i].z * wr[i].z, zo[i].z, dot);
+        dot = fmaf(zs[i].w * wr[i].w, zo[i].w, dot);
+      }
+      dot = kg_warp_sum(dot);
+      const float xv = dot + shift, y = __ldg(labels + rc.w);
+      loss += fmaxf(xv, 0.f) - xv * y + log1pf(expf(-fabsf(xv)));     // F.binary_cross_entropy_with_logits
+      g = (kg_sigmoid(xv) - y) * inv_S;
+      gsum += g;
+      if (lane == 0) {
+        g_out[rc.w] = g;
+        if (score_out) score_out[rc.w] = xv;
+      }
+    } else {
+      g = __ldg(g_in + rc.w);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      acc[i].x = fmaf(g * zs[i].x, zo[i].x, acc[i].x);
+      acc[i].y = fmaf(g * zs[i].y, zo[i].y, acc[i].y);
+      acc[i].z = fmaf(g * zs[i].z, zo[i].z, acc[i].z);
+      acc[i].w = fmaf(g * zs[i].w, zo[i].w, acc[i].w);
+    }
+    rc = nxt;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) red_add_v4(dw + (size_t)cr * h + 4 * c, acc[i]);
+  }
+  if (FUSED && lane == 0) {
+    loss_part[warp] = loss;
+    gsum_part[warp] = gsum;
+  }
+}
+
+// scalar variant for h % 4 != 0 or unaligned rows (no register caching)
+template <bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+distmult_rs_generic(const float* __restrict__ z, const float* __restrict__ w, const int4* __restrict__ rec,
+                    const float* __restrict__ labels, const float* __restrict__ g_in,
+                    const float* __restrict__ shift_p, int S, int h, float inv_S, float* __restrict__ score_out,
+                    float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ loss_part,
+                    float* __restrict__ gsum_part) {
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int k0 = warp * kChunkT;
+  if (k0 >= S) return;
+  const int k1 = min(S, k0 + kChunkT);
+  const float shift = (FUSED && shift_p) ? __ldg(shift_p) : 0.f;
+  float loss = 0.f, gsum = 0.f;
+  for (int k = k0; k < k1; ++k) {
+    const int4 rc = __ldg(rec + k);
+    const float* zs = z + (size_t)rc.x * h;
+    const float* wr = w + (size_t)rc.y * h;
+    const float* zo = z + (size_t)rc.z * h;
+    float g;
+    if (FUSED) {
+      float dot = 0.f;
+      for (int c = lane; c < h; c += 32) dot = fmaf(__ldg(zs + c) * __ldg(wr + c), __ldg(zo + c), dot);
+      dot = kg_warp_sum(dot);
+      const float xv = dot + shift, y = __ldg(labels + rc.w);
+      loss += fmaxf(xv, 0.f) - xv * y + log1pf(expf(-fabsf(xv)));
+      g = (kg_sigmoid(xv) - y) * inv_S;
+      gsum += g;
+      if (lane == 0) {
+        g_out[rc.w] = g;
+        if (score_out) score_out[rc.w] = xv;
+      }
+    } else {
+      g = __ldg(g_in + rc.w);
+    }
+    for (int c = lane; c < h; c += 32) atomicAdd(dw + (size_t)rc.y * h + c, g * __ldg(zs + c) * __ldg(zo + c));
+  }
+  if (FUSED && lane == 0) {
+    loss_part[warp] = loss;
+    gsum_part[warp] = gsum;
+  }
+}
+
+template <bool FUSED>
+static int launch_rs(const float* z, const float* w, const void* rs_rec, const float* labels, const float* g_in,
+                     const float* shift, int S, int h, float* score_out, float* g_out, float* dw,
+                     float* loss_part, float* gsum_part, cudaStream_t st) {
+  const int warps = kg_div_up(S, kChunkT);
+  const int grid = kg_div_up((long long)warps * 32, kThreads);
+  const int4* rec = reinterpret_cast<const int4*>(rs_rec);
+  const float inv_S = 1.0f / (float)S;
+  const bool vec = (h % 4 == 0) && h <= 1024 &&
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0;
+#define KG_RS_LAUNCH(NV_)                                                                                   \
+  distmult_rs_kernel<NV_, FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S,    \
+                                                            score_out, g_out, dw, loss_part, gsum_part)
+  if (!vec) distmult_rs_generic<FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, score_out, g_out, dw, loss_part, gsum_part);
+  else if (h <= 128) KG_RS_LAUNCH(1);
+  else if (h <= 256) KG_RS_LAUNCH(2);
+  else if (h <= 512) KG_RS_LAUNCH(4);
+  else KG_RS_LAUNCH(8);
+#undef KG_RS_LAUNCH
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+extern "C" size_t kg_distmult_bce_workspace_bytes(int n_triplets) {
+  const size_t warps = (size_t)kg_div_up(n_triplets > 0 ? n_triplets : 1, kChunkT);
+  return 2 * kg_align_up(warps * sizeof(float)) + kg_align_up(sizeof(float) * kMaxPartials) + 1024;
+}
+
+// Fused DistMult score + BCE-with-logits (mean) + gradient wrt the score and wrt w_relation.
+//   loss_out[0] = mean_t BCE(score_t, labels_t);  gsum_out[0] = sum_t g_t (gradient wrt the scalar shift)
+//   g_out[t] = dloss/dscore_t;  dw (zero-filled by the caller) += sum_t g_t z[s_t] z[o_t];  score_out optional
+extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
+                                   int n_triplets, int h, const float* shift, float* score_out, float* g_out,
+                                   float* dw, float* loss_out, float* gsum_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult bce: bad sizes");
+  cudaStream_t st = kg_stream(stream);
+  if (n_triplets == 0) {
+    KG_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    KG_CUDA(cudaMemsetAsync(gsum_out, 0, sizeof(float), st));
+    return KG_OK;
+  }
+  const size_t warps = (size_t)kg_div_up(n_triplets, kChunkT);
+  KgArena ws(workspace, workspace_bytes);
+  float* loss_part = ws.take<float>(warps);
+  float* gsum_part = ws.take<float>(warps);
+  float* red = ws.take<float>(kMaxPartials);
+  if (!loss_part || !gsum_part || !red) return kg_fail(KG_ERR_WORKSPACE, "distmult bce: workspace too small");
+  int rc = launch_rs<true>(z, w, rs_rec, labels, nullptr, shift, n_triplets, h, score_out, g_out, dw, loss_part,
+                           gsum_part, st);
+  if (rc != KG_OK) return rc;
+  rc = run_reduce(loss_part, nullptr, (long long)warps, 0, 1.0f / (float)n_triplets, 0.f, nullptr, loss_out, red,
+                  sizeof(float) * kMaxPartials, st);
+  if (rc != KG_OK) return rc;
+  return run_reduce(gsum_part, nullptr, (long long)warps, 0, 1.f, 0.f, nullptr, gsum_out, red,
+                    sizeof(float) * kMaxPartials, st);
+}
+
+// dw[r,:] += sum_{t: rel_t = r} gscore[t] * z[s_t,:] * z[o_t,:]; dw zero-filled by the caller
+extern "C" int kg_distmult_bwd_dw(const float* z, const float* gscore, const void* rs_rec, int n_triplets, int h,
+                                  float* dw, void* stream) {
+  KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult dw: bad sizes");
+  if (n_triplets == 0) return KG_OK;
+  return launch_rs<false>(z, nullptr, rs_rec, nullptr, gscore, nullptr, n_triplets, h, nullptr, nullptr, dw, nullptr,
+                          nullptr, kg_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// dz[v, :] = sum over the (entity, r)-ordered index of gscore[t] * w[r, :] * z[other, :]
+// one thread per (entity, VEC consecutive columns); w[r] stays in registers while r repeats; no atomics
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -250,19 +496,25 @@ distmult_dz_kernel(const float* __restrict__ z, const float* __restrict__ w,
   float acc[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+  int cr = -1;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
   for (int e = __ldg(ent_ptr + v); e < e_end; ++e) {
     const int4 p = __ldg(ent_pack + e);          // {other, rel, triplet, -}
     const float g = __ldg(gscore + p.z);
+    if (p.y != cr) {
+      cr = p.y;
+      if (VEC == 4) a = __ldg(reinterpret_cast<const float4*>(w + (size_t)cr * h) + c);
+      else a.x = __ldg(w + (size_t)cr * h + c);
+    }
     if (VEC == 4) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(w + (size_t)p.y * h) + c);
       const float4 b = __ldg(reinterpret_cast<const float4*>(z + (size_t)p.x * h) + c);
       acc[0] = fmaf(g * a.x, b.x, acc[0]);
       acc[1 % VEC] = fmaf(g * a.y, b.y, acc[1 % VEC]);
       acc[2 % VEC] = fmaf(g * a.z, b.z, acc[2 % VEC]);
       acc[3 % VEC] = fmaf(g * a.w, b.w, acc[3 % VEC]);
     } else {
-      acc[0] = fmaf(g * __ldg(w + (size_t)p.y * h + c), __ldg(z + (size_t)p.x * h + c), acc[0]);
+      acc[0] = fmaf(g * a.x, __ldg(z + (size_t)p.x * h + c), acc[0]);
     }
   }
   if (VEC == 4) {
@@ -287,47 +539,6 @@ extern "C" int kg_distmult_bwd_dz(const float* z, const float* w, const float* g
     distmult_dz_kernel<1><<<kg_div_up((long long)n_nodes * h, kThreads), kThreads, 0, kg_stream(stream)>>>(
         z, w, gscore, ent_ptr, pk, n_nodes, h, dz);
   }
-  KG_LAUNCH_OK();
-  return KG_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// dw[r, :] += sum_{t in rel group r} gscore[t] * z[s_t, :] * z[o_t, :]
-// CTA = chunk of relation-grouped triplets x 128 columns; a run of equal relations is
-// accumulated in a register and flushed once
-// ------------------------------------------------------------------------------------------
-static constexpr int kDwChunk = 256;
-
-__global__ void __launch_bounds__(128)
-distmult_dw_kernel(const float* __restrict__ z, const float* __restrict__ gscore,
-                   const int* __restrict__ trip, const int* __restrict__ rel_perm, int S, int h,
-                   float* __restrict__ dw) {
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  const bool active = c < h;
-  const int k0 = blockIdx.x * kDwChunk, k1 = min(S, k0 + kDwChunk);
-  float acc = 0.f;
-  int cur = -1;
-  for (int k = k0; k < k1; ++k) {
-    const int t = __ldg(rel_perm + k);
-    const int s = __ldg(trip + 3 * (size_t)t), r = __ldg(trip + 3 * (size_t)t + 1),
-              o = __ldg(trip + 3 * (size_t)t + 2);
-    if (r != cur) {
-      if (cur >= 0 && active) atomicAdd(dw + (size_t)cur * h + c, acc);
-      acc = 0.f;
-      cur = r;
-    }
-    if (active)
-      acc = fmaf(__ldg(gscore + t) * __ldg(z + (size_t)s * h + c), __ldg(z + (size_t)o * h + c), acc);
-  }
-  if (cur >= 0 && active) atomicAdd(dw + (size_t)cur * h + c, acc);
-}
-
-extern "C" int kg_distmult_bwd_dw(const float* z, const float* gscore, const int32_t* triplets,
-                                  const int32_t* rel_perm, int n_triplets, int h, float* dw, void* stream) {
-  KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult dw: bad sizes");
-  if (n_triplets == 0) return KG_OK;
-  dim3 grid(kg_div_up(n_triplets, kDwChunk), kg_div_up(h, 128));
-  distmult_dw_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, gscore, triplets, rel_perm, n_triplets, h, dw);
   KG_LAUNCH_OK();
   return KG_OK;
 }

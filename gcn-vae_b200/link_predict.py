@@ -48,8 +48,9 @@ class LinkPredict(nn.Module):
 
     def get_loss(self, g, embed, triplets, labels):
         """(loss, predict_loss, kl, mmd) as in link_predict.py:71-92."""
-        score = self.calc_score(embed, triplets, self._flow_shift())
-        predict_loss = ops.BceLogitsFn.apply(score, labels)
+        trip = ops.as_i32(triplets, embed.device)
+        lab = torch.as_tensor(labels, dtype=torch.float32, device=embed.device)
+        predict_loss = ops.DistMultBceFn.apply(embed, self.w_relation, trip, lab, self._flow_shift())
         reg_loss = self.regularization_loss(embed)
         zero = lambda: torch.zeros(1, device=embed.device)
         kl = self.encoder.get_kl(embed) if self.kl_param > 0 else zero()

@@ -191,20 +191,32 @@ int kg_sum_squares(const float* x, long long n, float* out, void* workspace, siz
                    void* stream);
 int kg_sum(const float* x, long long n, float* out, void* workspace, size_t workspace_bytes,
            void* stream);
-/* index structures for the backward pass, built once per batch of triplets:
- *   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, rel, triplet_id, 0}: for entity v, every
- *     triplet where v is subject (other = object) or object (other = subject)
- *   rel_ptr [n_rels+1], rel_perm [S]: triplet ids grouped by relation */
+/* index structures, built once per batch of triplets (integer work, radix sort, no atomics):
+ *   rs_rec  [S]  int4 {s, r, o, t}: the triplets in (r, s) order - runs share w[r] and z[s]
+ *   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, r, t, 0} in (entity, r) order: for entity v,
+ *     every triplet where v is subject (other = object) or object (other = subject)
+ * Limits: n_nodes < 2^24, n_rels < 2^16. */
 size_t kg_triplet_index_workspace_bytes(int n_triplets);
 int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
-                     int32_t* ent_ptr, void* ent_pack, int32_t* rel_ptr, int32_t* rel_perm,
+                     void* rs_rec, int32_t* ent_ptr, void* ent_pack,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Fused forward of get_loss' prediction term (link_predict.py:74-77) over rs_rec:
+ *   score_t = sum_d z[s,d] w[r,d] z[o,d] + shift;  loss_out[0] = mean_t BCE-with-logits(score_t, labels_t)
+ *   g_out[t] = dloss/dscore_t = (sigmoid(score_t) - labels_t) / S;  gsum_out[0] = sum_t g_t (d/dshift)
+ *   dw[r,:] += sum_{t: r_t = r} g_t z[s_t,:] z[o_t,:]   (dw zero-filled by the caller)
+ *   score_out [S] optional (may be NULL)
+ * workspace: kg_distmult_bce_workspace_bytes(S) */
+size_t kg_distmult_bce_workspace_bytes(int n_triplets);
+int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
+                        int n_triplets, int h, const float* shift /* device scalar or NULL */,
+                        float* score_out, float* g_out, float* dw, float* loss_out, float* gsum_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* dz[v,:] = sum_{(other, r, t) in ent(v)} gscore[t] * w[r,:] * z[other,:]    (no atomics) */
 int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore, const int32_t* ent_ptr,
                        const void* ent_pack, int n_nodes, int h, float* dz, void* stream);
 /* dw[r,:] += sum_{t: rel_t = r} gscore[t] * z[s_t,:] * z[o_t,:]; dw zero-filled by the caller */
-int kg_distmult_bwd_dw(const float* z, const float* gscore, const int32_t* triplets,
-                       const int32_t* rel_perm, int n_triplets, int h, float* dw, void* stream);
+int kg_distmult_bwd_dw(const float* z, const float* gscore, const void* rs_rec, int n_triplets, int h,
+                       float* dw, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a10  all-entity rank evaluation

@@ -278,7 +278,8 @@ def test_permute_is_involution():
 
 
 # ------------------------------------------------------------------------------ decoder (a9)
-@pytest.mark.parametrize("n,h,r,S", [(40, 20, 3, 500), (300, 100, 7, 5000), (25, 33, 2, 64), (10, 8, 2, 0)])
+@pytest.mark.parametrize("n,h,r,S", [(40, 20, 3, 500), (300, 100, 7, 5000), (25, 33, 2, 64), (10, 8, 2, 0),
+                                     (2000, 500, 37, 20000), (50, 260, 4, 1000)])
 def test_distmult_loss_fwd_bwd(n, h, r, S):
     g = torch.Generator().manual_seed(n + S)
     z = torch.randn(n, h, generator=g).requires_grad_(True)
@@ -300,6 +301,13 @@ def test_distmult_loss_fwd_bwd(n, h, r, S):
     assert_close(got, want, 1e-5, "bce")
     for name, a, b in zip(("dz", "dw", "dshift"), cu, (z, w, shift)):
         assert_close(a.grad, b.grad, RTOL, f"distmult {name}")
+    # the fused score + BCE + dw forward used by LinkPredict.get_loss
+    fu = [t.detach().to(DEV).requires_grad_(True) for t in (z, w, shift)]
+    loss = ops.DistMultBceFn.apply(fu[0], fu[1], torch.from_numpy(trip).to(torch.int32).to(DEV), labels.to(DEV), fu[2])
+    (loss * 3.0).backward()
+    assert_close(loss, want, 1e-5, "fused bce")
+    for name, a, b in zip(("dz", "dw", "dshift"), fu, (z, w, shift)):
+        assert_close(a.grad, 3.0 * b.grad, RTOL, f"fused distmult {name}")
 
 
 def test_mean_square():
