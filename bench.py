@@ -226,13 +226,7 @@ def run_gpu(args):
         loss, _, _, _ = model.get_loss(gr, embed, t["samples"], t["labels"])
         loss.backward()
         if world > 1:                                       # replicas: average gradients over NVLink
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
+            K.parallel.allreduce_mean_grads(params)
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
         return loss
@@ -292,7 +286,7 @@ def run_gpu(args):
     t_norm = torch.from_numpy(tnorm[tg._dst].reshape(-1, 1).astype(np.float32)).to(dev)
     test_host = test.to(torch.int32).pin_memory()
     test_dev = test_host.to(dev)
-    lo, hi = (data.num_nodes * rank) // world, (data.num_nodes * (rank + 1)) // world
+    lo, hi = K.parallel.entity_shard(data.num_nodes, rank, world)
 
     def eval_ranks(tt):
         with torch.no_grad():

@@ -7,7 +7,7 @@ node_norm_to_edge_norm, main), ``flow_network`` (MaskedLinear, PermuteLayer, MAD
 signature), ``graph`` (the DGLGraph surface the reference uses).  ``ops`` holds the autograd
 wrappers over the C ABI in ``include/kgvae_b200.h``; ``csrc/`` the CUDA kernels.
 """
-from . import _lib, datasets, flow_network, graph, link_predict, model, nn, ops, utils  # noqa: F401
+from . import _lib, datasets, flow_network, graph, link_predict, model, nn, ops, parallel, utils  # noqa: F401
 from .flow_network import MADE, MaskedLinear, PermuteLayer  # noqa: F401
 from .graph import DGLGraph, Graph  # noqa: F401
 from .link_predict import LinkPredict, node_norm_to_edge_norm  # noqa: F401

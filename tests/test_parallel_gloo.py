@@ -1,0 +1,106 @@
+"""Multi-process host logic on CPU: gloo backend, world_size 2.
+
+Covers what does not need a GPU: the replica gradient all-reduce, entity-sharded rank counts
+adding up to the single-process ranks (checked with the oracle's scores), destination-ownership
+partitioning and the padded all-gather of node features."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import O
+
+from gcn_vae_b200 import parallel
+
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        res = {}
+        # --- replicas: one flattened all-reduce averages the gradients ------------------------
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)),
+                  torch.nn.Parameter(torch.randn(2, 2))]
+        g = torch.Generator().manual_seed(100 + rank)
+        params[0].grad = torch.randn(5, 3, generator=g)
+        params[1].grad = torch.randn(7, generator=g)          # params[2] has no grad on any rank
+        parallel.allreduce_mean_grads(params)
+        res["grads"] = [p.grad.clone() for p in params]
+
+        # --- entity-sharded evaluation: shard counts add up ----------------------------------
+        rng = np.random.default_rng(5)
+        V, h, M = 101, 16, 37
+        emb = torch.from_numpy(rng.integers(-4, 5, size=(V, h)).astype(np.float32) / 4)
+        w = torch.from_numpy(rng.integers(-4, 5, size=(3, h)).astype(np.float32) / 4)
+        a, r, b = (torch.from_numpy(rng.integers(0, n, M)) for n in (V, 3, V))
+        score = O.eval_scores(emb, w, a, r)
+        st = score.gather(1, b.view(-1, 1))
+        col = torch.arange(V).view(1, -1)
+
+        def count(lo, hi):
+            ahead = (score > st) | ((score == st) & (col < b.view(-1, 1)))
+            return ahead[:, lo:hi].sum(1).to(torch.int32)
+
+        res["ranks"] = parallel.sharded_rank_counts(count, V)
+        res["want_ranks"] = O.rank_of_target(score, b)
+
+        # --- destination ownership + all-gather of the owned feature rows ---------------------
+        N, E = 23, 200
+        src, dst, et = rng.integers(0, N, E), rng.integers(0, N, E), rng.integers(0, 4, E)
+        parts = parallel.partition_by_destination(src, dst, et, None, N, WORLD)
+        mine = parts[rank]
+        feats = torch.arange(N * 3, dtype=torch.float32).view(N, 3)
+        full = parallel.allgather_rows(feats[mine["lo"]:mine["hi"]], N)
+        res["gathered_ok"] = bool(torch.equal(full, feats))
+        res["parts"] = [(p["lo"], p["hi"], p["edge_ids"]) for p in parts]
+        res["edges"] = (src, dst)
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_host_logic():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(port, out), nprocs=WORLD, join=True)
+        res = [out[r] for r in range(WORLD)]
+    # gradients: identical on both ranks and equal to the mean of the per-rank gradients
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(WORLD)]
+    g0 = torch.stack([torch.randn(5, 3, generator=g) for g in gens]).mean(0)
+    g1 = torch.stack([torch.randn(7, generator=g) for g in gens]).mean(0)
+    for r in range(WORLD):
+        assert torch.allclose(res[r]["grads"][0], g0) and torch.allclose(res[r]["grads"][1], g1)
+        assert torch.equal(res[r]["grads"][2], torch.zeros(2, 2))
+        assert torch.equal(res[r]["ranks"].long(), res[r]["want_ranks"])
+        assert res[r]["gathered_ok"]
+    # partition: every edge exactly once, owned by the rank whose node block holds its destination
+    src, dst = res[0]["edges"]
+    seen = np.concatenate([ids for _, _, ids in res[0]["parts"]])
+    assert np.array_equal(np.sort(seen), np.arange(len(dst)))
+    for lo, hi, ids in res[0]["parts"]:
+        assert ((dst[ids] >= lo) & (dst[ids] < hi)).all()
+        assert np.all(np.diff(ids) > 0)           # original relative order kept
+    assert res[0]["parts"][0][0] == 0 and res[0]["parts"][-1][1] == 23
+
+
+def test_block_range_covers_everything():
+    for n in (0, 1, 7, 14541):
+        for ws in (1, 2, 3, 8):
+            blocks = [parallel.block_range(n, r, ws) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
