@@ -54,7 +54,7 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=100, log=None):
+def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=100, log=None, shape="FB15k-237"):
     """Times oracle/kgvae_oracle.py (the CPU restatement of the reference path) on a bounded
     sample: the reference's default step (20 000 sampled edges of the same graph, h=500, 100
     blocks) and `eval_queries` test triples in both directions against all 14 541 entities."""
@@ -65,7 +65,7 @@ def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=10
     spec.loader.exec_module(datasets)          # synthetic triples only; no kernels, no package import
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    data = datasets.synthetic_kg("FB15k-237", seed=0)
+    data = datasets.synthetic_kg(shape, seed=0)
     params = O.init_params(data.num_nodes, H, data.num_rels, BASES, MOG_K, n_flows, seed=0)
     for p in params.values():
         p.requires_grad_(True)
@@ -102,20 +102,21 @@ def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=10
             "eval_triples_per_s": eval_queries / eval_dt,
             "sample": f"reference default step: {sample_edges} sampled edges ({sample_edges * (NEG + 1)} scored "
                       f"triplets) of the same graph, fwd+loss+bwd, {len(times)} timed steps; eval: "
-                      f"{eval_queries} test triples x 2 directions x 14541 candidates"}
+                      f"{eval_queries} test triples x 2 directions x {data.num_nodes} candidates"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_oracle_rates(args.steps, args.warmup, args.n_flows, log=lambda m: print(m, file=sys.stderr))
+    shape = "wn18" if args.workload.startswith("wn18") else "FB15k-237"
+    r = cpu_oracle_rates(args.steps, args.warmup, args.n_flows, log=lambda m: print(m, file=sys.stderr), shape=shape)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["train_edges_per_s"], "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fb15k237-full", "n_flows": args.n_flows, "h": H, "bases": BASES},
+        "config": {"workload": args.workload, "n_flows": args.n_flows, "h": H, "bases": BASES},
         "cpu_baseline": {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"],
                          "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["train_edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0,
@@ -192,8 +193,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
 
-    data = K.datasets.synthetic_kg("FB15k-237", seed=0)
-    batch = len(data.train) if args.workload == "fb15k237-full" else 20000
+    shape = "wn18" if args.workload.startswith("wn18") else "FB15k-237"
+    data = K.datasets.synthetic_kg(shape, seed=0)
+    batch = 20000 if args.workload.endswith("-step") else len(data.train)
     torch.manual_seed(0)
     model = K.LinkPredict(K.KGVAE, data.num_nodes, H, data.num_rels, num_bases=BASES, dropout=DROPOUT,
                           use_cuda=True, reg_param=REG, kl_param=KL, k=MOG_K, n_flows=args.n_flows).to(dev)
@@ -362,7 +364,7 @@ def run_gpu(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_rates(2, 1, args.n_flows, log=log)
+        r = cpu_oracle_rates(2, 1, args.n_flows, log=log, shape=shape)
         cpu = {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"], "eval_triples_per_s": r["eval_triples_per_s"]}
 
@@ -397,10 +399,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fb15k237-full", choices=["fb15k237-full", "fb15k237-step"])
+    ap.add_argument("--workload", default="fb15k237-full",
+                    choices=["fb15k237-full", "fb15k237-step", "wn18-full", "wn18-step"],
+                    help="fb15k237-full is the headline (BASELINE.json configs[1]); wn18-* with --n-flows 3 is configs[2]")
     ap.add_argument("--n-flows", type=int, default=0)
+    ap.add_argument("--bases", type=int, default=None,
+                    help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
+                         "36 directed relation types, which does not divide 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global BASES
+    BASES = args.bases if args.bases else (25 if args.workload.startswith("wn18") else 100)
     if args.impl == "reference":
         run_reference(args)
     else:

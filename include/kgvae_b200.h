@@ -100,6 +100,27 @@ int kg_bdd_rel_bwd(const float* x, const float* dagg, const void* rel_pack, int 
                    const float* w_bwd, int num_bases, int si, int so, float* dx, float* dweight,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * a4  RelGraphConv, regularizer="basis" (entity classification)
+ * replaces: dgl.nn.pytorch.RelGraphConv("basis").forward as constructed at
+ *           kgvae/entity_classify.py:30-43 (W_r = sum_b w_comp[r,b] V_b; V [NB, in, out])
+ * Integer node-id features (in = num_nodes): msg_e = norm_e * sum_b coef[r,b] V[b, id_e, :] without
+ * ever forming the [R, in, out] table (coef NULL: NB == R and msg_e = norm_e * V[r, id_e, :]).
+ * Dense features: msg_e = norm_e * x[src] @ W_r with W [R, in, out] composed by the caller (GEMM).
+ * `out` must hold the self-loop term (or zeros) on entry; gradients are accumulated into
+ * zero-filled buffers.  ids: optional int32 [n_src] row map (the 1-D feature tensor), NULL = identity.
+ * ---------------------------------------------------------------------------------- */
+int kg_basis_id_fwd(const float* V, const float* coef, const int32_t* ids, const int32_t* row_ptr,
+                    const void* fwd_pack, int n_dst, int n_in, int num_bases, int out_feat, float* out,
+                    void* stream);
+int kg_basis_id_bwd(const float* V, const float* coef, const int32_t* ids, const float* g,
+                    const void* rel_pack, int n_edges, int n_in, int num_bases, int out_feat,
+                    float* dV, float* dcoef, void* stream);
+int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int in_feat,
+                       int out_feat, float* out, void* stream);
+int kg_basis_dense_bwd(const float* x, const float* g, const void* rel_pack, int n_edges, const float* W,
+                       int in_feat, int out_feat, float* dx, float* dW, void* stream);
+
 /* out = dropout(act(agg + bias + loop)) tail of RelGraphConv.forward; backward of the same.
  * act: 0 identity, 1 relu.  drop_mask: [n, dim] keep-mask already scaled by 1/(1-p), or NULL. */
 int kg_act_dropout_bwd(const float* grad_out, const float* out, const float* drop_mask, int act,

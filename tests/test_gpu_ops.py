@@ -191,6 +191,78 @@ def test_bdd_layer_fwd_bwd(n, e, r, B, si, so, act):
         assert_close(a.grad, b.grad, RTOL, f"bdd {name}")
 
 
+@pytest.mark.parametrize("kind,n,e,r,nb,fin,fout,loop", [("dense", 80, 700, 6, 3, 10, 11, True), ("dense", 80, 700, 5, 5, 16, 8, False),
+                                                      ("dense", 50, 400, 9, 4, 300, 70, True), ("ids", 90, 900, 7, 3, 90, 10, True),
+                                                      ("ids", 90, 900, 6, 6, 90, 12, False), ("ids", 40, 0, 3, 2, 40, 5, True)])
+def test_basis_layer_fwd_bwd(kind, n, e, r, nb, fin, fout, loop):
+    """RelGraphConv("basis") on dense and on integer-id features (kgvae/entity_classify.py:30-43)."""
+    src, dst, et, norm = _rand_graph(5, n, e, r)
+    g = torch.Generator().manual_seed(n + e + nb)
+    V = (torch.randn(nb, fin, fout, generator=g) * 0.3).requires_grad_(True)
+    wc = torch.randn(r, nb, generator=g).requires_grad_(True) if nb < r else None
+    lw = (torch.randn(fin, fout, generator=g) * 0.2).requires_grad_(True) if loop else None
+    bias = torch.randn(fout, generator=g).requires_grad_(True)
+    mask = (torch.rand(n, fout, generator=g) < 0.8).float() / 0.8
+    gout = torch.randn(n, fout, generator=g)
+    x = torch.randperm(n, generator=g) if kind == "ids" else torch.randn(n, fin, generator=g).requires_grad_(True)
+    graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
+    want = O.rgcn_basis_layer(x, graph, V, wc, bias, lw, torch.relu, mask)
+    want.backward(gout)
+
+    layer = K.RelGraphConv(fin, fout, r, "basis", nb, activation=torch.relu, self_loop=loop, dropout=0.0).to(DEV)
+    with torch.no_grad():
+        layer.weight.copy_(V)
+        layer.h_bias.copy_(bias)
+        if wc is not None:
+            layer.w_comp.copy_(wc)
+        if loop:
+            layer.loop_weight.copy_(lw)
+    layer.dropout_mask = mask.to(DEV)
+    gr = K.Graph()
+    gr.add_nodes(n)
+    gr.add_edges(src, dst)
+    xc = x.to(DEV) if kind == "ids" else x.detach().to(DEV).requires_grad_(True)
+    out = layer(gr, xc, torch.from_numpy(et).to(DEV), torch.from_numpy(norm.reshape(-1, 1)).to(DEV))
+    out.backward(gout.to(DEV))
+    assert_close(out, want, RTOL, "basis out")
+    assert_close(layer.weight.grad, V.grad, RTOL, "basis dV")
+    assert_close(layer.h_bias.grad, bias.grad, RTOL, "basis dbias")
+    if wc is not None:
+        assert_close(layer.w_comp.grad, wc.grad, RTOL, "basis dw_comp")
+    if loop:
+        assert_close(layer.loop_weight.grad, lw.grad, RTOL, "basis dloop")
+    if kind == "dense":
+        assert_close(xc.grad, x.grad, RTOL, "basis dx")
+
+
+def test_entity_classify_model_runs():
+    from gcn_vae_b200 import entity_classify as EC
+    data = EC.synthetic_graph("toy", seed=1)
+    g = K.Graph()
+    g.add_nodes(data.num_nodes)
+    g.add_edges(data.edge_src, data.edge_dst)
+    torch.manual_seed(0)
+    model = EC.EntityClassify(len(g), 10, data.num_classes, data.num_rels, num_bases=4, num_hidden_layers=0,
+                              dropout=0.0, use_self_loop=True, use_cuda=True).to(DEV)
+    feats = model.create_features()
+    et = torch.from_numpy(data.edge_type).to(DEV)
+    en = torch.from_numpy(data.edge_norm).unsqueeze(1).to(DEV)
+    logits = model(g, feats, et, en)
+    loss = torch.nn.functional.cross_entropy(logits[torch.from_numpy(data.train_idx).to(DEV)],
+                                             torch.from_numpy(data.labels).to(DEV)[torch.from_numpy(data.train_idx).to(DEV)])
+    loss.backward()
+    # same model on the oracle
+    p = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    graph = {"num_nodes": data.num_nodes, "src": data.edge_src, "dst": data.edge_dst, "etype": data.edge_type,
+             "edge_norm": data.edge_norm.reshape(-1, 1)}
+    h = O.rgcn_basis_layer(torch.arange(data.num_nodes), graph, p["layers.0.weight"], p["layers.0.w_comp"],
+                           p["layers.0.h_bias"], p["layers.0.loop_weight"], torch.relu)
+    h = O.rgcn_basis_layer(h, graph, p["layers.1.weight"], p["layers.1.w_comp"], p["layers.1.h_bias"],
+                           p["layers.1.loop_weight"], lambda t: torch.softmax(t, dim=1))
+    assert_close(logits, h, RTOL, "entity classify logits")
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in model.parameters())
+
+
 def test_relgraphconv_module_matches_shim_semantics():
     """Module-level call with DGL's signature, no self loop / no bias / generic activation."""
     n, e, r, B = 40, 300, 5, 4
