@@ -48,6 +48,8 @@ class LinkPredict(nn.Module):
 
     def get_loss(self, g, embed, triplets, labels):
         """(loss, predict_loss, kl, mmd) as in link_predict.py:71-92."""
+        if getattr(g, "partition", None) is not None:
+            return self._get_loss_partitioned(g.partition, embed, triplets, labels)
         trip = ops.as_i32(triplets, embed.device)
         lab = torch.as_tensor(labels, dtype=torch.float32, device=embed.device)
         predict_loss = ops.DistMultBceFn.apply(embed, self.w_relation, trip, lab, self._flow_shift())
@@ -57,6 +59,35 @@ class LinkPredict(nn.Module):
         mmd = self.encoder.get_mmd(embed) if self.mmd_param > 0 else zero()
         loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl + self.mmd_param * mmd
         return loss, predict_loss, kl, mmd
+
+
+    def _get_loss_partitioned(self, part, embed, triplets, labels):
+        """Destination-partitioned form: ``embed`` holds this rank's rows of z, ``triplets`` (global
+        ids) / ``labels`` are this rank's share of the scored triplets.  Every term is scaled so
+        that the SUM over ranks of the returned loss is the reference's loss; gradients of
+        replicated parameters are then summed over ranks (parallel.allreduce_sum_grads)."""
+        from . import parallel
+        dev = embed.device
+        trip = ops.as_i32(triplets, dev)
+        lab = torch.as_tensor(labels, dtype=torch.float32, device=dev)
+        counts = torch.tensor([float(trip.shape[0])], device=dev)
+        torch.distributed.all_reduce(counts, group=part.group)
+        z_full = parallel.AllGatherRowsFn.apply(embed, part)
+        predict_loss = ops.DistMultBceFn.apply(z_full, self.w_relation, trip, lab, self._flow_shift())
+        predict_loss = predict_loss * (trip.shape[0] / float(counts.item()))
+        frac = part.n_local / part.n_global
+        reg_loss = ops.MeanSquareFn.apply(embed) * frac + ops.MeanSquareFn.apply(self.w_relation) / part.world_size
+        zero = lambda: torch.zeros(1, device=dev)
+        if self.kl_param > 0:
+            kl = ops.KlMogFn.apply(embed, self.encoder.z_mean, self.encoder.z_sigma, self.encoder.z_pre) * frac
+            if self.encoder.flow_log_prob is not None:
+                kl = kl + self.encoder.flow_log_prob / part.world_size
+        else:
+            kl = zero()
+        if self.mmd_param > 0:
+            raise NotImplementedError("the MMD term is not available in destination-partitioned training")
+        loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl
+        return loss, predict_loss, kl, zero()
 
 
 def node_norm_to_edge_norm(g, node_norm):

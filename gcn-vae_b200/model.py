@@ -83,7 +83,12 @@ class KGVAE(nn.Module):
                 if isinstance(flow, MADE):      # PermuteLayer contributes zeros
                     log_det_sum = log_det if log_det_sum is None else log_det_sum + log_det
             self.log_det_sum = log_det_sum
-            self.flow_log_prob = torch.mean(log_det_sum)
+            part = getattr(g, "partition", None)
+            if part is None:
+                self.flow_log_prob = torch.mean(log_det_sum)
+            else:                     # mean over ALL nodes: local sums, summed over the ranks
+                from . import parallel
+                self.flow_log_prob = parallel.AllReduceSumFn.apply(log_det_sum.sum(), part.group) / part.n_global
         return z
 
     def get_kl(self, z):

@@ -71,6 +71,7 @@ class RelGraphConv(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("kgvae_b200.RelGraphConv runs on CUDA only (no CPU fallback)")
         act_code, post = _classify_activation(self.activation)
+        part = getattr(g, "partition", None)
         mask = self._keep_mask(x.shape[0], x.device)
         gi = g.index_for(etypes, norm, self.num_rels)
         h_bias = self.h_bias if self.bias else None
@@ -78,11 +79,16 @@ class RelGraphConv(nn.Module):
         if self.regularizer == "bdd":
             if x.dtype == torch.int64 and x.dim() == 1:
                 raise TypeError("Block decomposition does not allow integer ID feature.")
+            lo, n_dst = -1, -1
+            if part is not None:      # destination-partitioned: gather every node's features first
+                from . import parallel
+                x = parallel.AllGatherRowsFn.apply(x, part)
+                lo, n_dst = part.lo, part.n_local
             if post is None:
                 return ops.BddConvFn.apply(x, self.weight, loop_w, h_bias, gi, self.num_bases,
-                                           act_code, mask)
+                                           act_code, mask, lo, n_dst)
             h = ops.BddConvFn.apply(x, self.weight, loop_w, h_bias, gi, self.num_bases,
-                                    _ACT_IDENTITY, None)
+                                    _ACT_IDENTITY, None, lo, n_dst)
             h = post(h)
             return h if mask is None else h * mask
         from . import basis   # entity-classification layers (config 4)

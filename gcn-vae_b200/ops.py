@@ -149,10 +149,14 @@ class EmbeddingFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 class BddConvFn(torch.autograd.Function):
     """One RelGraphConv(bdd) layer: out = dropout(act(sum_e norm_e W_{r_e} x_src + h_bias +
-    x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59."""
+    x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59.
+
+    ``dst_lo``/``n_dst`` select the destination-partitioned form: ``x`` then holds the features of
+    ALL nodes (edge sources are global ids), the layer produces rows for the ``n_dst`` nodes owned
+    by this rank (edge destinations are local ids) and the self-loop uses ``x[dst_lo:dst_lo+n_dst]``."""
 
     @staticmethod
-    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask):
+    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask, dst_lo=-1, n_dst=-1):
         x, weight = _c(x), _c(weight)
         dev = x.device
         n, in_feat = x.shape
@@ -160,13 +164,19 @@ class BddConvFn(torch.autograd.Function):
         si = in_feat // num_bases
         so = weight.shape[1] // (num_bases * si)
         out_feat = num_bases * so
-        if n != gi.n_nodes:
-            raise RuntimeError(f"RelGraphConv: {n} feature rows for a graph of {gi.n_nodes} nodes")
+        if dst_lo < 0:
+            if n != gi.n_nodes:
+                raise RuntimeError(f"RelGraphConv: {n} feature rows for a graph of {gi.n_nodes} nodes")
+            n_out, x_own = n, x
+        else:
+            if dst_lo + n_dst > n:
+                raise RuntimeError("RelGraphConv: owned node block lies outside the gathered features")
+            n_out, x_own = n_dst, x[dst_lo:dst_lo + n_dst]
         w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
         w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
         L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
                L.f32(w_bwd), L.stream())
-        agg = torch.zeros((n, out_feat), dtype=torch.float32, device=dev)
+        agg = torch.zeros((n_out, out_feat), dtype=torch.float32, device=dev)
         L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_fwd), num_bases, si, so,
                L.f32(agg), L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
         out = torch.empty_like(agg)
@@ -174,12 +184,13 @@ class BddConvFn(torch.autograd.Function):
         mask = None if drop_mask is None else _c(drop_mask)
         if loop_weight is not None:
             loop_weight = _c(loop_weight)
-            gemm(x, loop_weight, out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
+            gemm(x_own, loop_weight, out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
         else:
             epilogue_only(out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
         ctx.save_for_backward(x, weight, loop_weight, out, mask, w_bwd)
         ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
         ctx.has_bias = h_bias is not None
+        ctx.dst_lo, ctx.n_out = dst_lo, n_out
         return out
 
     @staticmethod
@@ -187,7 +198,7 @@ class BddConvFn(torch.autograd.Function):
         x, weight, loop_weight, out, mask, w_bwd = ctx.saved_tensors
         gi, B, si, so = ctx.gi, ctx.num_bases, ctx.si, ctx.so
         g = _c(g)
-        n = x.shape[0]
+        x_own = x if ctx.dst_lo < 0 else x[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
         gpre = torch.empty_like(out)
         L.call("kg_act_dropout_bwd", L.f32(g), L.f32(out), L.f32(mask), ctx.act, out.numel(),
                L.f32(gpre), L.stream())
@@ -198,15 +209,16 @@ class BddConvFn(torch.autograd.Function):
             L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_bwd),
                    B, si, so, L.f32(dx), L.f32(dw), L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
             if dx is not None and loop_weight is not None:
-                gemm(gpre, loop_weight, dx, trans_b=True, accumulate=True)
+                dx_own = dx if ctx.dst_lo < 0 else dx[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
+                gemm(gpre, loop_weight, dx_own, trans_b=True, accumulate=True)
             if not ctx.needs_input_grad[1]:
                 dw = None
         if loop_weight is not None and ctx.needs_input_grad[2]:
             dloop = torch.empty_like(loop_weight)
-            gemm(x, gpre, dloop, trans_a=True)
+            gemm(x_own, gpre, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = colsum(gpre)
-        return dx, dw, dloop, dbias, None, None, None, None
+        return dx, dw, dloop, dbias, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------

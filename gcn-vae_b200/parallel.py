@@ -95,3 +95,72 @@ def allgather_rows(local_rows, num_rows, group=None):
     out = [torch.empty_like(buf) for _ in range(ws)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# destination-partitioned training: differentiable collectives and the partition descriptor
+# ---------------------------------------------------------------------------------------------
+class Partition:
+    """Rank-local view of a destination-partitioned graph: this rank owns nodes [lo, hi) of
+    ``n_global`` and every edge whose destination is in that block (edge sources keep global ids,
+    destinations are local: dst - lo).  Attach to the graph object as ``g.partition``; RelGraphConv,
+    KGVAE and LinkPredict then insert the all-gathers / reductions below."""
+
+    def __init__(self, lo, hi, n_global, group=None):
+        self.lo, self.hi, self.n_global, self.group = int(lo), int(hi), int(n_global), group
+        self.n_local = self.hi - self.lo
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+
+class AllGatherRowsFn(torch.autograd.Function):
+    """x_local [n_local, d] -> x_full [n_global, d]; backward: reduce-scatter(sum) of the gradient -
+    every rank's loss depends on every row it gathered."""
+
+    @staticmethod
+    def forward(ctx, x_local, part):
+        ctx.part = part
+        return allgather_rows(x_local.contiguous(), part.n_global, part.group)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        part = ctx.part
+        g_full = g_full.contiguous()
+        dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=part.group)   # blocks differ by a row: sum, then slice
+        return g_full[part.lo:part.hi].clone(), None
+
+
+class AllReduceSumFn(torch.autograd.Function):
+    """sum over ranks of a tensor every rank then uses in its own loss; backward sums the upstream
+    gradients of all ranks."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def allreduce_sum_grads(params, group=None):
+    """Partitioned training: every rank holds a partial gradient of the replicated parameters;
+    the total is their SUM (one flattened all-reduce)."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n

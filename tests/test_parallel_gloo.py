@@ -66,6 +66,17 @@ def _worker(rank, port, out):
         res["gathered_ok"] = bool(torch.equal(full, feats))
         res["parts"] = [(p["lo"], p["hi"], p["edge_ids"]) for p in parts]
         res["edges"] = (src, dst)
+
+        # --- differentiable collectives of the partitioned step ---------------------------------
+        part = parallel.Partition(mine["lo"], mine["hi"], N)
+        xl = (feats[mine["lo"]:mine["hi"]] * 0.1).clone().requires_grad_(True)
+        wgt = torch.arange(N * 3, dtype=torch.float32).view(N, 3) * (rank + 1)      # rank-specific loss
+        full2 = parallel.AllGatherRowsFn.apply(xl, part)
+        s_loc = xl.sum()
+        s_all = parallel.AllReduceSumFn.apply(s_loc, None)
+        ((full2 * wgt).sum() + s_all * (rank + 2.0)).backward()
+        res["gather_grad"] = xl.grad.clone()
+        res["block"] = (mine["lo"], mine["hi"])
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -86,6 +97,12 @@ def test_two_rank_host_logic():
         assert torch.equal(res[r]["grads"][2], torch.zeros(2, 2))
         assert torch.equal(res[r]["ranks"].long(), res[r]["want_ranks"])
         assert res[r]["gathered_ok"]
+    # all-gather backward = sum over ranks of the gradient rows; all-reduce backward = sum of upstream grads
+    wsum = torch.arange(23 * 3, dtype=torch.float32).view(23, 3) * sum(r + 1 for r in range(WORLD))
+    for r in range(WORLD):
+        lo, hi = res[r]["block"]
+        want = wsum[lo:hi] + sum(q + 2.0 for q in range(WORLD))
+        assert torch.allclose(res[r]["gather_grad"], want)
     # partition: every edge exactly once, owned by the rank whose node block holds its destination
     src, dst = res[0]["edges"]
     seen = np.concatenate([ids for _, _, ids in res[0]["parts"]])
