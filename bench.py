@@ -179,6 +179,85 @@ def algorithmic_bytes(tag, shp):
     return None
 
 
+def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edges=32_000_000, iters=5):
+    """RGCN(bdd) message passing at the ogbl-wikikg2 shape (BASELINE.json configs[4]: 2.5 M entities,
+    2 x 535 relation types, 2 x 16 M directed edges, h = 500, 100 blocks) on ONE GPU: the regime the
+    HBM-roofline target of north_star is about - every feature matrix (5 / 10 GB) is far larger than
+    L2, so gathered rows really stream from HBM.  Times the four message-passing launches of one
+    encoder (layer 1: 500 -> 500, layer 2: 500 -> 1000; forward and fused dX + dW backward) with CUDA
+    events; algorithmic bytes per SURVEY.md 8(d) / DESIGN.md section 4."""
+    import gcn_vae_b200 as K
+    from gcn_vae_b200 import _lib as L
+    from gcn_vae_b200 import ops
+    out = {"shape": {"nodes": n_nodes, "etypes": n_etypes, "edges": n_edges, "h": H, "bases": BASES},
+           "regime": "streaming (x, agg, dagg, dx are 5-10 GB each; L2 is 126 MB)", "kernels": {}}
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for graph_kind in ("uniform", "skewed"):
+        if graph_kind == "uniform":
+            src = torch.randint(0, n_nodes, (n_edges,), device=dev, generator=gen, dtype=torch.int32)
+            dst = torch.randint(0, n_nodes, (n_edges,), device=dev, generator=gen, dtype=torch.int32)
+            et = torch.randint(0, n_etypes, (n_edges,), device=dev, generator=gen, dtype=torch.int32)
+        else:       # heavy-tailed degrees and relation frequencies (real KGs): id = floor(n * u^3)
+            pw = lambda n: (torch.rand(n_edges, device=dev, generator=gen).pow(3) * n).to(torch.int32).clamp_(max=n - 1)
+            src, dst, et = pw(n_nodes), pw(n_nodes), pw(n_etypes)
+        deg = torch.bincount(dst.long(), minlength=n_nodes).clamp_(min=1).float()
+        norm = (1.0 / deg)[dst.long()].contiguous()
+        t0 = time.perf_counter()
+        gi = ops.graph_index(src, dst, et, norm, n_nodes, n_etypes)
+        torch.cuda.synchronize()
+        index_ms = (time.perf_counter() - t0) * 1e3
+        x = torch.randn(n_nodes, H, device=dev, generator=gen)
+        res = {}
+        for si, so in ((H // BASES, H // BASES), (H // BASES, 2 * H // BASES)):
+            in_f, out_f = BASES * si, BASES * so
+            weight = torch.randn(n_etypes, BASES * si * so, device=dev, generator=gen) * 0.05
+            w_fwd = w_bwd = None
+            if L.lib().kg_bdd_layouts_needed(BASES, si, so):
+                w_fwd = torch.empty((n_etypes, si, out_f), device=dev)
+                w_bwd = torch.empty((n_etypes, so, in_f), device=dev)
+                L.call("kg_bdd_weight_layouts", L.f32(weight), n_etypes, BASES, si, so, L.f32(w_fwd), L.f32(w_bwd), L.stream())
+            agg = torch.empty((n_nodes, out_f), device=dev)
+            dx = torch.empty((n_nodes, in_f), device=dev)
+            dw = torch.empty_like(weight)
+            p_fwd = ops._rel_order(gi, 0, n_nodes, 4 * out_f)
+            p_bwd = ops._rel_order(gi, 1, n_nodes, 8 * in_f)
+
+            def fwd():
+                L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(p_fwd), n_edges, L.f32(weight), L.f32(w_fwd), BASES, si, so, L.f32(agg),
+                       ops.HINT_STREAM_X, L.stream())
+
+            def bwd():
+                L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(agg), L.i32(p_bwd), n_edges, L.f32(weight), L.f32(w_bwd), BASES, si, so,
+                       L.f32(dx), L.f32(dw), ops.HINT_STREAM_D, L.stream())
+
+            for name, fn, zero in ((f"kg_bdd_rel_fwd[{si}x{so}]", fwd, (agg,)), (f"kg_bdd_rel_bwd[{si}x{so}]", bwd, (dx, dw))):
+                ms = []
+                for it in range(iters + 2):
+                    for z in zero:
+                        z.zero_()                       # outside the timed events; also sweeps L2 (>= 5 GB)
+                    if name.startswith("kg_bdd_rel_bwd") and it == 0:
+                        agg.normal_(generator=gen)      # a dense upstream gradient
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    b.synchronize()
+                    if it >= 2:
+                        ms.append(a.elapsed_time(b))
+                t = sum(ms) / len(ms)
+                ab = algorithmic_bytes(name, {"N": n_nodes, "E": n_edges, "S": 0, "R2": n_etypes, "R": n_etypes // 2})
+                res[name] = {"ms": t, "algorithmic_bytes": ab, "achieved_gbs": ab / t / 1e6,
+                             "frac_of_hbm_peak": ab / t / 1e6 / pk["hbm_gbs"], "edges_per_s": n_edges / t * 1e3}
+                log(f"  [streaming/{graph_kind}] {name:26s} {t:8.2f} ms  {ab / t / 1e6:8.0f} GB/s  "
+                    f"{100 * ab / t / 1e6 / pk['hbm_gbs']:5.1f}% of measured HBM peak")
+            del agg, dx, dw, weight, w_fwd, w_bwd
+        out["kernels"][graph_kind] = res
+        out.setdefault("graph_index_ms", {})[graph_kind] = index_ms
+        del gi, x, src, dst, et, norm
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import gcn_vae_b200 as K
@@ -362,6 +441,12 @@ def run_gpu(args):
                              "of the fp32-exact two-term fp16 split (3 products, K padded to 512); the "
                              "launch time includes the operand split kernels; peak = measured bf16 sustained"}
 
+    streaming = None
+    if world == 1 and not args.no_streaming:
+        model = opt = None
+        torch.cuda.empty_cache()
+        streaming = streaming_layer_bench(dev, pk, log)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_oracle_rates(2, 1, args.n_flows, log=log, shape=shape)
@@ -387,6 +472,7 @@ def run_gpu(args):
                  "e2e_value": T * args.steps / (ms_eval_e2e * 1e-3), "roofline": eval_roof},
         "scored_triplets_per_s": S * world * args.steps / (ms_dev * 1e-3),
         "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
+        "rgcn_streaming": streaming,
     }
     print(json.dumps(line))
     if world > 1:
@@ -407,6 +493,8 @@ def main():
                     help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
                          "36 directed relation types, which does not divide 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true",
+                    help="skip the wikikg2-shaped message-passing leg (HBM-streaming regime, N=1 only)")
     args = ap.parse_args()
     global BASES
     BASES = args.bases if args.bases else (25 if args.workload.startswith("wn18") else 100)

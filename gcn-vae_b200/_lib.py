@@ -25,8 +25,11 @@ _SIGNATURES = {
     "kg_embedding_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_embedding_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_bdd_weight_layouts": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
-    "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
-    "kg_bdd_rel_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
+    "kg_bdd_rel_bwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "kg_bdd_layouts_needed": (_I, [_I, _I, _I]),
+    "kg_graph_rel_tiled_workspace_bytes": (_Z, [_I]),
+    "kg_graph_rel_tiled": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "kg_basis_id_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "kg_basis_id_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "kg_basis_dense_fwd": (_I, [_P, _P, _I, _P, _I, _I, _P, _P]),
@@ -79,7 +82,7 @@ def lib():
 
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
-    "kg_graph_build": 26, "kg_graph_index": 18, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2,
+    "kg_graph_build": 26, "kg_graph_index": 18, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2,
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
 }
 launches = 0          # running count of kernels launched through this binding

@@ -215,6 +215,58 @@ extern "C" int kg_graph_index(const int32_t* e_src, const int32_t* e_dst, const 
                      kg_stream(stream));
 }
 
+// ------------------------------------------------------------------------------------------
+// node-tiled relation-major list (graphs whose feature matrices exceed L2)
+// ------------------------------------------------------------------------------------------
+__global__ void tiled_rel_keys(const int* __restrict__ e_node, const int* __restrict__ e_type, int E,
+                               int tile_nodes, int type_bits, unsigned* keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  keys[i] = ((unsigned)(e_node[i] / tile_nodes) << type_bits) | (unsigned)e_type[i];
+}
+
+extern "C" size_t kg_graph_rel_tiled_workspace_bytes(int n_edges) {
+  int E = n_edges > 0 ? n_edges : 1;
+  size_t a = 0;
+  cub::DeviceRadixSort::SortPairs((void*)nullptr, a, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr,
+                                  (int*)nullptr, E);
+  return 4 * kg_align_up((size_t)E * 4) + kg_align_up(a + 256) + 1024;
+}
+
+extern "C" int kg_graph_rel_tiled(const int32_t* e_src, const int32_t* e_dst, const int32_t* e_type,
+                                  const float* e_norm, int n_edges, int num_nodes, int num_etypes,
+                                  int tile_nodes, int by_src, void* pack_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  KG_REQUIRE(n_edges >= 0 && num_nodes > 0 && num_etypes > 0 && tile_nodes > 0, "graph_rel_tiled: bad sizes");
+  const int E = n_edges;
+  if (E == 0) return KG_OK;
+  const int tiles = (num_nodes + tile_nodes - 1) / tile_nodes;
+  const int type_bits = bits_for(num_etypes), tile_bits = bits_for(tiles);
+  KG_REQUIRE(type_bits + tile_bits <= 32, "graph_rel_tiled: tile and relation ids exceed a 32-bit key");
+  cudaStream_t st = kg_stream(stream);
+  KgArena ws(workspace, workspace_bytes);
+  unsigned* k_in = ws.take<unsigned>(E);
+  unsigned* k_out = ws.take<unsigned>(E);
+  int* v_in = ws.take<int>(E);
+  int* v_out = ws.take<int>(E);
+  size_t temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs((void*)nullptr, temp_bytes, k_in, k_out, v_in, v_out, E);
+  void* temp = ws.take<char>(temp_bytes + 256);
+  if (!k_in || !k_out || !v_in || !v_out || !temp)
+    return kg_fail(KG_ERR_WORKSPACE, "graph_rel_tiled: workspace too small");
+  const int gridE = kg_div_up(E, kThreads);
+  tiled_rel_keys<<<gridE, kThreads, 0, st>>>(by_src ? e_src : e_dst, e_type, E, tile_nodes, type_bits, k_in);
+  KG_LAUNCH_OK();
+  iota<<<gridE, kThreads, 0, st>>>(v_in, E);
+  KG_LAUNCH_OK();
+  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, v_in, v_out, E, 0, type_bits + tile_bits,
+                                          st));
+  fill_pack<<<gridE, kThreads, 0, st>>>(v_out, e_src, e_dst, e_type, e_norm, nullptr, E, 2,
+                                        reinterpret_cast<int4*>(pack_out));
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
 __global__ void patch_pack_norm(int4* fwd, int4* bwd, int4* rel, const float* node_norm, int E) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;

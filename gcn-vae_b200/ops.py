@@ -31,7 +31,7 @@ class GraphIndex:
     """Device-resident edge orderings for one (graph, etypes, norm) triple."""
 
     __slots__ = ("n_nodes", "n_edges", "n_etypes", "row_ptr", "fwd_pack", "col_ptr", "bwd_pack",
-                 "rel_ptr", "rel_pack", "e_src", "e_dst", "e_type", "node_norm")
+                 "rel_ptr", "rel_pack", "e_src", "e_dst", "e_type", "node_norm", "e_norm", "_tiled")
 
     def __init__(self, n_nodes, n_edges, n_etypes, device):
         self.n_nodes, self.n_edges, self.n_etypes = int(n_nodes), int(n_edges), int(n_etypes)
@@ -42,7 +42,36 @@ class GraphIndex:
         self.fwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
         self.bwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
         self.rel_pack = torch.empty((max(n_edges, 1), 4), **i32)
-        self.e_src = self.e_dst = self.e_type = self.node_norm = None
+        self.e_src = self.e_dst = self.e_type = self.node_norm = self.e_norm = None
+        self._tiled = {}
+
+    def tiled_rel_pack(self, by_src, tile_nodes):
+        """kg_graph_rel_tiled: relation-major records grouped by node tile (built once, cached)."""
+        key = (int(bool(by_src)), int(tile_nodes))
+        if key not in self._tiled:
+            if self.e_norm is None and self.node_norm is not None:
+                self.e_norm = self.node_norm[self.e_dst.long()].contiguous()
+            pack = torch.empty_like(self.rel_pack)
+            ws = L.workspace(L.lib().kg_graph_rel_tiled_workspace_bytes(self.n_edges), pack.device)
+            L.call("kg_graph_rel_tiled", L.i32(self.e_src), L.i32(self.e_dst), L.i32(self.e_type),
+                   L.f32(self.e_norm), self.n_edges, self.n_nodes, self.n_etypes, key[1], key[0],
+                   L.i32(pack), L.ptr(ws), ws.numel(), L.stream())
+            self._tiled[key] = pack
+        return self._tiled[key]
+
+
+# Rows that message passing reduces into (agg[dst] forward, x[src] + dx[src] backward) are kept
+# L2-resident: graphs whose reduced matrix exceeds this budget are walked tile by tile.
+L2_TILE_BYTES = 32 << 20
+L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read with evict-first
+HINT_STREAM_X, HINT_STREAM_D = 1, 2
+
+
+def _rel_order(gi, by_src, n_rows, row_bytes):
+    """the relation-major record list to walk for a reduction into ``n_rows`` rows of ``row_bytes``"""
+    if n_rows * row_bytes <= L2_TILE_BYTES or gi.n_edges == 0:
+        return gi.rel_pack
+    return gi.tiled_rel_pack(by_src, max(L2_TILE_BYTES // row_bytes, 256))
 
 
 def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes):
@@ -54,6 +83,7 @@ def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes):
     gi.e_src, gi.e_dst, gi.e_type = e_src, e_dst, e_type
     ws = L.workspace(L.lib().kg_graph_index_workspace_bytes(E), dev)
     norm = None if e_norm is None else _c(e_norm.reshape(-1).to(torch.float32))
+    gi.e_norm = norm
     L.call("kg_graph_index", L.i32(e_src), L.i32(e_dst), L.i32(e_type), L.f32(norm), E, n_nodes,
            n_etypes, L.i32(gi.row_ptr), L.i32(gi.fwd_pack), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
            L.i32(gi.rel_ptr), L.i32(gi.rel_pack), L.ptr(ws), ws.numel(), L.stream())
@@ -172,13 +202,16 @@ class BddConvFn(torch.autograd.Function):
             if dst_lo + n_dst > n:
                 raise RuntimeError("RelGraphConv: owned node block lies outside the gathered features")
             n_out, x_own = n_dst, x[dst_lo:dst_lo + n_dst]
-        w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
-        w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
-        L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
-               L.f32(w_bwd), L.stream())
+        w_fwd = w_bwd = None
+        if L.lib().kg_bdd_layouts_needed(num_bases, si, so):
+            w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
+            w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
+            L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
+                   L.f32(w_bwd), L.stream())
         agg = torch.zeros((n_out, out_feat), dtype=torch.float32, device=dev)
-        L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_fwd), num_bases, si, so,
-               L.f32(agg), L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
+        hints = HINT_STREAM_X if x.numel() * 4 > L2_STREAM_BYTES else 0
+        L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(_rel_order(gi, 0, n_out, 4 * out_feat)), gi.n_edges, L.f32(weight),
+               L.f32(w_fwd), num_bases, si, so, L.f32(agg), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
         out = torch.empty_like(agg)
         bias = None if h_bias is None else _c(h_bias)
         mask = None if drop_mask is None else _c(drop_mask)
@@ -206,8 +239,11 @@ class BddConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
             dw = torch.zeros_like(weight)
-            L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges, L.f32(w_bwd),
-                   B, si, so, L.f32(dx), L.f32(dw), L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
+            # walked by source tile: x[src] and dx[src] stay L2-resident, dagg[dst] is the gathered row
+            pack = _rel_order(gi, 1, x.shape[0], (8 if dx is not None else 4) * x.shape[1])
+            hints = HINT_STREAM_D if gpre.numel() * 4 > L2_STREAM_BYTES else 0
+            L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(gpre), L.i32(pack), gi.n_edges, L.f32(weight), L.f32(w_bwd),
+                   B, si, so, L.f32(dx), L.f32(dw), hints, L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
             if dx is not None and loop_weight is not None:
                 dx_own = dx if ctx.dst_lo < 0 else dx[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
                 gemm(gpre, loop_weight, dx_own, trans_b=True, accumulate=True)

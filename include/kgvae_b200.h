@@ -89,16 +89,38 @@ int kg_embedding_bwd(const float* grad_out, const int32_t* ids, int n, int dim, 
  *   w_bwd [R, so, B*si]: w_bwd[r][o][b*si+i] = weight[r][b][i][o]                     */
 int kg_bdd_weight_layouts(const float* weight, int num_etypes, int num_bases, int si, int so,
                           float* w_fwd, float* w_bwd, void* stream);
-/* Message passing (rgcn_bdd_rel.cu): edges walked in (etype, dst) order - rel_pack - so the
- * block weights of a relation stay in shared memory for a run of edges; messages are accumulated
- * with vector reductions.  agg / dx / dweight must be zero-filled by the caller; dx may be NULL.
+/* Message passing (rgcn_bdd_rel.cu): edges walked in relation-major order - rel_pack from
+ * kg_graph_index, or a node-tiled list from kg_graph_rel_tiled - so that a thread keeps its columns
+ * of the relation's block weights in registers for a run of edges; messages are accumulated with
+ * vector reductions.  agg / dx / dweight must be zero-filled by the caller; dx may be NULL.
  *   fwd:  agg[dst] += norm * blockdiag(W[etype]) x[src]
- *   bwd:  dx[src] += norm * blockdiag(W[etype])^T dagg[dst];  dweight[etype] += norm * x[src] (x) dagg[dst] */
-int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges, const float* w_fwd,
-                   int num_bases, int si, int so, float* agg, void* stream);
+ *   bwd:  dx[src] += norm * blockdiag(W[etype])^T dagg[dst];  dweight[etype] += norm * x[src] (x) dagg[dst]
+ * hints: KG_HINT_STREAM_X / KG_HINT_STREAM_D mark the gathered matrix (x / dagg) as streamed from
+ * HBM (evict-first in L2) so that it does not displace the L2-resident tile being reduced into. */
+#define KG_HINT_STREAM_X 1
+#define KG_HINT_STREAM_D 2
+int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges, const float* weight,
+                   const float* w_fwd, int num_bases, int si, int so, float* agg, int hints, void* stream);
 int kg_bdd_rel_bwd(const float* x, const float* dagg, const void* rel_pack, int n_edges,
-                   const float* w_bwd, int num_bases, int si, int so, float* dx, float* dweight,
-                   void* stream);
+                   const float* weight, const float* w_bwd, int num_bases, int si, int so,
+                   float* dx, float* dweight, int hints, void* stream);
+/* The reference model's block shapes (5x5, 5x10; rgcn_bdd_own.cuh) read `weight` in the DGL layout
+ * directly - a thread owns whole diagonal blocks in registers - and need no derived layout: pass
+ * w_fwd / w_bwd = NULL when this returns 0.  Other shapes need kg_bdd_weight_layouts first. */
+int kg_bdd_layouts_needed(int num_bases, int si, int so);
+
+/* Node-tiled relation-major edge list for graphs whose feature matrices exceed L2 (wikikg2 / AM
+ * shapes; new - the reference has no counterpart, DGL walks edges in insertion order):
+ * records {src, dst, etype, bits(norm)} ordered by (tile(node), etype, original order) where
+ * node = dst (by_src = 0, forward: the rows reduced into are agg[dst]) or src (by_src = 1,
+ * backward: dx[src]) and tile(node) = node / tile_nodes.  One tile's rows stay L2-resident while
+ * its edges are processed, so the per-edge HBM traffic is the gathered row only.
+ * e_norm may be NULL (norm 1).  Limits: bits(num_nodes / tile_nodes) + bits(num_etypes) <= 32. */
+size_t kg_graph_rel_tiled_workspace_bytes(int n_edges);
+int kg_graph_rel_tiled(const int32_t* e_src, const int32_t* e_dst, const int32_t* e_type,
+                       const float* e_norm, int n_edges, int num_nodes, int num_etypes,
+                       int tile_nodes, int by_src, void* pack_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a4  RelGraphConv, regularizer="basis" (entity classification)

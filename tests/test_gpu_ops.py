@@ -191,6 +191,51 @@ def test_bdd_layer_fwd_bwd(n, e, r, B, si, so, act):
         assert_close(a.grad, b.grad, RTOL, f"bdd {name}")
 
 
+@pytest.mark.parametrize("n,e,r,tile,by_src", [(300, 5000, 40, 64, 0), (300, 5000, 40, 64, 1), (50, 400, 6, 1000, 0),
+                                               (1000, 20000, 474, 7, 1), (9, 0, 2, 4, 0)])
+def test_graph_rel_tiled_order_integer_exact(n, e, r, tile, by_src):
+    """kg_graph_rel_tiled: a permutation of the edges ordered by (node tile, etype), stable."""
+    src, dst, et, norm = _rand_graph(5, n, e, r)
+    gi = _index(src, dst, et, norm, n, r)
+    pack = gi.tiled_rel_pack(by_src, tile).cpu().numpy()[:e]
+    key = ((src if by_src else dst) // tile).astype(np.int64) * r + et
+    order = np.argsort(key, kind="stable")
+    want = np.stack([src[order], dst[order], et[order], norm[order].view(np.int32)], axis=1).astype(np.int32)
+    if e:
+        assert np.array_equal(pack, want)
+
+
+@pytest.mark.parametrize("B,si,so", [(100, 5, 5), (100, 5, 10), (50, 10, 10), (24, 4, 4), (16, 8, 8), (8, 5, 5)])
+@pytest.mark.parametrize("tiled", [False, True])
+def test_bdd_layer_fast_shapes_and_tiled_order(B, si, so, tiled, monkeypatch):
+    """The register-resident fast path at the real layer widths (1 and 2 slots per CTA, several
+    relation changes per chunk) and the same layer walked in node-tiled order (L2 budget forced
+    down so that every matrix counts as larger than L2, streaming hints on)."""
+    if tiled:
+        monkeypatch.setattr(ops, "L2_TILE_BYTES", 40 * 4 * B * so)
+        monkeypatch.setattr(ops, "L2_STREAM_BYTES", 0)
+    n, e, r = 300, 6000, 11
+    src, dst, et, norm = _rand_graph(7, n, e, r)
+    g = torch.Generator().manual_seed(B + si)
+    x = torch.randn(n, B * si, generator=g, requires_grad=True)
+    weight = (torch.randn(r, B * si * so, generator=g) * 0.3).requires_grad_(True)
+    loop = torch.randn(B * si, B * so, generator=g) * 0.05
+    bias = torch.randn(B * so, generator=g)
+    gout = torch.randn(n, B * so, generator=g)
+    graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
+    want = O.rgcn_bdd_layer(x, graph, weight, bias, loop, B, None, None)
+    want.backward(gout)
+    gi = _index(src, dst, et, norm, n, r)
+    cx, cw = x.detach().to(DEV).requires_grad_(True), weight.detach().to(DEV).requires_grad_(True)
+    out = ops.BddConvFn.apply(cx, cw, loop.to(DEV), bias.to(DEV), gi, B, 0, None)
+    out.backward(gout.to(DEV))
+    if tiled:
+        assert len(gi._tiled) == 2          # a dst-tiled list (forward) and a src-tiled list (backward)
+    assert_close(out, want, RTOL, "bdd out")
+    assert_close(cx.grad, x.grad, RTOL, "bdd dx")
+    assert_close(cw.grad, weight.grad, RTOL, "bdd dW")
+
+
 @pytest.mark.parametrize("kind,n,e,r,nb,fin,fout,loop", [("dense", 80, 700, 6, 3, 10, 11, True), ("dense", 80, 700, 5, 5, 16, 8, False),
                                                       ("dense", 50, 400, 9, 4, 300, 70, True), ("ids", 90, 900, 7, 3, 90, 10, True),
                                                       ("ids", 90, 900, 6, 6, 90, 12, False), ("ids", 40, 0, 3, 2, 40, 5, True)])
