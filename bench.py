@@ -172,8 +172,9 @@ def algorithmic_bytes(tag, shp):
     if tag.startswith("kg_bdd_rel_bwd"):                # per edge 4*(in+out) + 12, per node 4*in (dx), weights r+w
         si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
         return E * (4 * BASES * (si + so) + 16) + 4 * N * BASES * si + 2 * 4 * R2 * BASES * si * so
-    if tag == "kg_distmult_bce_fwd":                    # 3 rows + record per triplet; g out; dw once
-        return S * (3 * 4 * h + 16 + 4 + 4) + 4 * shp["R"] * h
+    if tag == "kg_distmult_bce_fwd":                    # 3 rows + record per triplet for the score, and
+        # the backward into z in the same pass: one row of gradient into dz[s] and one into dz[o]; dw, dz once
+        return S * (5 * 4 * h + 16 + 4 + 4) + 4 * shp["R"] * h + 4 * N * h
     if tag == "kg_distmult_bwd_dz":                     # each triplet seen from both ends: w row + other row + record
         return 2 * S * (2 * 4 * h + 16 + 4) + 4 * N * h
     return None
@@ -224,11 +225,11 @@ def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edge
 
             def fwd():
                 L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(p_fwd), n_edges, L.f32(weight), L.f32(w_fwd), BASES, si, so, L.f32(agg),
-                       ops.HINT_STREAM_X, L.stream())
+                       ops.HINT_STREAM_X | int(os.environ.get("KG_HINT_EXTRA", "0")), L.stream())
 
             def bwd():
                 L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(agg), L.i32(p_bwd), n_edges, L.f32(weight), L.f32(w_bwd), BASES, si, so,
-                       L.f32(dx), L.f32(dw), ops.HINT_STREAM_D, L.stream())
+                       L.f32(dx), L.f32(dw), ops.HINT_STREAM_D | int(os.environ.get("KG_HINT_EXTRA", "0")), L.stream())
 
             for name, fn, zero in ((f"kg_bdd_rel_fwd[{si}x{so}]", fwd, (agg,)), (f"kg_bdd_rel_bwd[{si}x{so}]", bwd, (dx, dw))):
                 ms = []
@@ -493,12 +494,19 @@ def main():
                     help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
                          "36 directed relation types, which does not divide 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streaming-only", action="store_true",
+                    help="run only the wikikg2-shaped message-passing leg (profiling aid; prints its JSON object)")
     ap.add_argument("--no-streaming", action="store_true",
                     help="skip the wikikg2-shaped message-passing leg (HBM-streaming regime, N=1 only)")
     args = ap.parse_args()
     global BASES
     BASES = args.bases if args.bases else (25 if args.workload.startswith("wn18") else 100)
-    if args.impl == "reference":
+    if args.streaming_only:
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+        print(json.dumps(streaming_layer_bench(dev, peaks(), lambda m: print(m, file=sys.stderr, flush=True),
+                                               iters=max(1, args.steps))))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -54,7 +54,7 @@ _SIGNATURES = {
     "kg_triplet_index_workspace_bytes": (_Z, [_I]),
     "kg_triplet_index": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "kg_distmult_bce_workspace_bytes": (_Z, [_I]),
-    "kg_distmult_bce_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_distmult_bce_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "kg_distmult_bwd_dz": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_rank_workspace_bytes": (_Z, [_I, _I, _I]),

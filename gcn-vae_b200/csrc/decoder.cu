@@ -231,6 +231,7 @@ extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_n
     return KG_OK;
   }
   KgArena ws(workspace, workspace_bytes);
+  const bool want_ent = ent_ptr != nullptr && ent_pack != nullptr;     // the (entity, r) index is optional
   unsigned long long* ek_in = ws.take<unsigned long long>(2 * (size_t)S + 1);
   unsigned long long* ek_out = ws.take<unsigned long long>(2 * (size_t)S + 1);
   int* ev_in = ws.take<int>(2 * (size_t)S + 1);
@@ -247,11 +248,13 @@ extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_n
   triplet_keys<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, nb, rb, rk_in, rv_in, ek_in, ev_in);
   KG_LAUNCH_OK();
   size_t tb = temp_bytes;
-  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, 2 * S, 0, nb + rb, st));
-  fill_ent_pack<<<kg_div_up(2LL * S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
-  KG_LAUNCH_OK();
-  ent_lower_bound<<<kg_div_up(n_nodes + 1, kThreads), kThreads, 0, st>>>(ek_out, 2 * S, rb, n_nodes, ent_ptr);
-  KG_LAUNCH_OK();
+  if (want_ent) {
+    KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, 2 * S, 0, nb + rb, st));
+    fill_ent_pack<<<kg_div_up(2LL * S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
+    KG_LAUNCH_OK();
+    ent_lower_bound<<<kg_div_up(n_nodes + 1, kThreads), kThreads, 0, st>>>(ek_out, 2 * S, rb, n_nodes, ent_ptr);
+    KG_LAUNCH_OK();
+  }
   tb = temp_bytes;
   KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, rk_in, rk_out, rv_in, rv_out, S, 0, nb + rb, st));
   fill_rs_rec<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, rv_out, S, reinterpret_cast<int4*>(rs_rec));
@@ -274,27 +277,40 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
-template <int NV, bool FUSED>
+template <int NV, bool FUSED, bool DZ>
 __global__ void __launch_bounds__(kThreads)
 distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, const int4* __restrict__ rec,
                    const float* __restrict__ labels, const float* __restrict__ g_in,
                    const float* __restrict__ shift_p, int S, int h, float inv_S, float* __restrict__ score_out,
-                   float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ loss_part,
-                   float* __restrict__ gsum_part) {
+                   float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ dz,
+                   float* __restrict__ loss_part, float* __restrict__ gsum_part) {
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int k0 = warp * kChunkT;
   if (k0 >= S) return;
   const int k1 = min(S, k0 + kChunkT), nvec = h >> 2;
   const float shift = (FUSED && shift_p) ? __ldg(shift_p) : 0.f;
-  float4 zs[NV], wr[NV], acc[NV];
+  float4 zs[NV], wr[NV], acc[NV], acs[DZ ? NV : 1];   // acc: dw[r] of the run, acs: dz[s] of the run
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (DZ ? NV : 1); ++i) acs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cs = -1, cr = -1;
   float loss = 0.f, gsum = 0.f;
+  auto flush_s = [&]() {                      // dz[cs] += sum over the (r, s) run of g w[r] z[o]
+    if (DZ && cs >= 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) red_add_v4(dz + (size_t)cs * h + 4 * c, acs[i]);
+        acs[DZ ? i : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
   int4 rc = __ldg(rec + k0);
   for (int k = k0; k < k1; ++k) {
     const int4 nxt = k + 1 < k1 ? __ldg(rec + k + 1) : rc;      // prefetch the next record
     if (rc.y != cr) {
+      flush_s();
       if (cr >= 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -305,7 +321,7 @@ distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, con
       }
       cr = rc.y;
       cs = -1;
-      if (FUSED) {
+      if (FUSED || DZ) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = lane + 32 * i;
@@ -314,6 +330,7 @@ distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, con
       }
     }
     if (rc.x != cs) {
+      flush_s();
       cs = rc.x;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -349,15 +366,32 @@ distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, con
     } else {
       g = __ldg(g_in + rc.w);
     }
+    if (DZ) {                                 // dz[o] += g w[r] z[s]: one coalesced 2 KB vector reduction per triplet
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec)
+          red_add_v4(dz + (size_t)rc.z * h + 4 * c,
+                     make_float4(g * wr[i].x * zs[i].x, g * wr[i].y * zs[i].y, g * wr[i].z * zs[i].z, g * wr[i].w * zs[i].w));
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      acc[i].x = fmaf(g * zs[i].x, zo[i].x, acc[i].x);
-      acc[i].y = fmaf(g * zs[i].y, zo[i].y, acc[i].y);
-      acc[i].z = fmaf(g * zs[i].z, zo[i].z, acc[i].z);
-      acc[i].w = fmaf(g * zs[i].w, zo[i].w, acc[i].w);
+      const float tx = g * zo[i].x, ty = g * zo[i].y, tz = g * zo[i].z, tw = g * zo[i].w;
+      acc[i].x = fmaf(tx, zs[i].x, acc[i].x);
+      acc[i].y = fmaf(ty, zs[i].y, acc[i].y);
+      acc[i].z = fmaf(tz, zs[i].z, acc[i].z);
+      acc[i].w = fmaf(tw, zs[i].w, acc[i].w);
+      if (DZ) {
+        acs[DZ ? i : 0].x = fmaf(tx, wr[i].x, acs[DZ ? i : 0].x);
+        acs[DZ ? i : 0].y = fmaf(ty, wr[i].y, acs[DZ ? i : 0].y);
+        acs[DZ ? i : 0].z = fmaf(tz, wr[i].z, acs[DZ ? i : 0].z);
+        acs[DZ ? i : 0].w = fmaf(tw, wr[i].w, acs[DZ ? i : 0].w);
+      }
     }
     rc = nxt;
   }
+  flush_s();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
@@ -375,8 +409,8 @@ __global__ void __launch_bounds__(kThreads)
 distmult_rs_generic(const float* __restrict__ z, const float* __restrict__ w, const int4* __restrict__ rec,
                     const float* __restrict__ labels, const float* __restrict__ g_in,
                     const float* __restrict__ shift_p, int S, int h, float inv_S, float* __restrict__ score_out,
-                    float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ loss_part,
-                    float* __restrict__ gsum_part) {
+                    float* __restrict__ g_out, float* __restrict__ dw, float* __restrict__ dz,
+                    float* __restrict__ loss_part, float* __restrict__ gsum_part) {
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int k0 = warp * kChunkT;
   if (k0 >= S) return;
@@ -404,7 +438,15 @@ distmult_rs_generic(const float* __restrict__ z, const float* __restrict__ w, co
     } else {
       g = __ldg(g_in + rc.w);
     }
-    for (int c = lane; c < h; c += 32) atomicAdd(dw + (size_t)rc.y * h + c, g * __ldg(zs + c) * __ldg(zo + c));
+    for (int c = lane; c < h; c += 32) {
+      const float a = __ldg(zs + c), b = __ldg(zo + c);
+      atomicAdd(dw + (size_t)rc.y * h + c, g * a * b);
+      if (dz) {
+        const float wv = __ldg(w + (size_t)rc.y * h + c);
+        atomicAdd(dz + (size_t)rc.x * h + c, g * wv * b);
+        atomicAdd(dz + (size_t)rc.z * h + c, g * wv * a);
+      }
+    }
   }
   if (FUSED && lane == 0) {
     loss_part[warp] = loss;
@@ -414,18 +456,25 @@ distmult_rs_generic(const float* __restrict__ z, const float* __restrict__ w, co
 
 template <bool FUSED>
 static int launch_rs(const float* z, const float* w, const void* rs_rec, const float* labels, const float* g_in,
-                     const float* shift, int S, int h, float* score_out, float* g_out, float* dw,
+                     const float* shift, int S, int h, float* score_out, float* g_out, float* dw, float* dz,
                      float* loss_part, float* gsum_part, cudaStream_t st) {
   const int warps = kg_div_up(S, kChunkT);
   const int grid = kg_div_up((long long)warps * 32, kThreads);
   const int4* rec = reinterpret_cast<const int4*>(rs_rec);
   const float inv_S = 1.0f / (float)S;
   const bool vec = (h % 4 == 0) && h <= 1024 &&
-                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0;
-#define KG_RS_LAUNCH(NV_)                                                                                   \
-  distmult_rs_kernel<NV_, FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S,    \
-                                                            score_out, g_out, dw, loss_part, gsum_part)
-  if (!vec) distmult_rs_generic<FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, score_out, g_out, dw, loss_part, gsum_part);
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw) |
+                     reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+#define KG_RS_LAUNCH(NV_)                                                                                       \
+  do {                                                                                                          \
+    if (dz)                                                                                                     \
+      distmult_rs_kernel<NV_, FUSED, true><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, \
+                                                                      score_out, g_out, dw, dz, loss_part, gsum_part); \
+    else                                                                                                        \
+      distmult_rs_kernel<NV_, FUSED, false><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, \
+                                                                       score_out, g_out, dw, dz, loss_part, gsum_part); \
+  } while (0)
+  if (!vec) distmult_rs_generic<FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, score_out, g_out, dw, dz, loss_part, gsum_part);
   else if (h <= 128) KG_RS_LAUNCH(1);
   else if (h <= 256) KG_RS_LAUNCH(2);
   else if (h <= 512) KG_RS_LAUNCH(4);
@@ -443,9 +492,12 @@ extern "C" size_t kg_distmult_bce_workspace_bytes(int n_triplets) {
 // Fused DistMult score + BCE-with-logits (mean) + gradient wrt the score and wrt w_relation.
 //   loss_out[0] = mean_t BCE(score_t, labels_t);  gsum_out[0] = sum_t g_t (gradient wrt the scalar shift)
 //   g_out[t] = dloss/dscore_t;  dw (zero-filled by the caller) += sum_t g_t z[s_t] z[o_t];  score_out optional
+//   dz (optional, zero-filled by the caller) += sum_t g_t w[r_t] (z[o_t] into row s_t, z[s_t] into row o_t):
+//   the whole backward into z in the same pass - z[o] is in registers anyway, dz[s] is kept in registers over
+//   an (r, s) run and dz[o] goes out as one coalesced 2 KB vector reduction per triplet
 extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
                                    int n_triplets, int h, const float* shift, float* score_out, float* g_out,
-                                   float* dw, float* loss_out, float* gsum_out, void* workspace,
+                                   float* dw, float* dz, float* loss_out, float* gsum_out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult bce: bad sizes");
   cudaStream_t st = kg_stream(stream);
@@ -460,7 +512,7 @@ extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* r
   float* gsum_part = ws.take<float>(warps);
   float* red = ws.take<float>(kMaxPartials);
   if (!loss_part || !gsum_part || !red) return kg_fail(KG_ERR_WORKSPACE, "distmult bce: workspace too small");
-  int rc = launch_rs<true>(z, w, rs_rec, labels, nullptr, shift, n_triplets, h, score_out, g_out, dw, loss_part,
+  int rc = launch_rs<true>(z, w, rs_rec, labels, nullptr, shift, n_triplets, h, score_out, g_out, dw, dz, loss_part,
                            gsum_part, st);
   if (rc != KG_OK) return rc;
   rc = run_reduce(loss_part, nullptr, (long long)warps, 0, 1.0f / (float)n_triplets, 0.f, nullptr, loss_out, red,
@@ -476,7 +528,7 @@ extern "C" int kg_distmult_bwd_dw(const float* z, const float* gscore, const voi
   KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult dw: bad sizes");
   if (n_triplets == 0) return KG_OK;
   return launch_rs<false>(z, nullptr, rs_rec, nullptr, gscore, nullptr, n_triplets, h, nullptr, nullptr, dw, nullptr,
-                          nullptr, kg_stream(stream));
+                          nullptr, nullptr, kg_stream(stream));
 }
 
 // ------------------------------------------------------------------------------------------

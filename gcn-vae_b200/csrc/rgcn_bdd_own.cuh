@@ -26,7 +26,7 @@
 namespace bddown {
 
 constexpr int kCta = 128;     // threads per CTA (4 warps)
-constexpr int kChunk = 128;   // consecutive relation-sorted edges per CTA
+constexpr int kChunk = 256;   // consecutive relation-sorted edges per CTA
 constexpr int kDepth = 4;     // gathered rows in flight per slot
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -39,6 +39,12 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 __device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
   uint64_t pol;
   if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_last(bool evict_last) {
+  uint64_t pol;
+  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
@@ -74,9 +80,9 @@ __device__ __forceinline__ void bulk_g2s(float* dst, const float* __restrict__ s
       : "memory");
 }
 // bulk reduction shared -> global: dst[0..bytes/4) += src[0..bytes/4) (fp32), part of the thread's bulk group
-__device__ __forceinline__ void bulk_red_add(float* dst, const float* src, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-               "r"(smem_u32(src)), "r"(bytes)
+__device__ __forceinline__ void bulk_red_add(float* dst, const float* src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.f32 [%0], [%1], %2, %3;"
+               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -181,7 +187,7 @@ fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
   const int4* rec = P_s + k_lo;
   float* ring = X_s + slot * kDepth * in_w;
   uint64_t* full = bars + slot * kDepth;
-  const uint64_t pol = l2_policy(hints & 1);
+  const uint64_t pol = l2_policy(hints & 1), pol_red = l2_policy_last(hints & 4);
   const uint32_t row_bytes = (uint32_t)in_w * 4;
   const bool leader = wsl == 0 && lane == 0;  // issues the slot's gathers
 
@@ -242,7 +248,7 @@ fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
         }
         slot_sync<WPS>(slot);                 // outputs parked; everybody has consumed ring stage u
         if (lane == 0) {
-          if (warp_bytes) bulk_red_add(const_cast<float*>(row_at(out_w, p.y, width)), tb_cur, warp_bytes);
+          if (warp_bytes) bulk_red_add(const_cast<float*>(row_at(out_w, p.y, width)), tb_cur, warp_bytes, pol_red);
           bulk_commit();
         }
         if (leader && k + u + kDepth < n_my) {              // refill the stage just consumed
@@ -287,7 +293,8 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ dagg, const in
   const int4* rec = P_s + k_lo;
   float* ring = R_s + slot * kDepth * row_w;
   uint64_t* full = bars + slot * kDepth;
-  const uint64_t pol_x = l2_policy(hints & 1), pol_d = l2_policy(hints & 2);
+  const uint64_t pol_x = (hints & 4) ? l2_policy_last(true) : l2_policy(hints & 1), pol_d = l2_policy(hints & 2);
+  const uint64_t pol_red = l2_policy_last(hints & 4);
   const uint32_t x_bytes = (uint32_t)in_w * 4, d_bytes = (uint32_t)out_w * 4;
   const bool leader = wsl == 0 && lane == 0;
 
@@ -388,7 +395,7 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ dagg, const in
         slot_sync<WPS>(slot);                 // gradients parked; everybody has consumed ring stage u
         if (xrole && lane == 0) {
           if (dx != nullptr && warp_bytes)
-            bulk_red_add(const_cast<float*>(row_at(dx_w, p.x, in_w)), tb_cur, warp_bytes);
+            bulk_red_add(const_cast<float*>(row_at(dx_w, p.x, in_w)), tb_cur, warp_bytes, pol_red);
           bulk_commit();
         }
         if (leader && k + u + kDepth < n_my) gather(k + u + kDepth, u);

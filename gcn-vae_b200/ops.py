@@ -62,7 +62,7 @@ class GraphIndex:
 
 # Rows that message passing reduces into (agg[dst] forward, x[src] + dx[src] backward) are kept
 # L2-resident: graphs whose reduced matrix exceeds this budget are walked tile by tile.
-L2_TILE_BYTES = 32 << 20
+L2_TILE_BYTES = int(__import__("os").environ.get("KG_TILE_MB", "32")) << 20
 L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read with evict-first
 HINT_STREAM_X, HINT_STREAM_D = 1, 2
 
@@ -405,16 +405,16 @@ class ReverseColumnsFn(torch.autograd.Function):
 # a9  DistMult + BCE + regulariser
 # ---------------------------------------------------------------------------------------------
 class TripletIndex:
-    """(r, s)-ordered and (entity, r)-ordered views of one batch of triplets."""
+    """(r, s)-ordered and, on request, (entity, r)-ordered views of one batch of triplets."""
 
-    def __init__(self, triplets, n_nodes, n_rels):
+    def __init__(self, triplets, n_nodes, n_rels, entity_index=True):
         dev = triplets.device
         S = triplets.shape[0]
         i32 = dict(dtype=torch.int32, device=dev)
         self.n = S
         self.rs_rec = torch.empty((max(S, 1), 4), **i32)
-        self.ent_ptr = torch.empty(n_nodes + 1, **i32)
-        self.ent_pack = torch.empty((max(2 * S, 1), 4), **i32)
+        self.ent_ptr = torch.empty(n_nodes + 1, **i32) if entity_index else None
+        self.ent_pack = torch.empty((max(2 * S, 1), 4), **i32) if entity_index else None
         ws = L.workspace(L.lib().kg_triplet_index_workspace_bytes(S), dev)
         L.call("kg_triplet_index", L.i32(triplets), S, n_nodes, n_rels, L.i32(self.rs_rec), L.i32(self.ent_ptr),
                L.i32(self.ent_pack), L.ptr(ws), ws.numel(), L.stream())
@@ -458,41 +458,39 @@ class DistMultScoreFn(torch.autograd.Function):
 class DistMultBceFn(torch.autograd.Function):
     """mean BCE-with-logits of the DistMult scores (+ shift) in one pass: the prediction term of
     LinkPredict.get_loss (kgvae/link_predict.py:74-77).  The forward kernel also produces
-    dloss/dscore and the gradient wrt w_relation; backward is one gather pass for dz."""
+    dloss/dscore and the gradients wrt w_relation and (when z needs one) wrt z: each triplet's
+    rows are in registers once, for the score and for all three gradients."""
 
     @staticmethod
     def forward(ctx, z, w, triplets, labels, shift):
         z, w, labels = _c(z), _c(w), _c(labels)
         S, h = triplets.shape[0], z.shape[1]
         dev = z.device
-        idx = TripletIndex(triplets, z.shape[0], w.shape[0])
+        idx = TripletIndex(triplets, z.shape[0], w.shape[0], entity_index=False)
         g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
         dw = torch.zeros_like(w)
+        dz = torch.zeros_like(z) if ctx.needs_input_grad[0] else None
         out = torch.empty(2, dtype=torch.float32, device=dev)         # loss, sum of g
         sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
         ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
         L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
-               None, L.f32(g), L.f32(dw), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(), L.stream())
-        ctx.save_for_backward(z, w, g, dw, out)
-        ctx.idx = idx
+               None, L.f32(g), L.f32(dw), L.f32(dz), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
+               L.stream())
+        ctx.save_for_backward(dw, dz, out)
         ctx.shift_shape = None if shift is None else shift.shape
         return out[0].clone()
 
     @staticmethod
     def backward(ctx, go):
-        z, w, g, dw, out = ctx.saved_tensors
-        idx = ctx.idx
-        dz = dwo = dshift = None
+        dw, dz, out = ctx.saved_tensors
+        dzo = dwo = dshift = None
         if ctx.needs_input_grad[0]:
-            dz = torch.empty_like(z)
-            L.call("kg_distmult_bwd_dz", L.f32(z), L.f32(w), L.f32(g), L.i32(idx.ent_ptr),
-                   L.i32(idx.ent_pack), z.shape[0], z.shape[1], L.f32(dz), L.stream())
-            dz = dz * go
+            dzo = dz * go
         if ctx.needs_input_grad[1]:
             dwo = dw * go
         if ctx.shift_shape is not None and ctx.needs_input_grad[4]:
             dshift = (out[1] * go).reshape(ctx.shift_shape)
-        return dz, dwo, None, None, dshift
+        return dzo, dwo, None, None, dshift
 
 
 class BceLogitsFn(torch.autograd.Function):

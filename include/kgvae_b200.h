@@ -238,6 +238,7 @@ int kg_sum(const float* x, long long n, float* out, void* workspace, size_t work
  *   rs_rec  [S]  int4 {s, r, o, t}: the triplets in (r, s) order - runs share w[r] and z[s]
  *   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, r, t, 0} in (entity, r) order: for entity v,
  *     every triplet where v is subject (other = object) or object (other = subject)
+ * ent_ptr / ent_pack may be NULL: only rs_rec is built (the fused kg_distmult_bce_fwd needs no entity index).
  * Limits: n_nodes < 2^24, n_rels < 2^16. */
 size_t kg_triplet_index_workspace_bytes(int n_triplets);
 int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
@@ -247,13 +248,15 @@ int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n
  *   score_t = sum_d z[s,d] w[r,d] z[o,d] + shift;  loss_out[0] = mean_t BCE-with-logits(score_t, labels_t)
  *   g_out[t] = dloss/dscore_t = (sigmoid(score_t) - labels_t) / S;  gsum_out[0] = sum_t g_t (d/dshift)
  *   dw[r,:] += sum_{t: r_t = r} g_t z[s_t,:] z[o_t,:]   (dw zero-filled by the caller)
+ *   dz[s_t,:] += g_t w[r_t,:] z[o_t,:];  dz[o_t,:] += g_t w[r_t,:] z[s_t,:]   (optional: dz zero-filled by
+ *     the caller, or NULL - then kg_distmult_bwd_dz over the entity index gives the same, deterministically)
  *   score_out [S] optional (may be NULL)
  * workspace: kg_distmult_bce_workspace_bytes(S) */
 size_t kg_distmult_bce_workspace_bytes(int n_triplets);
 int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
                         int n_triplets, int h, const float* shift /* device scalar or NULL */,
-                        float* score_out, float* g_out, float* dw, float* loss_out, float* gsum_out,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        float* score_out, float* g_out, float* dw, float* dz, float* loss_out,
+                        float* gsum_out, void* workspace, size_t workspace_bytes, void* stream);
 /* dz[v,:] = sum_{(other, r, t) in ent(v)} gscore[t] * w[r,:] * z[other,:]    (no atomics) */
 int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore, const int32_t* ent_ptr,
                        const void* ent_pack, int n_nodes, int h, float* dz, void* stream);
