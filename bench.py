@@ -224,12 +224,12 @@ def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edge
             p_bwd = ops._rel_order(gi, 1, n_nodes, 8 * in_f)
 
             def fwd():
-                L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(p_fwd), n_edges, L.f32(weight), L.f32(w_fwd), BASES, si, so, L.f32(agg),
-                       ops.HINT_STREAM_X | int(os.environ.get("KG_HINT_EXTRA", "0")), L.stream())
+                L.call("kg_bdd_rel_fwd", L.f32(x), None, 0, L.i32(p_fwd), n_edges, L.f32(weight), L.f32(w_fwd), BASES, si, so, L.f32(agg),
+                       ops.HINT_STREAM_X | ops.HINT_TILE_RESIDENT, L.stream())
 
             def bwd():
-                L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(agg), L.i32(p_bwd), n_edges, L.f32(weight), L.f32(w_bwd), BASES, si, so,
-                       L.f32(dx), L.f32(dw), ops.HINT_STREAM_D | int(os.environ.get("KG_HINT_EXTRA", "0")), L.stream())
+                L.call("kg_bdd_rel_bwd", L.f32(x), None, 0, L.f32(agg), L.i32(p_bwd), n_edges, L.f32(weight), L.f32(w_bwd), BASES, si, so,
+                       L.f32(dx), L.f32(dw), ops.HINT_STREAM_D | ops.HINT_TILE_RESIDENT, L.stream())
 
             for name, fn, zero in ((f"kg_bdd_rel_fwd[{si}x{so}]", fwd, (agg,)), (f"kg_bdd_rel_bwd[{si}x{so}]", bwd, (dx, dw))):
                 ms = []

@@ -18,6 +18,10 @@ _SIGNATURES = {
     "kg_last_error": (ctypes.c_char_p, []),
     "kg_version": (_I, []),
     "kg_device_info": (_I, [_P, _P, _P]),
+    "kg_peer_alloc": (_I, [_Z, _P, _P]),
+    "kg_peer_open": (_I, [_P, _P]),
+    "kg_peer_close": (_I, [_P]),
+    "kg_peer_free": (_I, [_P]),
     "kg_graph_build_workspace_bytes": (_Z, [_I]),
     "kg_graph_build": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "kg_graph_index_workspace_bytes": (_Z, [_I]),
@@ -25,8 +29,8 @@ _SIGNATURES = {
     "kg_embedding_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_embedding_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "kg_bdd_weight_layouts": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
-    "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
-    "kg_bdd_rel_bwd": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
+    "kg_bdd_rel_bwd": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
     "kg_bdd_layouts_needed": (_I, [_I, _I, _I]),
     "kg_graph_rel_tiled_workspace_bytes": (_Z, [_I]),
     "kg_graph_rel_tiled": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

@@ -48,6 +48,38 @@ extern "C" int kg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return KG_OK;
 }
 
+// Peer-visible device buffers (parallel.PeerRows): plain cudaMalloc memory exported with CUDA IPC and
+// opened by the other ranks of the node ON THEIR OWN current device with lazy peer access, so that
+// their kernels (LDG and the TMA bulk copies alike) can dereference it over NVLink.
+extern "C" int kg_peer_alloc(size_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */) {
+  KG_REQUIRE(bytes > 0 && ptr && handle_out, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  KG_CUDA(cudaMalloc(ptr, bytes));
+  KG_CUDA(cudaMemset(*ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  KG_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return KG_OK;
+}
+
+extern "C" int kg_peer_open(const unsigned char* handle /* 64 bytes */, void** ptr) {
+  KG_REQUIRE(handle && ptr, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  KG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KG_OK;
+}
+
+extern "C" int kg_peer_close(void* ptr) {
+  KG_CUDA(cudaIpcCloseMemHandle(ptr));
+  return KG_OK;
+}
+
+extern "C" int kg_peer_free(void* ptr) {
+  KG_CUDA(cudaFree(ptr));
+  return KG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------

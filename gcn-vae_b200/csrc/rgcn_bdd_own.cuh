@@ -111,6 +111,22 @@ __device__ __forceinline__ const float* row_at(const float* base, int row, int w
   return base + (size_t)(unsigned)row * (unsigned)width;
 }
 
+// Where gathered rows live: one matrix, or (destination-partitioned training) one row block per
+// rank, each in the owner's HBM and mapped into this process (CUDA IPC): row r is row r % part_rows
+// of parts[r / part_rows].  A peer row is fetched by the same bulk copy, over NVLink - the
+// "all-gather" of layer inputs is fused into the gather stage of the message-passing kernel and
+// moves only the rows this rank's edges reference.
+struct RowSource {
+  const float* base;
+  const float* const* parts;
+  int part_rows;
+  __device__ __forceinline__ const float* row(int r, int width) const {
+    if (parts == nullptr) return row_at(base, r, width);
+    const int owner = r / part_rows;
+    return row_at(parts[owner], r - owner * part_rows, width);
+  }
+};
+
 // N contiguous floats from shared memory with the widest loads the alignment of N allows
 template <int N>
 __device__ __forceinline__ void lds_vec(float (&v)[N], const float* p) {
@@ -162,7 +178,7 @@ __device__ __forceinline__ int group_of(int warp_in_role, int lane, int per, int
 // ------------------------------------------------------------------------------------------
 template <int FI, int FO, int TB, int WPS>
 __global__ void __launch_bounds__(kCta)
-fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
+fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E,
            const float* __restrict__ weight, int B, int hints, float* __restrict__ out) {
   constexpr int XN = TB * FI, CN = TB * FO, WN = TB * FI * FO, SLOTS = 4 / WPS;
   extern __shared__ __align__(16) float sm[];
@@ -196,7 +212,7 @@ fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
     for (int k = 0; k < kDepth; ++k)
       if (k < n_my) {
         mbar_expect_tx(full + k, row_bytes);
-        bulk_g2s(ring + k * in_w, row_at(feat, rec[k].x, in_w), row_bytes, full + k, pol);
+        bulk_g2s(ring + k * in_w, feat.row(rec[k].x, in_w), row_bytes, full + k, pol);
       }
   }
 
@@ -253,7 +269,7 @@ fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
         }
         if (leader && k + u + kDepth < n_my) {              // refill the stage just consumed
           mbar_expect_tx(full + u, row_bytes);
-          bulk_g2s(ring + u * in_w, row_at(feat, rec[k + u + kDepth].x, in_w), row_bytes, full + u, pol);
+          bulk_g2s(ring + u * in_w, feat.row(rec[k + u + kDepth].x, in_w), row_bytes, full + u, pol);
         }
       }
     }
@@ -269,7 +285,7 @@ fwd_kernel(const float* __restrict__ feat, const int4* __restrict__ pack, int E,
 // ------------------------------------------------------------------------------------------
 template <int SI, int SO, int TB, int WPR>
 __global__ void __launch_bounds__(kCta)
-bwd_kernel(const float* __restrict__ x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
+bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
            const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
   constexpr int XN = TB * SI, DN = TB * SO, WN = TB * SI * SO, WPS = 2 * WPR, SLOTS = 4 / WPS;
   extern __shared__ __align__(16) float sm[];
@@ -301,7 +317,7 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ dagg, const in
   auto gather = [&](int k, int stage) {       // leader only
     const int4 p = rec[k];
     mbar_expect_tx(full + stage, x_bytes + d_bytes);
-    bulk_g2s(ring + stage * row_w, row_at(x, p.x, in_w), x_bytes, full + stage, pol_x);
+    bulk_g2s(ring + stage * row_w, x.row(p.x, in_w), x_bytes, full + stage, pol_x);
     bulk_g2s(ring + stage * row_w + in_w, row_at(dagg, p.y, out_w), d_bytes, full + stage, pol_d);
   };
   if (leader) {
@@ -410,7 +426,7 @@ bwd_kernel(const float* __restrict__ x, const float* __restrict__ dagg, const in
 // host side
 // ------------------------------------------------------------------------------------------
 template <int FI, int FO, int TB, int WPS>
-int launch_fwd(const float* feat, const void* pack, int E, const float* weight, int B, int hints, float* out,
+int launch_fwd(RowSource feat, const void* pack, int E, const float* weight, int B, int hints, float* out,
                cudaStream_t st) {
   constexpr int SLOTS = 4 / WPS;
   const size_t smem = sizeof(float) * ((size_t)4 * kChunk + (size_t)SLOTS * kDepth * B * FI + 4 * 2 * 32 * TB * FO) +
@@ -423,7 +439,7 @@ int launch_fwd(const float* feat, const void* pack, int E, const float* weight, 
 }
 
 template <int SI, int SO, int TB, int WPR>
-int launch_bwd(const float* x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
+int launch_bwd(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
                float* dx, float* dW, cudaStream_t st) {
   constexpr int SLOTS = 4 / (2 * WPR);
   const size_t smem = sizeof(float) * ((size_t)4 * kChunk + (size_t)SLOTS * kDepth * B * (SI + SO) + 4 * 2 * 32 * TB * SI) +

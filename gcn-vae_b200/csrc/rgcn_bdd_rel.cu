@@ -447,16 +447,19 @@ extern "C" int kg_bdd_layouts_needed(int num_bases, int si, int so) {
 }
 
 // agg[dst] += norm * blockdiag(W[etype]) x[src] over relation-sorted edges; agg zero-filled by the caller
-extern "C" int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges, const float* weight,
-                              const float* w_fwd, int num_bases, int si, int so, float* agg, int hints,
-                              void* stream) {
+extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows, const void* rel_pack,
+                              int n_edges, const float* weight, const float* w_fwd, int num_bases, int si,
+                              int so, float* agg, int hints, void* stream) {
   KG_REQUIRE(n_edges >= 0 && num_bases > 0 && si > 0 && so > 0, "bdd rel fwd: bad sizes");
+  KG_REQUIRE(x_parts == nullptr || part_rows > 0, "bdd rel fwd: part_rows must be positive");
   if (n_edges == 0) return KG_OK;
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(weight) && aligned16(agg)) {
-    if (so == 5) return bddown::launch_fwd<5, 5, 4, 1>(x, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    return bddown::launch_fwd<5, 10, 2, 2>(x, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
+    if (so == 5) return bddown::launch_fwd<5, 5, 4, 1>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    return bddown::launch_fwd<5, 10, 2, 2>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
   }
+  KG_REQUIRE(x_parts == nullptr, "bdd rel fwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
   KG_REQUIRE(w_fwd != nullptr, "bdd rel fwd: this block shape needs the w_fwd layout (kg_bdd_weight_layouts)");
   if (fast_shape(num_bases, si, so) && aligned16(x) && aligned16(w_fwd) && aligned16(agg)) {
     KG_BDD_DISPATCH(launch_scatter, 5, 5, x, rel_pack, n_edges, w_fwd, num_bases, hints, agg, st);
@@ -475,18 +478,22 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges,
 }
 
 // dx (zero-filled, may be NULL) and dweight (zero-filled) of the same layer
-extern "C" int kg_bdd_rel_bwd(const float* x, const float* dagg, const void* rel_pack, int n_edges,
-                              const float* weight, const float* w_bwd, int num_bases, int si, int so,
-                              float* dx, float* dweight, int hints, void* stream) {
+extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows, const float* dagg,
+                              const void* rel_pack, int n_edges, const float* weight, const float* w_bwd,
+                              int num_bases, int si, int so, float* dx, float* dweight, int hints,
+                              void* stream) {
   KG_REQUIRE(n_edges >= 0 && num_bases > 0 && si > 0 && so > 0, "bdd rel bwd: bad sizes");
+  KG_REQUIRE(x_parts == nullptr || part_rows > 0, "bdd rel bwd: part_rows must be positive");
   if (n_edges == 0) return KG_OK;
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(dagg) && aligned16(weight) &&
       aligned16(dx) && aligned16(dweight)) {
+    const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
     if (so == 5)
-      return bddown::launch_bwd<5, 5, 4, 1>(x, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    return bddown::launch_bwd<5, 10, 2, 2>(x, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+      return bddown::launch_bwd<5, 5, 4, 1>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    return bddown::launch_bwd<5, 10, 2, 2>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
   }
+  KG_REQUIRE(x_parts == nullptr, "bdd rel bwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
   KG_REQUIRE(w_bwd != nullptr, "bdd rel bwd: this block shape needs the w_bwd layout (kg_bdd_weight_layouts)");
   if (fast_shape(num_bases, si, so) && aligned16(x) && aligned16(dagg) && aligned16(w_bwd) && aligned16(dx)) {
     KG_BDD_DISPATCH(launch_backward, 5, 5, x, dagg, rel_pack, n_edges, w_bwd, num_bases, hints, dx, dweight, st);

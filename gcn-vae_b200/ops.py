@@ -62,9 +62,9 @@ class GraphIndex:
 
 # Rows that message passing reduces into (agg[dst] forward, x[src] + dx[src] backward) are kept
 # L2-resident: graphs whose reduced matrix exceeds this budget are walked tile by tile.
-L2_TILE_BYTES = int(__import__("os").environ.get("KG_TILE_MB", "32")) << 20
+L2_TILE_BYTES = 32 << 20
 L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read with evict-first
-HINT_STREAM_X, HINT_STREAM_D = 1, 2
+HINT_STREAM_X, HINT_STREAM_D, HINT_TILE_RESIDENT = 1, 2, 4
 
 
 def _rel_order(gi, by_src, n_rows, row_bytes):
@@ -181,12 +181,18 @@ class BddConvFn(torch.autograd.Function):
     """One RelGraphConv(bdd) layer: out = dropout(act(sum_e norm_e W_{r_e} x_src + h_bias +
     x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59.
 
-    ``dst_lo``/``n_dst`` select the destination-partitioned form: ``x`` then holds the features of
-    ALL nodes (edge sources are global ids), the layer produces rows for the ``n_dst`` nodes owned
-    by this rank (edge destinations are local ids) and the self-loop uses ``x[dst_lo:dst_lo+n_dst]``."""
+    Destination-partitioned forms (edge sources are global ids, destinations local ids, the layer
+    produces the rows of the nodes this rank owns):
+    * ``dst_lo``/``n_dst``: ``x`` holds the features of ALL nodes (all-gathered by the caller), the
+      self-loop uses ``x[dst_lo:dst_lo+n_dst]``;
+    * ``peer`` (parallel.PeerRows) + ``part``: ``x`` holds only this rank's rows; they are published
+      in the rank's peer-visible block and every rank's kernel gathers the source rows it needs
+      straight from the owners' HBM over NVLink (no all-gather); the gradient wrt the sources is
+      accumulated for all nodes and reduce-scattered to the owners."""
 
     @staticmethod
-    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask, dst_lo=-1, n_dst=-1):
+    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask, dst_lo=-1, n_dst=-1,
+                peer=None, part=None):
         x, weight = _c(x), _c(weight)
         dev = x.device
         n, in_feat = x.shape
@@ -194,23 +200,35 @@ class BddConvFn(torch.autograd.Function):
         si = in_feat // num_bases
         so = weight.shape[1] // (num_bases * si)
         out_feat = num_bases * so
-        if dst_lo < 0:
+        needs_layouts = bool(L.lib().kg_bdd_layouts_needed(num_bases, si, so))
+        if peer is not None:
+            if needs_layouts:
+                raise RuntimeError("RelGraphConv: the peer-memory gather needs 5x5 / 5x10 blocks")
+            n_out, x_own = n, x
+            peer.publish(x)
+            src_args = (None, L.ptr(peer.ptrs), peer.blk)
+            n_src_rows = peer.blk * peer.world_size
+        elif dst_lo < 0:
             if n != gi.n_nodes:
                 raise RuntimeError(f"RelGraphConv: {n} feature rows for a graph of {gi.n_nodes} nodes")
             n_out, x_own = n, x
+            src_args, n_src_rows = (L.f32(x), None, 0), n
         else:
             if dst_lo + n_dst > n:
                 raise RuntimeError("RelGraphConv: owned node block lies outside the gathered features")
             n_out, x_own = n_dst, x[dst_lo:dst_lo + n_dst]
+            src_args, n_src_rows = (L.f32(x), None, 0), n
         w_fwd = w_bwd = None
-        if L.lib().kg_bdd_layouts_needed(num_bases, si, so):
+        if needs_layouts:
             w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
             w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
             L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
                    L.f32(w_bwd), L.stream())
         agg = torch.zeros((n_out, out_feat), dtype=torch.float32, device=dev)
-        hints = HINT_STREAM_X if x.numel() * 4 > L2_STREAM_BYTES else 0
-        L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(_rel_order(gi, 0, n_out, 4 * out_feat)), gi.n_edges, L.f32(weight),
+        pack = _rel_order(gi, 0, n_out, 4 * out_feat)
+        hints = (HINT_STREAM_X if n_src_rows * in_feat * 4 > L2_STREAM_BYTES else 0) | \
+                (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
+        L.call("kg_bdd_rel_fwd", *src_args, L.i32(pack), gi.n_edges, L.f32(weight),
                L.f32(w_fwd), num_bases, si, so, L.f32(agg), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
         out = torch.empty_like(agg)
         bias = None if h_bias is None else _c(h_bias)
@@ -223,13 +241,13 @@ class BddConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight, loop_weight, out, mask, w_bwd)
         ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
         ctx.has_bias = h_bias is not None
-        ctx.dst_lo, ctx.n_out = dst_lo, n_out
+        ctx.dst_lo, ctx.n_out, ctx.peer, ctx.part = dst_lo, n_out, peer, part
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight, loop_weight, out, mask, w_bwd = ctx.saved_tensors
-        gi, B, si, so = ctx.gi, ctx.num_bases, ctx.si, ctx.so
+        gi, B, si, so, peer = ctx.gi, ctx.num_bases, ctx.si, ctx.so, ctx.peer
         g = _c(g)
         x_own = x if ctx.dst_lo < 0 else x[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
         gpre = torch.empty_like(out)
@@ -237,16 +255,30 @@ class BddConvFn(torch.autograd.Function):
                L.f32(gpre), L.stream())
         dx = dw = dloop = dbias = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+            if peer is not None:       # source rows are still in the peers' blocks (published in forward)
+                n_src_rows = peer.blk * peer.world_size
+                src_args = (None, L.ptr(peer.ptrs), peer.blk)
+            else:
+                n_src_rows, src_args = x.shape[0], (L.f32(x), None, 0)
+            dx = torch.zeros((n_src_rows, x.shape[1]), dtype=torch.float32, device=x.device) \
+                if ctx.needs_input_grad[0] else None
             dw = torch.zeros_like(weight)
             # walked by source tile: x[src] and dx[src] stay L2-resident, dagg[dst] is the gathered row
-            pack = _rel_order(gi, 1, x.shape[0], (8 if dx is not None else 4) * x.shape[1])
-            hints = HINT_STREAM_D if gpre.numel() * 4 > L2_STREAM_BYTES else 0
-            L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(gpre), L.i32(pack), gi.n_edges, L.f32(weight), L.f32(w_bwd),
+            pack = _rel_order(gi, 1, n_src_rows, (8 if dx is not None else 4) * x.shape[1])
+            hints = (HINT_STREAM_D if gpre.numel() * 4 > L2_STREAM_BYTES else 0) | \
+                    (HINT_TILE_RESIDENT if pack is not gi.rel_pack and peer is None else 0)
+            L.call("kg_bdd_rel_bwd", *src_args, L.f32(gpre), L.i32(pack), gi.n_edges, L.f32(weight), L.f32(w_bwd),
                    B, si, so, L.f32(dx), L.f32(dw), hints, L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
             if dx is not None and loop_weight is not None:
-                dx_own = dx if ctx.dst_lo < 0 else dx[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
+                if peer is not None:
+                    lo = peer.rank * peer.blk
+                    dx_own = dx[lo:lo + ctx.n_out]
+                else:
+                    dx_own = dx if ctx.dst_lo < 0 else dx[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
                 gemm(gpre, loop_weight, dx_own, trans_b=True, accumulate=True)
+            if dx is not None and peer is not None:      # every rank holds partial sums for all nodes
+                from . import parallel
+                dx = parallel.reduce_scatter_rows(dx, ctx.part)
             if not ctx.needs_input_grad[1]:
                 dw = None
         if loop_weight is not None and ctx.needs_input_grad[2]:
@@ -254,7 +286,7 @@ class BddConvFn(torch.autograd.Function):
             gemm(x_own, gpre, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = colsum(gpre)
-        return dx, dw, dloop, dbias, None, None, None, None, None, None
+        return dx, dw, dloop, dbias, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------

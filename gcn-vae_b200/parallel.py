@@ -15,6 +15,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
+
 
 def world():
     """(rank, world_size) of the default process group, (0, 1) when not initialised."""
@@ -29,6 +31,14 @@ def block_range(n, rank, world_size):
 
 
 entity_shard = block_range
+
+
+def uniform_block_range(n, rank, world_size):
+    """Contiguous blocks of ONE size, ceil(n / world_size) (the last ranks may own fewer rows or none):
+    the owner of row r is r // blk, which is what a kernel can compute per edge (PeerRows)."""
+    blk = (n + world_size - 1) // world_size
+    lo = min(n, rank * blk)
+    return lo, min(n, lo + blk)
 
 
 def allreduce_mean_grads(params, group=None):
@@ -64,15 +74,17 @@ def sharded_rank_counts(count_fn, num_entities, group=None):
     return counts
 
 
-def partition_by_destination(src, dst, etype, norm, num_nodes, world_size):
+def partition_by_destination(src, dst, etype, norm, num_nodes, world_size, uniform=False):
     """Destination-node ownership: returns a list (one entry per rank) of dicts with the owned node
     block ``[lo, hi)``, the rank's edges (every edge with dst in the block, original relative
     order kept - so per-destination summation order equals the single-GPU order) and
-    ``needed_src``: the sorted unique source ids the rank must receive features for."""
+    ``needed_src``: the sorted unique source ids the rank must receive features for.
+    ``uniform``: blocks of one size (uniform_block_range), required by the peer-memory gather."""
     src, dst, etype = (np.asarray(a) for a in (src, dst, etype))
     norm = None if norm is None else np.asarray(norm).reshape(-1)
     # owner of an edge: the rank p with lo_p <= dst < hi_p
-    bounds = np.array([block_range(num_nodes, p, world_size)[0] for p in range(world_size)] + [num_nodes])
+    rng = uniform_block_range if uniform else block_range
+    bounds = np.array([rng(num_nodes, p, world_size)[0] for p in range(world_size)] + [num_nodes])
     owner = np.searchsorted(bounds, dst, side="right") - 1
     parts = []
     for p in range(world_size):
@@ -83,18 +95,28 @@ def partition_by_destination(src, dst, etype, norm, num_nodes, world_size):
     return parts
 
 
-def allgather_rows(local_rows, num_rows, group=None):
+def allgather_rows(local_rows, num_rows, group=None, uniform=False):
     """All-gather of node features for destination-partitioned message passing: every rank holds
-    rows [lo, hi) of a [num_rows, d] matrix and receives the full matrix.  Blocks may differ by one
-    row, so the gather is padded to the largest block."""
+    rows [lo, hi) of a [num_rows, d] matrix and receives the full matrix.  Blocks may differ in
+    size (block_range: by one row; uniform_block_range: the last ones are shorter), so the gather
+    is padded to the largest block."""
     rank, ws = dist.get_rank(group), dist.get_world_size(group)
-    sizes = [block_range(num_rows, p, ws)[1] - block_range(num_rows, p, ws)[0] for p in range(ws)]
+    rng = uniform_block_range if uniform else block_range
+    sizes = [rng(num_rows, p, ws)[1] - rng(num_rows, p, ws)[0] for p in range(ws)]
     pad = max(sizes)
     buf = local_rows.new_zeros((pad,) + tuple(local_rows.shape[1:]))
     buf[:local_rows.shape[0]] = local_rows
-    out = [torch.empty_like(buf) for _ in range(ws)]
-    dist.all_gather(out, buf, group=group)
-    return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
+    out = local_rows.new_empty((ws * pad,) + tuple(local_rows.shape[1:]))
+    if hasattr(dist, "all_gather_into_tensor") and dist.get_backend(group) != "gloo":
+        dist.all_gather_into_tensor(out, buf, group=group)
+        parts = out.view((ws, pad) + tuple(local_rows.shape[1:]))
+    else:
+        lst = [torch.empty_like(buf) for _ in range(ws)]
+        dist.all_gather(lst, buf, group=group)
+        parts = lst
+    if all(n == pad for n in sizes):
+        return out if not isinstance(parts, list) else torch.cat(parts, dim=0)
+    return torch.cat([parts[p][:n] for p, n in enumerate(sizes)], dim=0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -106,11 +128,99 @@ class Partition:
     destinations are local: dst - lo).  Attach to the graph object as ``g.partition``; RelGraphConv,
     KGVAE and LinkPredict then insert the all-gathers / reductions below."""
 
-    def __init__(self, lo, hi, n_global, group=None):
+    def __init__(self, lo, hi, n_global, group=None, peer_gather=None):
         self.lo, self.hi, self.n_global, self.group = int(lo), int(hi), int(n_global), group
         self.n_local = self.hi - self.lo
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # uniform blocks (uniform_block_range) allow the fused peer-memory gather: the kernel finds
+        # the owner of a source row as row // blk
+        blk = (self.n_global + self.world_size - 1) // self.world_size
+        uniform = (self.lo, self.hi) == uniform_block_range(self.n_global, self.rank, self.world_size)
+        self.blk = blk if uniform else None
+        self.peer_gather = uniform if peer_gather is None else (bool(peer_gather) and uniform)
+        self._peer_rows = {}
+
+    def peer_rows(self, key, width, device):
+        """The PeerRows buffer of one layer (created collectively on first use, then reused)."""
+        k = (key, int(width))
+        if k not in self._peer_rows:
+            self._peer_rows[k] = PeerRows(self.blk, width, device, self.group)
+        return self._peer_rows[k]
+
+
+class _DeviceMemory:
+    """Exposes raw device memory through __cuda_array_interface__ so torch can alias it (no copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _wrap_device_memory(ptr, shape, device):
+    return torch.as_tensor(_DeviceMemory(ptr, shape), device=device)
+
+
+class PeerRows:
+    """One [blk, width] fp32 row block per rank, each in its owner's HBM and mapped into every
+    process of the node with CUDA IPC, so that a kernel on any rank can read any rank's rows over
+    NVLink.  ``publish(x)`` copies this rank's rows in between two stream-ordered barriers: the
+    first keeps peers that still read the previous contents (their backward pass) safe, the second
+    makes the new rows visible before anyone gathers from them.  ``ptrs`` is the device-resident
+    table of the P block base pointers that kg_bdd_rel_fwd / kg_bdd_rel_bwd take as ``x_parts``."""
+
+    def __init__(self, blk_rows, width, device, group=None):
+        import ctypes
+        self.group = group
+        self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+        self.blk, self.width = int(blk_rows), int(width)
+        self.device = torch.device(device)
+        nbytes = self.blk * self.width * 4
+        with torch.cuda.device(self.device):
+            ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            L.call("kg_peer_alloc", nbytes, ctypes.byref(ptr), handle)
+            self._own_ptr = ptr.value
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._peer_ptrs, base = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    base.append(self._own_ptr)
+                    continue
+                p, buf = ctypes.c_void_p(), (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                L.call("kg_peer_open", buf, ctypes.byref(p))      # mapped on MY device, peer access enabled
+                self._peer_ptrs.append(p.value)
+                base.append(p.value)
+        self.local = _wrap_device_memory(self._own_ptr, (self.blk, self.width), self.device)
+        self.views = [self.local if r == self.rank else _wrap_device_memory(b, (self.blk, self.width), self.device)
+                      for r, b in enumerate(base)]
+        self.ptrs = torch.tensor(base, dtype=torch.int64, device=self.device)
+        self._sync = torch.zeros(1, device=self.device)
+
+    def close(self):
+        """Unmap the peers' blocks and free this rank's (collective: every rank must be done reading)."""
+        if self._own_ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        self.barrier()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._peer_ptrs:
+                L.call("kg_peer_close", p)
+            self.barrier()
+            torch.cuda.synchronize(self.device)
+            L.call("kg_peer_free", self._own_ptr)
+        self._own_ptr, self._peer_ptrs, self.views, self.local = None, [], [], None
+
+    def barrier(self):
+        dist.all_reduce(self._sync, group=self.group)       # stream-ordered on every rank
+
+    def publish(self, x):
+        if x.shape[0] > self.blk or x.shape[1] != self.width:
+            raise RuntimeError(f"PeerRows: {tuple(x.shape)} rows do not fit a [{self.blk}, {self.width}] block")
+        self.barrier()
+        self.local[:x.shape[0]].copy_(x)
+        self.barrier()
 
 
 class AllGatherRowsFn(torch.autograd.Function):
@@ -120,14 +230,29 @@ class AllGatherRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, part):
         ctx.part = part
-        return allgather_rows(x_local.contiguous(), part.n_global, part.group)
+        return allgather_rows(x_local.contiguous(), part.n_global, part.group, uniform=part.blk is not None)
 
     @staticmethod
     def backward(ctx, g_full):
         part = ctx.part
-        g_full = g_full.contiguous()
-        dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=part.group)   # blocks differ by a row: sum, then slice
-        return g_full[part.lo:part.hi].clone(), None
+        return reduce_scatter_rows(g_full.contiguous(), part), None
+
+
+def reduce_scatter_rows(g_full, part):
+    """Sum over ranks of a [n_global (or more), d] matrix of per-row contributions; every rank keeps
+    its own rows [lo, hi).  Uniform blocks: one reduce-scatter (each rank receives 1/P of the
+    bytes); otherwise all-reduce and slice."""
+    if part.blk is not None and hasattr(dist, "reduce_scatter_tensor") and dist.get_backend(part.group) != "gloo":
+        rows = part.blk * part.world_size
+        if g_full.shape[0] < rows:
+            pad = g_full.new_zeros((rows,) + tuple(g_full.shape[1:]))
+            pad[:g_full.shape[0]] = g_full
+            g_full = pad
+        out = g_full.new_empty((part.blk,) + tuple(g_full.shape[1:]))
+        dist.reduce_scatter_tensor(out, g_full[:rows], op=dist.ReduceOp.SUM, group=part.group)
+        return out[:part.n_local]
+    dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=part.group)
+    return g_full[part.lo:part.hi].clone()
 
 
 class AllReduceSumFn(torch.autograd.Function):

@@ -34,6 +34,14 @@ const char* kg_last_error(void);
 int kg_version(void);
 /* device attributes used for grid sizing (SM count etc.); also a liveness check */
 int kg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Peer-visible buffers for destination-partitioned training (new; the reference is single-process):
+ * cudaMalloc'ed, zero-filled memory exported with CUDA IPC (64-byte handle) and opened by the other
+ * ranks of the node on their own current device with lazy peer access; the returned pointers go
+ * into the x_parts table of kg_bdd_rel_fwd / kg_bdd_rel_bwd. */
+int kg_peer_alloc(size_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
+int kg_peer_open(const unsigned char* handle /* 64 bytes */, void** ptr);
+int kg_peer_close(void* ptr);
+int kg_peer_free(void* ptr);
 
 /* ------------------------------------------------------------------------------------
  * a1  graph construction
@@ -99,11 +107,17 @@ int kg_bdd_weight_layouts(const float* weight, int num_etypes, int num_bases, in
  * HBM (evict-first in L2) so that it does not displace the L2-resident tile being reduced into. */
 #define KG_HINT_STREAM_X 1
 #define KG_HINT_STREAM_D 2
-int kg_bdd_rel_fwd(const float* x, const void* rel_pack, int n_edges, const float* weight,
-                   const float* w_fwd, int num_bases, int si, int so, float* agg, int hints, void* stream);
-int kg_bdd_rel_bwd(const float* x, const float* dagg, const void* rel_pack, int n_edges,
-                   const float* weight, const float* w_bwd, int num_bases, int si, int so,
-                   float* dx, float* dweight, int hints, void* stream);
+#define KG_HINT_TILE_RESIDENT 4   /* node-tiled list: keep the rows reduced into (and x in backward) evict-last */
+/* x_parts (optional, device array of pointers) + part_rows: destination-partitioned training - source
+ * rows live in one block per rank (row r = row r % part_rows of x_parts[r / part_rows], peer blocks
+ * mapped with CUDA IPC) and are fetched over NVLink by the kernel's own gather stage, replacing the
+ * all-gather of layer inputs (5x5 / 5x10 block shapes only; pass NULL, 0 and x otherwise). */
+int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows, const void* rel_pack, int n_edges,
+                   const float* weight, const float* w_fwd, int num_bases, int si, int so, float* agg,
+                   int hints, void* stream);
+int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows, const float* dagg,
+                   const void* rel_pack, int n_edges, const float* weight, const float* w_bwd,
+                   int num_bases, int si, int so, float* dx, float* dweight, int hints, void* stream);
 /* The reference model's block shapes (5x5, 5x10; rgcn_bdd_own.cuh) read `weight` in the DGL layout
  * directly - a thread owns whole diagonal blocks in registers - and need no derived layout: pass
  * w_fwd / w_bwd = NULL when this returns 0.  Other shapes need kg_bdd_weight_layouts first. */

@@ -36,7 +36,7 @@ def _setup(K, dev, n_flows):
     return model, g, etype, node_norm, trip, labels, eps, m1, m2, n_ent
 
 
-def _worker(rank, port, n_flows, out):
+def _worker(rank, port, n_flows, mode, out):
     import gcn_vae_b200 as K
     from gcn_vae_b200 import parallel
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -60,13 +60,15 @@ def _worker(rank, port, n_flows, out):
         model.zero_grad(set_to_none=True)
 
         # ---- partitioned step ------------------------------------------------------------------
-        parts = parallel.partition_by_destination(g._src, g._dst, etype, edge_norm, N, WORLD)
+        peer = mode == "peer"
+        parts = parallel.partition_by_destination(g._src, g._dst, etype, edge_norm, N, WORLD, uniform=peer)
         mine = parts[rank]
         lo, hi = mine["lo"], mine["hi"]
         pg = K.Graph()
         pg.add_nodes(N)
         pg.add_edges(mine["src"], mine["dst"] - lo)
-        pg.partition = parallel.Partition(lo, hi, N)
+        pg.partition = parallel.Partition(lo, hi, N, peer_gather=peer)
+        assert pg.partition.peer_gather == peer
         enc.preset_eps = eps[lo:hi].to(dev)
         enc.rconv_layer_1.dropout_mask, enc.rconv_layer_2.dropout_mask = m1[lo:hi].to(dev), m2[lo:hi].to(dev)
         zl = model(pg, ids[lo:hi], torch.from_numpy(mine["etype"]).to(dev),
@@ -85,14 +87,16 @@ def _worker(rank, port, n_flows, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_flows", [0, 1])
-def test_partitioned_step_matches_single_gpu(n_flows):
+@pytest.mark.parametrize("n_flows,mode", [(0, "allgather"), (1, "allgather"), (0, "peer"), (1, "peer")])
+def test_partitioned_step_matches_single_gpu(n_flows, mode):
+    """mode "allgather": NCCL all-gather of every layer input; mode "peer": the message-passing kernels
+    gather source rows from the owners' HBM over NVLink (CUDA IPC row blocks), reduce-scatter backward."""
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 GPUs")
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(port, n_flows, out), nprocs=WORLD, join=True)
+        mp.spawn(_worker, args=(port, n_flows, mode, out), nprocs=WORLD, join=True)
         res = [out[r] for r in range(WORLD)]
     for r in range(WORLD):
         w = res[r]["want"]

@@ -77,6 +77,16 @@ def _worker(rank, port, out):
         ((full2 * wgt).sum() + s_all * (rank + 2.0)).backward()
         res["gather_grad"] = xl.grad.clone()
         res["block"] = (mine["lo"], mine["hi"])
+
+        # --- uniform blocks (what the peer-memory gather needs): ceil(N / P) rows each --------------
+        uparts = parallel.partition_by_destination(src, dst, et, None, N, WORLD, uniform=True)
+        um = uparts[rank]
+        upart = parallel.Partition(um["lo"], um["hi"], N)
+        res["uniform"] = (um["lo"], um["hi"], upart.blk, upart.peer_gather, part.blk)
+        ufull = parallel.allgather_rows(feats[um["lo"]:um["hi"]], N, uniform=True)
+        res["uniform_gathered_ok"] = bool(torch.equal(ufull, feats))
+        contrib = torch.arange(WORLD * upart.blk * 3, dtype=torch.float32).view(-1, 3) * (rank + 1)
+        res["rs_rows"] = parallel.reduce_scatter_rows(contrib.clone(), upart)
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -103,6 +113,13 @@ def test_two_rank_host_logic():
         lo, hi = res[r]["block"]
         want = wsum[lo:hi] + sum(q + 2.0 for q in range(WORLD))
         assert torch.allclose(res[r]["gather_grad"], want)
+    # uniform blocks: [0, 12), [12, 23) for N = 23; owner(row) = row // 12; reduce-scatter keeps own rows
+    total = torch.arange(WORLD * 12 * 3, dtype=torch.float32).view(-1, 3) * sum(r + 1 for r in range(WORLD))
+    for r in range(WORLD):
+        lo, hi, blk, peer_ok, blk_nonuniform = res[r]["uniform"]
+        assert (lo, hi, blk) == ((0, 12, 12) if r == 0 else (12, 23, 12)) and peer_ok and blk_nonuniform is None
+        assert res[r]["uniform_gathered_ok"]
+        assert torch.equal(res[r]["rs_rows"], total[lo:hi])
     # partition: every edge exactly once, owned by the rank whose node block holds its destination
     src, dst = res[0]["edges"]
     seen = np.concatenate([ids for _, _, ids in res[0]["parts"]])

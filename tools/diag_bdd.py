@@ -19,7 +19,7 @@ for (n, e, r, B, si, so) in [(1900, 4000, 474, 100, 5, 5), (1900, 4000, 474, 100
     w_fwd = torch.empty((r, si, B * so), device=dev); w_bwd = torch.empty((r, so, B * si), device=dev)
     L.call("kg_bdd_weight_layouts", L.f32(w), r, B, si, so, L.f32(w_fwd), L.f32(w_bwd), L.stream())
     agg = torch.zeros(n, B * so, device=dev)
-    L.call("kg_bdd_rel_fwd", L.f32(x), L.i32(gi.rel_pack), e, L.f32(w), L.f32(w_fwd), B, si, so, L.f32(agg), 0, L.stream())
+    L.call("kg_bdd_rel_fwd", L.f32(x), None, 0, L.i32(gi.rel_pack), e, L.f32(w), L.f32(w_fwd), B, si, so, L.f32(agg), 0, L.stream())
     # float64 reference in chunks
     ref = torch.zeros(n, B * so, device=dev, dtype=torch.float64)
     dref_x = torch.zeros(n, B * si, device=dev, dtype=torch.float64)
@@ -35,6 +35,6 @@ for (n, e, r, B, si, so) in [(1900, 4000, 474, 100, 5, 5), (1900, 4000, 474, 100
         dref_x.index_add_(0, src[sl].long(), torch.matmul(ws, gd).view(-1, B * si))
         dref_w.index_add_(0, et[sl].long(), torch.matmul(xs.transpose(-1, -2), gd.transpose(-1, -2)))
     dx = torch.zeros(n, B * si, device=dev); dw = torch.zeros_like(w)
-    L.call("kg_bdd_rel_bwd", L.f32(x), L.f32(g), L.i32(gi.rel_pack), e, L.f32(w), L.f32(w_bwd), B, si, so, L.f32(dx), L.f32(dw), 0, L.stream())
+    L.call("kg_bdd_rel_bwd", L.f32(x), None, 0, L.f32(g), L.i32(gi.rel_pack), e, L.f32(w), L.f32(w_bwd), B, si, so, L.f32(dx), L.f32(dw), 0, L.stream())
     rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
     print(f"n={n} e={e} B={B} {si}x{so}: fwd {rel(agg, ref):.2e}  dx {rel(dx, dref_x):.2e}  dW {rel(dw.view(r, B, si, so), dref_w):.2e}", flush=True)
