@@ -259,6 +259,133 @@ def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edge
     return out
 
 
+def run_partitioned(args):
+    """--workload wikikg2-part (BASELINE.json configs[4]): full-graph GCN-VAE training step on a synthetic
+    ogbl-wikikg2-shaped KG (2.5 M entities, 535 relations, 16 M triples = 32 M directed edges, h = 500,
+    100 blocks), destination-partitioned over the N GPUs of one box: rank p owns a block of nodes, every
+    edge into it, and its rows of the embedding table / h1 / h2 / z.  Layer inputs are NOT all-gathered:
+    the message-passing kernels gather source rows from the owners' HBM over NVLink (peer row blocks);
+    gradients wrt the sources are reduce-scattered; the decoder scores 2.2 M sampled triplets (split over
+    the ranks) against the all-gathered z.  STRONG scaling: the graph is fixed, value = 32 M edges / step
+    time (max over ranks).  N = 1 runs the same step unpartitioned."""
+    import torch.distributed as dist
+    import gcn_vae_b200 as K
+    from gcn_vae_b200 import _lib as L
+    from gcn_vae_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    scale = args.scale
+    n_nodes, n_rels, n_trip = int(2_500_000 * scale), 535, int(16_000_000 * scale)
+    n_scored = int(2_200_000 * scale)
+    # the same global graph on every rank (same device generator seed), then this rank's share
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    s = torch.randint(0, n_nodes, (n_trip,), device=dev, generator=gen, dtype=torch.int32)
+    o = torch.randint(0, n_nodes, (n_trip,), device=dev, generator=gen, dtype=torch.int32)
+    r = torch.randint(0, n_rels, (n_trip,), device=dev, generator=gen, dtype=torch.int32)
+    src, dst, et = torch.cat([s, o]), torch.cat([o, s]), torch.cat([r, r + n_rels])     # + reverse edges
+    deg = torch.bincount(dst.long(), minlength=n_nodes).clamp_(min=1).float()
+    trip = torch.stack([torch.randint(0, n_nodes, (n_scored,), device=dev, generator=gen, dtype=torch.int32),
+                        torch.randint(0, n_rels, (n_scored,), device=dev, generator=gen, dtype=torch.int32),
+                        torch.randint(0, n_nodes, (n_scored,), device=dev, generator=gen, dtype=torch.int32)], 1)
+    labels = (torch.rand(n_scored, device=dev, generator=gen) < 1.0 / (NEG + 1)).float()
+    n_edges_global = int(src.numel())
+    if world > 1:
+        lo, hi = parallel.uniform_block_range(n_nodes, rank, world)
+        keep = (dst >= lo) & (dst < hi)
+        src, dst, et = src[keep].contiguous(), (dst[keep] - lo).contiguous(), et[keep].contiguous()
+        norm = (1.0 / deg)[lo:hi][dst.long()].contiguous()
+        t0, t1 = parallel.block_range(n_scored, rank, world)
+        trip, labels = trip[t0:t1].contiguous(), labels[t0:t1].contiguous()
+    else:
+        lo, hi = 0, n_nodes
+        norm = (1.0 / deg)[dst.long()].contiguous()
+    del deg, s, o, r
+    n_local = hi - lo
+    g = K.Graph()
+    g._n = n_nodes if world > 1 else n_local
+    g._dev_edges[dev] = (src, dst)
+    if world > 1:
+        g.partition = parallel.Partition(lo, hi, n_nodes, peer_gather=not args.allgather)
+    torch.manual_seed(0)
+    # the embedding table is sharded by owner: each rank holds (and updates) only its rows
+    model = K.LinkPredict(K.KGVAE, max(n_local, 1), H, n_rels, num_bases=BASES, dropout=DROPOUT, use_cuda=True,
+                          reg_param=REG, kl_param=KL, k=MOG_K, n_flows=0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    sharded = {id(model.encoder.input_layer.embedding.weight)}
+    replicated = [p for p in model.parameters() if p.requires_grad and id(p) not in sharded]
+    ids = torch.arange(n_local, dtype=torch.int32, device=dev).view(-1, 1)
+    norm2 = norm.view(-1, 1)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        embed = model(g, ids, et, norm2)
+        loss, _, _, _ = model.get_loss(g, embed, trip, labels)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_sum_grads(replicated)
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    model.train()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    clocks = ClockSampler(local)
+    L.launches = 0
+    L.profile = {}
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = step()
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b)
+    launches = L.launches
+    prof, L.profile = L.profile, None
+    sync_all()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    clock_info = clocks.stop()
+    if rank == 0:
+        op_ms = {tag: sum(x.elapsed_time(y) for x, y in evs) for tag, evs in prof.items()}
+        total_ops = sum(op_ms.values())
+        for tag, v in sorted(op_ms.items(), key=lambda kv: -kv[1])[:12]:
+            log(f"  {tag:44s} {v / args.steps:8.3f} ms/step  {100 * v / total_ops:5.1f}%")
+        line = {
+            "metric": METRIC, "value": n_edges_global * args.steps / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "wikikg2-part", "entities": n_nodes, "relations": n_rels, "graph_edges": n_edges_global,
+                       "scored_triplets": n_scored, "h": H, "bases": BASES, "scale": scale,
+                       "parallelism": (f"destination-partitioned x{world}, "
+                                       + ("NCCL all-gather of layer inputs" if args.allgather else
+                                          "layer inputs gathered from peer HBM by the message-passing kernels (NVLink)")
+                                       + ", reduce-scatter of source gradients, all-gather of z for the decoder")
+                                      if world > 1 else "single GPU, unpartitioned",
+                       "timed": "fwd + loss + bwd + grad all-reduce + Adam; one CUDA-event pair over all steps",
+                       "l2": "inputs (5 GB feature matrices) far larger than L2"},
+            "loss": float(loss), "gpu_launches": launches, "clocks": clock_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import gcn_vae_b200 as K
@@ -487,12 +614,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fb15k237-full",
-                    choices=["fb15k237-full", "fb15k237-step", "wn18-full", "wn18-step"],
+                    choices=["fb15k237-full", "fb15k237-step", "wn18-full", "wn18-step", "wikikg2-part"],
                     help="fb15k237-full is the headline (BASELINE.json configs[1]); wn18-* with --n-flows 3 is configs[2]")
     ap.add_argument("--n-flows", type=int, default=0)
     ap.add_argument("--bases", type=int, default=None,
                     help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
                          "36 directed relation types, which does not divide 500)")
+    ap.add_argument("--scale", type=float, default=1.0, help="wikikg2-part: shrink the graph (tests)")
+    ap.add_argument("--allgather", action="store_true",
+                    help="wikikg2-part: NCCL all-gather of layer inputs instead of the peer-memory gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streaming-only", action="store_true",
                     help="run only the wikikg2-shaped message-passing leg (profiling aid; prints its JSON object)")
@@ -508,6 +638,8 @@ def main():
                                                iters=max(1, args.steps))))
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "wikikg2-part":
+        run_partitioned(args)
     else:
         run_gpu(args)
 

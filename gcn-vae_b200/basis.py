@@ -66,6 +66,7 @@ class BasisIdConvFn(torch.autograd.Function):
         else:
             agg = torch.zeros((n, out_f), dtype=torch.float32, device=dev)
         cf = None if coef is None else _c(coef)
+        gi.ensure_node_major()
         L.call("kg_basis_id_fwd", L.f32(V), L.f32(cf), L.i32(ids32), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), n,
                n_in, NB, out_f, L.f32(agg), L.stream())
         mask = None if drop_mask is None else _c(drop_mask)

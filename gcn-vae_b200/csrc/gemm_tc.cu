@@ -64,7 +64,7 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int K, int rows, i
                        const unsigned* __restrict__ amax_bits, __half* __restrict__ cat,
                        float* __restrict__ inv_scale) {
   __shared__ float tile[32][33];
-  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;     // K (up to millions of nodes) on grid.x
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int k = k0 + i, r = r0 + threadIdx.x;
     tile[i][threadIdx.x] = (k < K && r < rows) ? __ldg(src + (size_t)k * ld + r) : 0.f;
@@ -76,7 +76,7 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int K, int rows, i
     const float s = split_scale(__uint_as_float(__ldg(amax_bits + r)));
     __half* row = cat + (size_t)r * 2 * Kp;
     split_store(tile[threadIdx.x][i], s, row + k, row + Kp + k);
-    if (blockIdx.y == 0 && threadIdx.x == 0) inv_scale[r] = 1.f / s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[r] = 1.f / s;
   }
 }
 
@@ -239,7 +239,7 @@ int convert_operand(const float* src, int ld, bool k_contig, int rows, int K, in
     const int k_chunk = 512;
     colmax_kernel<<<dim3(kg_div_up(rows, 32), kg_div_up(K, k_chunk)), dim3(32, 8), 0, st>>>(src, ld, K, rows, k_chunk, amax);
     KG_LAUNCH_OK();
-    split_transpose_kernel<<<dim3(kg_div_up(rows, 32), Kp / 32), dim3(32, 8), 0, st>>>(src, ld, K, rows, Kp, amax, cat, inv_scale);
+    split_transpose_kernel<<<dim3(Kp / 32, kg_div_up(rows, 32)), dim3(32, 8), 0, st>>>(src, ld, K, rows, Kp, amax, cat, inv_scale);
     KG_LAUNCH_OK();
   }
   return KG_OK;

@@ -204,8 +204,9 @@ static int build_index(const int* e_src, const int* e_dst, const int* e_type, co
 
   iota<<<gridE, kThreads, 0, st>>>(vals_in, E);
   KG_LAUNCH_OK();
-  // dst-major (stable: original order is the tie-break)
-  if (dst_sorted) {
+  // dst-major (stable: original order is the tie-break); optional
+  if (fwd_pack == nullptr) {
+  } else if (dst_sorted) {
     fill_pack<<<gridE, kThreads, 0, st>>>(nullptr, e_src, e_dst, e_type, e_norm, node_norm, E, 0, fwd_pack);
   } else {
     tb = temp_bytes;
@@ -214,12 +215,14 @@ static int build_index(const int* e_src, const int* e_dst, const int* e_type, co
     fill_pack<<<gridE, kThreads, 0, st>>>(vals_out, e_src, e_dst, e_type, e_norm, node_norm, E, 0, fwd_pack);
   }
   KG_LAUNCH_OK();
-  // src-major
-  tb = temp_bytes;
-  KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, e_src, keys_out, vals_in, vals_out, E, 0,
-                                          bits_for(N), st));
-  fill_pack<<<gridE, kThreads, 0, st>>>(vals_out, e_src, e_dst, e_type, e_norm, node_norm, E, 1, bwd_pack);
-  KG_LAUNCH_OK();
+  // src-major; optional
+  if (bwd_pack != nullptr) {
+    tb = temp_bytes;
+    KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, e_src, keys_out, vals_in, vals_out, E, 0,
+                                            bits_for(N), st));
+    fill_pack<<<gridE, kThreads, 0, st>>>(vals_out, e_src, e_dst, e_type, e_norm, node_norm, E, 1, bwd_pack);
+    KG_LAUNCH_OK();
+  }
   // etype-major
   tb = temp_bytes;
   KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, e_type, keys_out, vals_in, vals_out, E, 0,
@@ -302,12 +305,16 @@ extern "C" int kg_graph_rel_tiled(const int32_t* e_src, const int32_t* e_dst, co
 __global__ void patch_pack_norm(int4* fwd, int4* bwd, int4* rel, const float* node_norm, int E) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;
-  int4 f = fwd[k];
-  f.z = __float_as_int(node_norm[f.w]);      // {src, etype, norm, dst}
-  fwd[k] = f;
-  int4 b = bwd[k];
-  b.z = __float_as_int(node_norm[b.x]);      // {dst, etype, norm, edge}
-  bwd[k] = b;
+  if (fwd) {
+    int4 f = fwd[k];
+    f.z = __float_as_int(node_norm[f.w]);      // {src, etype, norm, dst}
+    fwd[k] = f;
+  }
+  if (bwd) {
+    int4 b = bwd[k];
+    b.z = __float_as_int(node_norm[b.x]);      // {dst, etype, norm, edge}
+    bwd[k] = b;
+  }
   int4 r = rel[k];
   r.w = __float_as_int(node_norm[r.y]);      // {src, dst, etype, norm}
   rel[k] = r;

@@ -74,48 +74,73 @@ __global__ void prior_prepare_kernel(const float* __restrict__ z_pre, int k, int
   ws[(size_t)2 * k * h + t] = logf(sqrtf(v));
 }
 
+// A warp takes kKlWarpRows consecutive rows at a time so that every prior value it fetches
+// (3 arrays x k mixtures per column) is applied to several rows: 3 + 3k / kKlWarpRows loads per
+// element instead of 3 + 3k.
+static constexpr int kKlWarpRows = 4;
+
 __global__ void __launch_bounds__(kThreads)
 kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
                   const float* __restrict__ zv, const float* __restrict__ z_pre,
                   const float* __restrict__ ws, int n, int h, int k, float* __restrict__ kl_rows,
                   float* __restrict__ resp) {
-  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int row0 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kKlWarpRows;
   const int lane = threadIdx.x & 31;
-  if (row >= n) return;
+  if (row0 >= n) return;
   const float* inv2v = ws + (size_t)k * h;
   const float* lsq = ws + (size_t)2 * k * h;
-  float a = 0.f, b[kMaxMix];
+  float a[kKlWarpRows], b[kKlWarpRows][kMaxMix];
 #pragma unroll
-  for (int i = 0; i < kMaxMix; ++i) b[i] = 0.f;
+  for (int q = 0; q < kKlWarpRows; ++q) {
+    a[q] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxMix; ++i) b[q][i] = 0.f;
+  }
   for (int d = lane; d < h; d += 32) {
-    const float zc = z[(size_t)row * h + d];
-    const float t = zc - zm[(size_t)row * h + d];
-    const float v = zv[(size_t)row * h + d];
-    a += -(t * t) / (2.f * v) - logf(sqrtf(v)) - KG_LOG_SQRT_2PI;          // utils.py:396
+    float zc[kKlWarpRows];
+#pragma unroll
+    for (int q = 0; q < kKlWarpRows; ++q) {
+      const int row = min(row0 + q, n - 1);                  // rows past the end repeat the last one (not stored)
+      zc[q] = z[(size_t)row * h + d];
+      const float t = zc[q] - zm[(size_t)row * h + d];
+      const float v = zv[(size_t)row * h + d];
+      a[q] += -(t * t) / (2.f * v) - logf(sqrtf(v)) - KG_LOG_SQRT_2PI;      // utils.py:396
+    }
 #pragma unroll
     for (int i = 0; i < kMaxMix; ++i)
       if (i < k) {
-        const float u = zc - __ldg(z_pre + (size_t)i * h + d);
-        b[i] += -(u * u) * __ldg(inv2v + (size_t)i * h + d) - __ldg(lsq + (size_t)i * h + d) - KG_LOG_SQRT_2PI;
+        const float pm = __ldg(z_pre + (size_t)i * h + d), iv = __ldg(inv2v + (size_t)i * h + d),
+                    ls = __ldg(lsq + (size_t)i * h + d);
+#pragma unroll
+        for (int q = 0; q < kKlWarpRows; ++q) {
+          const float u = zc[q] - pm;
+          b[q][i] += -(u * u) * iv - ls - KG_LOG_SQRT_2PI;
+        }
       }
   }
-  a = kg_warp_sum(a);
-  float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < kMaxMix; ++i)
-    if (i < k) {
-      b[i] = kg_warp_sum(b[i]);
-      mx = fmaxf(mx, b[i]);
+  for (int q = 0; q < kKlWarpRows; ++q) {
+    const int row = row0 + q;
+    const float aq = kg_warp_sum(a[q]);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxMix; ++i)
+      if (i < k) {
+        b[q][i] = kg_warp_sum(b[q][i]);
+        mx = fmaxf(mx, b[q][i]);
+      }
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxMix; ++i)
+      if (i < k) se += expf(b[q][i] - mx);
+    const float lse = mx + logf(se);                                        // utils.py:413-415
+    if (row < n) {
+      if (lane == 0) kl_rows[row] = aq - (lse - logf((float)k));            // utils.py:428, model.py:86
+#pragma unroll
+      for (int i = 0; i < kMaxMix; ++i)
+        if (i < k && lane == (i & 31)) resp[(size_t)row * k + i] = expf(b[q][i] - lse);
     }
-  float se = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxMix; ++i)
-    if (i < k) se += expf(b[i] - mx);
-  const float lse = mx + logf(se);                                          // utils.py:413-415
-  if (lane == 0) kl_rows[row] = a - (lse - logf((float)k));                 // utils.py:428, model.py:86
-#pragma unroll
-  for (int i = 0; i < kMaxMix; ++i)
-    if (i < k && lane == (i & 31)) resp[(size_t)row * k + i] = expf(b[i] - lse);
+  }
 }
 
 static constexpr int kKlRows = 64;   // rows per CTA in the backward kernel
@@ -174,7 +199,7 @@ extern "C" int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z
   prior_prepare_kernel<<<kg_div_up((long long)k * h, kThreads), kThreads, 0, st>>>(z_pre, k, h, prior_ws);
   KG_LAUNCH_OK();
   if (n == 0) return KG_OK;
-  kl_mog_fwd_kernel<<<kg_div_up((long long)n * 32, kThreads), kThreads, 0, st>>>(
+  kl_mog_fwd_kernel<<<kg_div_up((long long)kg_div_up(n, kKlWarpRows) * 32, kThreads), kThreads, 0, st>>>(
       z, z_mean, z_var, z_pre, prior_ws, n, h, k, kl_rows, resp);
   KG_LAUNCH_OK();
   return KG_OK;

@@ -39,18 +39,30 @@ class GraphIndex:
         self.row_ptr = torch.empty(n_nodes + 1, **i32)
         self.col_ptr = torch.empty(n_nodes + 1, **i32)
         self.rel_ptr = torch.empty(n_etypes + 1, **i32)
-        self.fwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
-        self.bwd_pack = torch.empty((max(n_edges, 1), 4), **i32)
+        self.fwd_pack = self.bwd_pack = None      # dst-major / src-major lists: built on request only
         self.rel_pack = torch.empty((max(n_edges, 1), 4), **i32)
         self.e_src = self.e_dst = self.e_type = self.node_norm = self.e_norm = None
         self._tiled = {}
+
+    def ensure_node_major(self):
+        """Build the dst-major (fwd_pack + row_ptr) and src-major (bwd_pack + col_ptr) lists as well
+        (the basis id-feature kernel walks destinations; message passing itself only needs rel_pack)."""
+        if self.fwd_pack is None:
+            full = graph_index(self.e_src, self.e_dst, self.e_type, self._norm_per_edge(), self.n_nodes,
+                               self.n_etypes, node_major=True)
+            self.fwd_pack, self.bwd_pack, self.row_ptr, self.col_ptr = full.fwd_pack, full.bwd_pack, full.row_ptr, full.col_ptr
+        return self
+
+    def _norm_per_edge(self):
+        if self.e_norm is None and self.node_norm is not None:
+            self.e_norm = self.node_norm[self.e_dst.long()].contiguous()
+        return self.e_norm
 
     def tiled_rel_pack(self, by_src, tile_nodes):
         """kg_graph_rel_tiled: relation-major records grouped by node tile (built once, cached)."""
         key = (int(bool(by_src)), int(tile_nodes))
         if key not in self._tiled:
-            if self.e_norm is None and self.node_norm is not None:
-                self.e_norm = self.node_norm[self.e_dst.long()].contiguous()
+            self._norm_per_edge()
             pack = torch.empty_like(self.rel_pack)
             ws = L.workspace(L.lib().kg_graph_rel_tiled_workspace_bytes(self.n_edges), pack.device)
             L.call("kg_graph_rel_tiled", L.i32(self.e_src), L.i32(self.e_dst), L.i32(self.e_type),
@@ -63,23 +75,28 @@ class GraphIndex:
 # Rows that message passing reduces into (agg[dst] forward, x[src] + dx[src] backward) are kept
 # L2-resident: graphs whose reduced matrix exceeds this budget are walked tile by tile.
 L2_TILE_BYTES = 32 << 20
+L2_RESIDENT_BYTES = 96 << 20        # a reduced matrix up to this size is left untiled (126 MB L2)
 L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read with evict-first
 HINT_STREAM_X, HINT_STREAM_D, HINT_TILE_RESIDENT = 1, 2, 4
 
 
 def _rel_order(gi, by_src, n_rows, row_bytes):
     """the relation-major record list to walk for a reduction into ``n_rows`` rows of ``row_bytes``"""
-    if n_rows * row_bytes <= L2_TILE_BYTES or gi.n_edges == 0:
+    if n_rows * row_bytes <= max(L2_TILE_BYTES, L2_RESIDENT_BYTES) or gi.n_edges == 0:
         return gi.rel_pack
     return gi.tiled_rel_pack(by_src, max(L2_TILE_BYTES // row_bytes, 256))
 
 
-def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes):
-    """kg_graph_index: CSR by destination / source / relation for an edge list given in the
-    reference's order (DGLGraph.add_edges + etypes + norm, kgvae/utils.py:141-148)."""
+def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes, node_major=False):
+    """kg_graph_index: relation-major edge records (and, with ``node_major``, the dst-major and
+    src-major lists) for an edge list given in the reference's order (DGLGraph.add_edges + etypes +
+    norm, kgvae/utils.py:141-148)."""
     dev = e_src.device
     E = int(e_src.numel())
     gi = GraphIndex(n_nodes, E, n_etypes, dev)
+    if node_major:
+        gi.fwd_pack = torch.empty((max(E, 1), 4), dtype=torch.int32, device=dev)
+        gi.bwd_pack = torch.empty((max(E, 1), 4), dtype=torch.int32, device=dev)
     gi.e_src, gi.e_dst, gi.e_type = e_src, e_dst, e_type
     ws = L.workspace(L.lib().kg_graph_index_workspace_bytes(E), dev)
     norm = None if e_norm is None else _c(e_norm.reshape(-1).to(torch.float32))
@@ -90,13 +107,16 @@ def graph_index(e_src, e_dst, e_type, e_norm, n_nodes, n_etypes):
     return gi
 
 
-def graph_build(src, rel, dst, n_nodes, n_rels):
+def graph_build(src, rel, dst, n_nodes, n_rels, node_major=False):
     """kg_graph_build: the whole of utils.build_graph_from_triplets + node_norm_to_edge_norm
     (kgvae/utils.py:127-150, kgvae/link_predict.py:95-100) on the device."""
     dev = src.device
     T = int(src.numel())
     gi = GraphIndex(n_nodes, 2 * T, 2 * n_rels, dev)
     i32 = dict(dtype=torch.int32, device=dev)
+    if node_major:
+        gi.fwd_pack = torch.empty((max(2 * T, 1), 4), **i32)
+        gi.bwd_pack = torch.empty((max(2 * T, 1), 4), **i32)
     gi.e_src, gi.e_dst, gi.e_type = (torch.empty(max(2 * T, 1), **i32) for _ in range(3))
     gi.node_norm = torch.empty(n_nodes, dtype=torch.float32, device=dev)
     ws = L.workspace(L.lib().kg_graph_build_workspace_bytes(T), dev)

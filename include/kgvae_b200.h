@@ -54,7 +54,8 @@ int kg_peer_free(void* ptr);
  *   fwd_pack [2T] int4 {src, etype, bits(norm[dst]), dst}        (dst-major order)
  *   col_ptr [N+1], bwd_pack [2T] int4 {dst, etype, bits(norm), edge_id}  (src-major order)
  *   rel_ptr [2R+1], rel_pack [2T] int4 {src, dst, etype, bits(norm)}     (etype-major)
- * Limits: N < 2^24, 2R < 2^16.
+ * fwd_pack and bwd_pack are optional (NULL: that ordering is not built; the bdd message passing
+ * only walks rel_pack).  Limits: N < 2^24, 2R < 2^16.
  * ---------------------------------------------------------------------------------- */
 size_t kg_graph_build_workspace_bytes(int n_triplets);
 int kg_graph_build(const int32_t* src, const int32_t* rel, const int32_t* dst, int n_triplets,

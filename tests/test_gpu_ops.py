@@ -26,10 +26,10 @@ def _rand_graph(seed, n, e, r):
     return src, dst, et, norm
 
 
-def _index(src, dst, et, norm, n, r):
+def _index(src, dst, et, norm, n, r, node_major=False):
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(DEV)
     return ops.graph_index(t(src, torch.int32), t(dst, torch.int32), t(et, torch.int32),
-                           t(norm, torch.float32), n, r)
+                           t(norm, torch.float32), n, r, node_major=node_major)
 
 
 # ------------------------------------------------------------------------------ graph (a1)
@@ -37,7 +37,7 @@ def _index(src, dst, et, norm, n, r):
 def test_graph_index_integer_exact(n, e, r):
     src, dst, et, norm = _rand_graph(0, n, e, r)
     perm = np.random.default_rng(1).permutation(e)       # hand it over unsorted
-    gi = _index(src[perm], dst[perm], et[perm], norm[perm], n, r)
+    gi = _index(src[perm], dst[perm], et[perm], norm[perm], n, r, node_major=True)
     s_, d_, t_, w_ = src[perm], dst[perm], et[perm], norm[perm]
     for ptr, pack, key, cols in ((gi.row_ptr, gi.fwd_pack, d_, (s_, t_, w_.view(np.int32), d_)),
                                  (gi.col_ptr, gi.bwd_pack, s_, (d_, t_, w_.view(np.int32), np.arange(e))),
@@ -57,7 +57,7 @@ def test_graph_build_matches_reference_order(n, t, r):
     s, o, rel = rng.integers(0, n, t), rng.integers(0, n, t), rng.integers(0, r, t)
     want = O.build_graph_from_triplets(n, r, s, rel, o)
     dv = lambda a: torch.from_numpy(a.astype(np.int32)).to(DEV)
-    gi = ops.graph_build(dv(s), dv(rel), dv(o), n, r)
+    gi = ops.graph_build(dv(s), dv(rel), dv(o), n, r, node_major=True)
     assert np.array_equal(gi.e_src.cpu().numpy(), want["src"])
     assert np.array_equal(gi.e_dst.cpu().numpy(), want["dst"])
     assert np.array_equal(gi.e_type.cpu().numpy(), want["etype"])
@@ -213,6 +213,7 @@ def test_bdd_layer_fast_shapes_and_tiled_order(B, si, so, tiled, monkeypatch):
     down so that every matrix counts as larger than L2, streaming hints on)."""
     if tiled:
         monkeypatch.setattr(ops, "L2_TILE_BYTES", 40 * 4 * B * so)
+        monkeypatch.setattr(ops, "L2_RESIDENT_BYTES", 0)
         monkeypatch.setattr(ops, "L2_STREAM_BYTES", 0)
     n, e, r = 300, 6000, 11
     src, dst, et, norm = _rand_graph(7, n, e, r)
