@@ -249,8 +249,11 @@ int kg_sum_squares(const float* x, long long n, float* out, void* workspace, siz
                    void* stream);
 int kg_sum(const float* x, long long n, float* out, void* workspace, size_t workspace_bytes,
            void* stream);
-/* index structures, built once per batch of triplets (integer work, radix sort, no atomics):
- *   rs_rec  [S]  int4 {s, r, o, t}: the triplets in (r, s) order - runs share w[r] and z[s]
+/* index structures, built once per batch of triplets (integer work, radix sort):
+ *   rs_rec  [S]  int4 {a, r, b, t}: the triplets in (r, a) order - runs share w[r] and z[a].  DistMult
+ *     is symmetric in its two entities, so {a, b} is {s, o} or, for batches of >= 2^14 triplets, {o, s}
+ *     when the object end has the longer run of equal (r, entity) (estimated with a hashed counter
+ *     table; negatives that corrupt the subject share (r, o) with their positive)
  *   ent_ptr [n_nodes+1], ent_pack [2S] int4 {other, r, t, 0} in (entity, r) order: for entity v,
  *     every triplet where v is subject (other = object) or object (other = subject)
  * ent_ptr / ent_pack may be NULL: only rs_rec is built (the fused kg_distmult_bce_fwd needs no entity index).

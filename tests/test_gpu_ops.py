@@ -428,6 +428,45 @@ def test_distmult_loss_fwd_bwd(n, h, r, S):
         assert_close(a.grad, 3.0 * b.grad, RTOL, f"fused distmult {name}")
 
 
+def test_distmult_negative_sampled_batch():
+    """A batch shaped like the training step's (reference negative_sampling: each positive followed,
+    blockwise, by negatives that corrupt its subject or its object): the fused pass walks every
+    triplet from the end with the longer (relation, entity) run - objects for subject-corrupted
+    negatives - and must give the same loss and gradients whichever end leads."""
+    n, h, r, pos = 5000, 64, 9, 3000
+    rng = np.random.default_rng(11)
+    p = np.stack([rng.integers(0, n, pos), rng.integers(0, r, pos), rng.integers(0, n, pos)], 1).astype(np.int64)
+    np.random.seed(5)
+    trip, lab = K.utils.negative_sampling(p, n, 10)
+    assert len(trip) == 11 * pos >= 1 << 14
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(n, h, generator=g).requires_grad_(True)
+    w = torch.randn(r, h, generator=g).requires_grad_(True)
+    labels = torch.from_numpy(lab.astype(np.float32))
+    want = torch.nn.functional.binary_cross_entropy_with_logits(O.distmult_score(z, w, trip), labels)
+    want.backward()
+    cz, cw = z.detach().to(DEV).requires_grad_(True), w.detach().to(DEV).requires_grad_(True)
+    t32 = torch.from_numpy(trip).to(torch.int32).to(DEV)
+    loss = ops.DistMultBceFn.apply(cz, cw, t32, labels.to(DEV), None)
+    loss.backward()
+    assert_close(loss, want, 1e-5, "fused bce")
+    assert_close(cz.grad, z.grad, RTOL, "fused dz")
+    assert_close(cw.grad, w.grad, RTOL, "fused dw")
+    # the orientation really is used: some records lead with the object
+    idx = ops.TripletIndex(t32, n, r, entity_index=False)
+    rec = idx.rs_rec.cpu().numpy()
+    orig = trip[rec[:, 3]]
+    swapped = (rec[:, 0] == orig[:, 2]) & (rec[:, 2] == orig[:, 0]) & (orig[:, 0] != orig[:, 2])
+    kept = (rec[:, 0] == orig[:, 0]) & (rec[:, 2] == orig[:, 2])
+    assert bool(np.all(swapped | kept)) and np.array_equal(rec[:, 1], orig[:, 1])
+    assert swapped.sum() > pos                      # subject-corrupted negatives lead with their object
+    key = rec[:, 1].astype(np.int64) * n + rec[:, 0]
+    assert bool(np.all(np.diff(key) >= 0))          # (relation, leading entity) order
+    runs = 1 + int((np.diff(key) != 0).sum())
+    plain = len(np.unique(trip[:, 1] * n + trip[:, 0]))
+    assert runs < 0.6 * plain                       # far fewer, longer runs than (r, s) order gives
+
+
 def test_mean_square():
     x = torch.randn(300, 50).requires_grad_(True)
     x.pow(2).mean().backward()
