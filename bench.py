@@ -131,15 +131,18 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken while the benchmark runs.  nvidia-smi needs about a
+    second to start, so the sampler is created first thing; `mark()` / `stop()` bracket the window whose
+    samples are reported (warm-up through the last timed region - all of it GPU load)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_ms=20):
+        self.rows, self.proc, self.t0 = [], None, None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", str(period_ms),
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -148,19 +151,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, wait_s=3.0):
+        """Start of the reported window; waits (bounded) until nvidia-smi has produced its first sample."""
+        deadline = time.time() + wait_s
+        while self.proc is not None and not self.rows and time.time() < deadline:
+            time.sleep(0.02)
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time() + 0.03
+        time.sleep(0.05)                                      # let the last in-window sample arrive
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        num = lambda x: x.replace(".", "").isdigit()
+        sm = [float(r[0]) for r in rows if num(r[0])]
+        mx = [float(r[1]) for r in rows if num(r[1])]
+        pw = [float(r[2]) for r in rows if num(r[2])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
 def algorithmic_bytes(tag, shp):
@@ -281,6 +297,7 @@ def run_partitioned(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    clocks = ClockSampler(local)
     scale = args.scale
     n_nodes, n_rels, n_trip = int(2_500_000 * scale), 535, int(16_000_000 * scale)
     n_scored = int(2_200_000 * scale)
@@ -340,10 +357,10 @@ def run_partitioned(args):
             torch.cuda.synchronize()
 
     model.train()
+    clocks.mark()
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    clocks = ClockSampler(local)
     L.launches = 0
     L.profile = {}
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -399,6 +416,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    clocks = ClockSampler(local)
 
     shape = "wn18" if args.workload.startswith("wn18") else "FB15k-237"
     data = K.datasets.synthetic_kg(shape, seed=0)
@@ -470,10 +488,10 @@ def run_gpu(args):
         return float(t)
 
     model.train()
+    clocks.mark()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sync_all()
-    clocks = ClockSampler(local)
     L.launches = 0
     L.profile = {}
     ms_dev = max_over_ranks(timed(lambda: step(resident), args.steps))

@@ -203,7 +203,8 @@ fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E,
   const int4* rec = P_s + k_lo;
   float* ring = X_s + slot * kDepth * in_w;
   uint64_t* full = bars + slot * kDepth;
-  const uint64_t pol = l2_policy(hints & 1), pol_red = l2_policy_last(hints & 4);
+  // peer rows bypass the local L2 anyway; a cache hint on them only slows the copies down (measured 4x)
+  const uint64_t pol = l2_policy((hints & 1) && feat.parts == nullptr), pol_red = l2_policy_last(hints & 4);
   const uint32_t row_bytes = (uint32_t)in_w * 4;
   const bool leader = wsl == 0 && lane == 0;  // issues the slot's gathers
 
@@ -309,7 +310,8 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
   const int4* rec = P_s + k_lo;
   float* ring = R_s + slot * kDepth * row_w;
   uint64_t* full = bars + slot * kDepth;
-  const uint64_t pol_x = (hints & 4) ? l2_policy_last(true) : l2_policy(hints & 1), pol_d = l2_policy(hints & 2);
+  const uint64_t pol_x = x.parts != nullptr ? l2_policy(false) : (hints & 4) ? l2_policy_last(true) : l2_policy(hints & 1);
+  const uint64_t pol_d = l2_policy(hints & 2);
   const uint64_t pol_red = l2_policy_last(hints & 4);
   const uint32_t x_bytes = (uint32_t)in_w * 4, d_bytes = (uint32_t)out_w * 4;
   const bool leader = wsl == 0 && lane == 0;

@@ -81,7 +81,7 @@ class RelGraphConv(nn.Module):
                 raise TypeError("Block decomposition does not allow integer ID feature.")
             lo, n_dst, peer = -1, -1, None
             if part is not None:      # destination-partitioned
-                peer_ok = part.peer_gather and not ops.L.lib().kg_bdd_layouts_needed(
+                peer_ok = part.use_peer_gather(gi.n_edges) and not ops.L.lib().kg_bdd_layouts_needed(
                     self.num_bases, self.submat_in, self.submat_out)
                 if peer_ok:           # fused: the kernel gathers source rows from the owners' HBM
                     peer = part.peer_rows(id(self), self.in_feat, x.device)

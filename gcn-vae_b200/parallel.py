@@ -138,8 +138,19 @@ class Partition:
         blk = (self.n_global + self.world_size - 1) // self.world_size
         uniform = (self.lo, self.hi) == uniform_block_range(self.n_global, self.rank, self.world_size)
         self.blk = blk if uniform else None
-        self.peer_gather = uniform if peer_gather is None else (bool(peer_gather) and uniform)
+        # None: decide per graph (use_peer_gather); True/False: forced (True still needs uniform blocks)
+        self.peer_gather = None if peer_gather is None else (bool(peer_gather) and uniform)
         self._peer_rows = {}
+
+    def use_peer_gather(self, n_local_edges):
+        """Fused peer-memory gather or NCCL all-gather for a layer input?  Peer loads bypass the local
+        L2, so the gather moves one row per EDGE whose source is remote, the all-gather one row per
+        remote NODE: gather from peers when this rank has fewer edges than the graph has nodes."""
+        if self.blk is None:
+            return False
+        if self.peer_gather is not None:
+            return self.peer_gather
+        return int(n_local_edges) < self.n_global
 
     def peer_rows(self, key, width, device):
         """The PeerRows buffer of one layer (created collectively on first use, then reused)."""

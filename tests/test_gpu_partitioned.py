@@ -68,7 +68,7 @@ def _worker(rank, port, n_flows, mode, out):
         pg.add_nodes(N)
         pg.add_edges(mine["src"], mine["dst"] - lo)
         pg.partition = parallel.Partition(lo, hi, N, peer_gather=peer)
-        assert pg.partition.peer_gather == peer
+        assert pg.partition.use_peer_gather(len(mine["src"])) == peer
         enc.preset_eps = eps[lo:hi].to(dev)
         enc.rconv_layer_1.dropout_mask, enc.rconv_layer_2.dropout_mask = m1[lo:hi].to(dev), m2[lo:hi].to(dev)
         zl = model(pg, ids[lo:hi], torch.from_numpy(mine["etype"]).to(dev),

@@ -82,7 +82,9 @@ def _worker(rank, port, out):
         uparts = parallel.partition_by_destination(src, dst, et, None, N, WORLD, uniform=True)
         um = uparts[rank]
         upart = parallel.Partition(um["lo"], um["hi"], N)
-        res["uniform"] = (um["lo"], um["hi"], upart.blk, upart.peer_gather, part.blk)
+        res["uniform"] = (um["lo"], um["hi"], upart.blk,
+                          upart.use_peer_gather(N - 1) and not upart.use_peer_gather(N) and not part.use_peer_gather(1),
+                          part.blk)
         ufull = parallel.allgather_rows(feats[um["lo"]:um["hi"]], N, uniform=True)
         res["uniform_gathered_ok"] = bool(torch.equal(ufull, feats))
         contrib = torch.arange(WORLD * upart.blk * 3, dtype=torch.float32).view(-1, 3) * (rank + 1)
