@@ -27,9 +27,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL's version banner / warnings go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "train edges/s (fwd+bwd) + eval triples/s, FB15k-237 shape, 1/2/4/8 B200"
 H, BASES, MOG_K, DROPOUT, NEG = 500, 100, 10, 0.2, 10
