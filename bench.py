@@ -405,6 +405,151 @@ def run_partitioned(args):
         dist.destroy_process_group()
 
 
+def run_entity(args):
+    """--workload am-entity (BASELINE.json configs[3]): baselines/rgcn entity classification on a synthetic
+    AM-shaped typed graph (1 666 764 nodes, 133 relation types, 5 988 321 directed edges, 11 classes), the
+    reference's AM flags (kgvae/entity_classify.py:138-170 with baselines/rgcn/README.md:35-38: --n-bases 40
+    --n-hidden 10 --l2norm 5e-4, two layers, featureless nodes = integer ids).  One STEP = one full-graph
+    training epoch as in entity_classify.py:106-113: forward over every edge (input layer = basis lookup
+    sum_b coef[r,b] V[b, src, :] without materialising the [R, N, h] table, output layer = dense basis
+    conv + softmax), cross-entropy on the training nodes, backward, Adam(weight_decay).  value = directed
+    edges per second; N > 1 runs independent replicas (weak scaling, gradients all-reduced)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import gcn_vae_b200 as K
+    from gcn_vae_b200 import _lib as L
+    from gcn_vae_b200 import entity_classify as EC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    clocks = ClockSampler(local)
+    n_hidden, n_bases, l2norm = 10, 40, 5e-4
+    t0 = time.perf_counter()
+    data = EC.synthetic_graph("am", seed=rank, scale=args.scale)
+    log(f"synthetic AM-shaped graph: {time.perf_counter() - t0:.1f}s; nodes={data.num_nodes} edges={len(data.edge_src)}")
+    E, N = len(data.edge_src), data.num_nodes
+    pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory()
+    host = {"src": pin(data.edge_src, torch.int32), "dst": pin(data.edge_dst, torch.int32),
+            "etype": pin(data.edge_type, torch.int32), "norm": pin(data.edge_norm.reshape(-1, 1), torch.float32),
+            "labels": pin(data.labels, torch.int64), "train_idx": pin(data.train_idx, torch.int64)}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    torch.manual_seed(0)
+    model = EC.EntityClassify(N, n_hidden, data.num_classes, data.num_rels, num_bases=n_bases, num_hidden_layers=0,
+                              dropout=0.0, use_self_loop=False, use_cuda=True).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=l2norm, fused=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    feats = model.create_features()
+
+    def step(t):
+        gr = K.Graph()                                      # fresh graph: the index is rebuilt every step
+        gr._n = N
+        gr._dev_edges[dev] = (t["src"], t["dst"])
+        opt.zero_grad(set_to_none=True)
+        logits = model(gr, feats, t["etype"], t["norm"])
+        loss = F.cross_entropy(logits[t["train_idx"]], t["labels"][t["train_idx"]])
+        loss.backward()
+        if world > 1:
+            K.parallel.allreduce_mean_grads(params)
+        opt.step()
+        return loss
+
+    def e2e_step():
+        return float(step({k: v.to(dev, non_blocking=True) for k, v in host.items()}))
+
+    def timed(fn, n_steps):
+        total = 0.0
+        for _ in range(n_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            total += a.elapsed_time(b)
+        return total
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    model.train()
+    clocks.mark()
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sync_all()
+    L.launches = 0
+    L.profile = {}
+    ms_dev = max_over_ranks(timed(lambda: step(resident), args.steps))
+    launches = L.launches
+    prof, L.profile = L.profile, None
+    sync_all()
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    ms_e2e = max_over_ranks(timed(e2e_step, args.steps))
+    sync_all()
+    clock_info = clocks.stop()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    op_ms = {tag: sum(a.elapsed_time(b) for a, b in evs) for tag, evs in prof.items()}
+    op_n = {tag: len(evs) for tag, evs in prof.items()}
+    total_ops = sum(op_ms.values())
+    top = sorted(op_ms.items(), key=lambda kv: -kv[1])
+    for tag, ms in top[:12]:
+        log(f"  {tag:44s} {ms / args.steps:8.3f} ms/step  {100 * ms / total_ops:5.1f}%  x{op_n[tag] // args.steps}")
+    pk = peaks()
+    # algorithmic bytes of the input-layer lookup (SURVEY 8(d), row a4): per edge the n_bases rows
+    # V[b, src, :] (4*h bytes each) + the 16-byte record + the coefficient row; per node the h-wide output
+    ab = {"kg_basis_id_fwd": E * (n_bases * 4 * n_hidden + 16 + 4 * n_bases) + 4 * N * n_hidden,
+          # backward: the same rows read-modify-written as gradient, the upstream gradient row per edge
+          "kg_basis_id_bwd": E * (3 * n_bases * 4 * n_hidden + 16 + 4 * n_hidden + 4 * n_bases)}
+    roof = None
+    for tag, ms in top:
+        if tag in ab:
+            per = ms / op_n[tag]
+            ach = ab[tag] / (per * 1e-3) / 1e9
+            roof = {"kernel": tag, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "ms_per_launch": per,
+                    "algorithmic_bytes": ab[tag], "share_of_step": ms / total_ops,
+                    "regime": "streaming: the basis table V is 2.67 GB, its gradient another 2.67 GB"}
+            break
+    total_edges = E * world * args.steps
+    line = {
+        "metric": METRIC, "value": total_edges / (ms_dev * 1e-3), "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "am-entity", "nodes": N, "relations": data.num_rels, "graph_edges": E,
+                   "classes": data.num_classes, "n_hidden": n_hidden, "n_bases": n_bases, "l2norm": l2norm,
+                   "train_nodes": len(data.train_idx), "scale": args.scale,
+                   "parallelism": f"replicas x{world} (grad all-reduce)",
+                   "timed": "graph index + fwd + cross-entropy + bwd + Adam; per-step CUDA events",
+                   "l2": "inputs (2.67 GB basis table) far larger than L2"},
+        "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import gcn_vae_b200 as K
@@ -634,13 +779,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fb15k237-full",
-                    choices=["fb15k237-full", "fb15k237-step", "wn18-full", "wn18-step", "wikikg2-part"],
-                    help="fb15k237-full is the headline (BASELINE.json configs[1]); wn18-* with --n-flows 3 is configs[2]")
+                    choices=["fb15k237-full", "fb15k237-step", "wn18-full", "wn18-step", "wikikg2-part", "am-entity"],
+                    help="fb15k237-full is the headline (BASELINE.json configs[1]); wn18-* with --n-flows 3 is configs[2]; "
+                         "am-entity is configs[3] (entity classification, basis RGCN); wikikg2-part is configs[4]")
     ap.add_argument("--n-flows", type=int, default=0)
     ap.add_argument("--bases", type=int, default=None,
                     help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
                          "36 directed relation types, which does not divide 500)")
-    ap.add_argument("--scale", type=float, default=1.0, help="wikikg2-part: shrink the graph (tests)")
+    ap.add_argument("--scale", type=float, default=1.0, help="wikikg2-part / am-entity: shrink the graph (tests)")
     ap.add_argument("--allgather", action="store_true",
                     help="wikikg2-part: NCCL all-gather of layer inputs instead of the peer-memory gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -660,6 +806,8 @@ def main():
         run_reference(args)
     elif args.workload == "wikikg2-part":
         run_partitioned(args)
+    elif args.workload == "am-entity":
+        run_entity(args)
     else:
         run_gpu(args)
 

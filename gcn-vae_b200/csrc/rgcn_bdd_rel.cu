@@ -22,6 +22,7 @@
 // dagg row).  Summation order across CTAs is not fixed: results are reproducible to fp32 rounding.
 #include "common.cuh"
 #include "rgcn_bdd_own.cuh"
+#include "rgcn_bdd_tile.cuh"
 
 namespace {
 
@@ -468,6 +469,8 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows
     KG_BDD_DISPATCH(launch_scatter, 4, 4, x, rel_pack, n_edges, w_fwd, num_bases, hints, agg, st);
     KG_BDD_DISPATCH(launch_scatter, 8, 8, x, rel_pack, n_edges, w_fwd, num_bases, hints, agg, st);
   }
+  if (bddtile::eligible(num_bases, si, so) && aligned16(x) && aligned16(w_fwd) && aligned16(agg))
+    return bddtile::launch_fwd(x, rel_pack, n_edges, w_fwd, si, so, num_bases, 0, agg, st);
   const size_t smem = sizeof(float) * ((size_t)si * num_bases * so + (size_t)num_bases * si);
   KG_REQUIRE(smem <= 200 * 1024, "bdd rel fwd: block weights of one relation exceed shared memory");
   KG_CUDA(cudaFuncSetAttribute(bdd_rel_scatter_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,6 +504,14 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
     KG_BDD_DISPATCH(launch_backward, 10, 10, x, dagg, rel_pack, n_edges, w_bwd, num_bases, hints, dx, dweight, st);
     KG_BDD_DISPATCH(launch_backward, 4, 4, x, dagg, rel_pack, n_edges, w_bwd, num_bases, hints, dx, dweight, st);
     KG_BDD_DISPATCH(launch_backward, 8, 8, x, dagg, rel_pack, n_edges, w_bwd, num_bases, hints, dx, dweight, st);
+  }
+  if (bddtile::eligible(num_bases, si, so) && aligned16(x) && aligned16(dagg) && aligned16(w_bwd) &&
+      aligned16(dx) && aligned16(dweight)) {
+    if (dx != nullptr) {
+      const int rc = bddtile::launch_fwd(dagg, rel_pack, n_edges, w_bwd, so, si, num_bases, 1, dx, st);
+      if (rc != KG_OK) return rc;
+    }
+    return bddtile::launch_dw(x, dagg, rel_pack, n_edges, si, so, num_bases, dweight, st);
   }
   const int in_w = num_bases * si, out_w = num_bases * so;
   const size_t smem = sizeof(float) * ((size_t)so * in_w + (size_t)num_bases * si * so + in_w + out_w);

@@ -205,7 +205,11 @@ def test_graph_rel_tiled_order_integer_exact(n, e, r, tile, by_src):
         assert np.array_equal(pack, want)
 
 
-@pytest.mark.parametrize("B,si,so", [(100, 5, 5), (100, 5, 10), (50, 10, 10), (24, 4, 4), (16, 8, 8), (8, 5, 5)])
+@pytest.mark.parametrize("B,si,so", [(100, 5, 5), (100, 5, 10), (50, 10, 10), (24, 4, 4), (16, 8, 8), (8, 5, 5),
+                                     # register-tile kernels (rgcn_bdd_tile.cuh): the WN18-shape blocks, odd
+                                     # widths, K-split threads, 512-thread slots
+                                     (25, 20, 20), (25, 20, 40), (50, 10, 20), (20, 25, 25), (20, 25, 50),
+                                     (10, 50, 50), (10, 50, 100), (4, 20, 40)])
 @pytest.mark.parametrize("tiled", [False, True])
 def test_bdd_layer_fast_shapes_and_tiled_order(B, si, so, tiled, monkeypatch):
     """The register-resident fast path at the real layer widths (1 and 2 slots per CTA, several
