@@ -36,6 +36,9 @@ _SIGNATURES = {
     "kg_graph_rel_tiled": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "kg_basis_id_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "kg_basis_id_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "kg_basis_id_src_eligible": (_I, [_I, _I, _I]),
+    "kg_basis_id_src_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "kg_basis_id_src_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "kg_basis_dense_fwd": (_I, [_P, _P, _I, _P, _I, _I, _P, _P]),
     "kg_basis_dense_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),

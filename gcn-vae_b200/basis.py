@@ -50,6 +50,24 @@ def _tail_bwd(g, out, mask, act_code):
     return gpre
 
 
+_ARANGE_CACHE = {}
+
+
+def _is_arange(ids32):
+    """ids == arange(len(ids))?  (the reference's featureless input, entity_classify.py:63).  One
+    device comparison per distinct feature tensor; the answer is cached on (storage, version)."""
+    key = (ids32.data_ptr(), ids32.numel(), ids32._version, ids32.device)
+    hit = _ARANGE_CACHE.get(key)
+    if hit is None:
+        n = ids32.numel()
+        hit = bool(n > 0 and torch.equal(ids32, torch.arange(n, dtype=ids32.dtype, device=ids32.device)))
+        if len(_ARANGE_CACHE) > 64:
+            _ARANGE_CACHE.clear()
+        _ARANGE_CACHE[key] = (hit, ids32)          # the tensor is kept alive so its address is not reused
+        return hit
+    return hit[0]
+
+
 class BasisIdConvFn(torch.autograd.Function):
     """Integer-id features: out = dropout(act(sum_e norm_e sum_b coef[r_e,b] V[b, id_src, :] + h_bias
     + loop_weight[id]))."""
@@ -67,12 +85,19 @@ class BasisIdConvFn(torch.autograd.Function):
             agg = torch.zeros((n, out_f), dtype=torch.float32, device=dev)
         cf = None if coef is None else _c(coef)
         gi.ensure_node_major()
-        L.call("kg_basis_id_fwd", L.f32(V), L.f32(cf), L.i32(ids32), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), n,
-               n_in, NB, out_f, L.f32(agg), L.stream())
+        # featureless input (ids = arange) with a composed basis: source-tiled kernels, V read once
+        src_tiled = bool(cf is not None and n_in == n and ids32.numel() == n and
+                         L.lib().kg_basis_id_src_eligible(cf.shape[0], NB, out_f) and _is_arange(ids32))
+        if src_tiled:
+            L.call("kg_basis_id_src_fwd", L.f32(V), L.f32(cf), L.i32(gi.col_ptr), L.i32(gi.bwd_pack), n,
+                   cf.shape[0], NB, out_f, L.f32(agg), L.stream())
+        else:
+            L.call("kg_basis_id_fwd", L.f32(V), L.f32(cf), L.i32(ids32), L.i32(gi.row_ptr), L.i32(gi.fwd_pack), n,
+                   n_in, NB, out_f, L.f32(agg), L.stream())
         mask = None if drop_mask is None else _c(drop_mask)
         out = _tail(agg, h_bias, act, mask)
         ctx.save_for_backward(V, cf, ids32, out, mask)
-        ctx.gi, ctx.act = gi, act
+        ctx.gi, ctx.act, ctx.src_tiled = gi, act, src_tiled
         ctx.loop_shape = None if loop_weight is None else loop_weight.shape
         ctx.has_bias = h_bias is not None
         return out
@@ -83,10 +108,15 @@ class BasisIdConvFn(torch.autograd.Function):
         gi = ctx.gi
         NB, n_in, out_f = V.shape
         gpre = _tail_bwd(g, out, mask, ctx.act)
-        dV = torch.zeros_like(V)
         dcoef = None if cf is None else torch.zeros_like(cf)
-        L.call("kg_basis_id_bwd", L.f32(V), L.f32(cf), L.i32(ids32), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges,
-               n_in, NB, out_f, L.f32(dV), L.f32(dcoef), L.stream())
+        if ctx.src_tiled:
+            dV = torch.empty_like(V)                      # every row is written exactly once
+            L.call("kg_basis_id_src_bwd", L.f32(V), L.f32(cf), L.f32(gpre), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
+                   n_in, cf.shape[0], NB, out_f, L.f32(dV), L.f32(dcoef), L.stream())
+        else:
+            dV = torch.zeros_like(V)
+            L.call("kg_basis_id_bwd", L.f32(V), L.f32(cf), L.i32(ids32), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges,
+                   n_in, NB, out_f, L.f32(dV), L.f32(dcoef), L.stream())
         dloop = None
         if ctx.loop_shape is not None:
             dloop = torch.zeros(ctx.loop_shape, dtype=torch.float32, device=V.device)

@@ -100,6 +100,211 @@ basis_id_bwd_kernel(const float* __restrict__ V, const float* __restrict__ coef,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// integer-id features with ids == arange (the reference's `feats = torch.arange(num_nodes)`,
+// kgvae/entity_classify.py:63): SOURCE-TILED kernels over the src-major edge list (col_ptr +
+// records {dst, etype, norm, edge}).  A CTA takes NT consecutive source nodes, so the basis rows it
+// needs - V[b, n0 .. n0+NT, :] for every b - are NB contiguous runs: the 2.67 GB table (AM shape)
+// is read ONCE, coalesced, instead of one 40-byte row per (edge, basis), and its gradient is
+// WRITTEN once with plain stores (each (b, node) row has exactly one owner thread): no atomics on
+// dV, no zero-fill.  The rows reduced into (out[dst], 67 MB at the AM shape) are L2-resident.
+// Nodes with more than kHeavy out-edges are finished by the whole CTA (hubs of real RDF graphs).
+// ------------------------------------------------------------------------------------------
+constexpr int kHeavy = 512;
+
+// forward: thread (n, o) keeps the column V[0..NB, n, o] in registers; per out-edge NB FMAs against
+// the relation's coefficient row (shared memory) and one atomic add into out[dst, o]
+template <int NBR>
+__global__ void __launch_bounds__(512)
+basis_id_src_fwd_kernel(const float* __restrict__ V, const float* __restrict__ coef, const int* __restrict__ col_ptr,
+                        const int4* __restrict__ pack, int n_src, int R, int NB, int out_f, int NT,
+                        float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float* coef_s = sm;                                  // [R][NBR] (zero padded)
+  float* Vh_s = sm + (size_t)R * NBR;                  // [NBR] column of a heavy node, per o: [out_f][NBR]
+  for (int i = threadIdx.x; i < R * NBR; i += blockDim.x) {
+    const int r = i / NBR, b = i - r * NBR;
+    coef_s[i] = b < NB ? __ldg(coef + (size_t)r * NB + b) : 0.f;
+  }
+  __syncthreads();
+  const int per_tile = NT * out_f;
+  for (int n0 = blockIdx.x * NT; n0 < n_src; n0 += gridDim.x * NT) {
+    const int nt = min(NT, n_src - n0);
+    const int t = threadIdx.x;
+    const bool mine = t < nt * out_f;
+    const int n = n0 + (mine ? t / out_f : 0), o = mine ? t % out_f : 0;
+    float v[NBR];
+#pragma unroll
+    for (int b = 0; b < NBR; ++b) v[b] = (mine && b < NB) ? __ldg(V + ((size_t)b * n_src + n) * out_f + o) : 0.f;
+    int e0 = 0, e1 = 0;
+    if (mine) { e0 = __ldg(col_ptr + n); e1 = __ldg(col_ptr + n + 1); }
+    const bool heavy = e1 - e0 > kHeavy;
+    if (!heavy) {
+      for (int e = e0; e < e1; ++e) {
+        const int4 p = __ldg(pack + e);                // {dst, etype, norm, edge}
+        const float4* c4 = reinterpret_cast<const float4*>(coef_s + (size_t)p.y * NBR);
+        float m = 0.f;
+#pragma unroll
+        for (int b = 0; b < NBR; b += 4) {
+          const float4 c = c4[b / 4];
+          m = fmaf(c.x, v[b], m); m = fmaf(c.y, v[b + 1], m); m = fmaf(c.z, v[b + 2], m); m = fmaf(c.w, v[b + 3], m);
+        }
+        atomicAdd(out + (size_t)p.x * out_f + o, __int_as_float(p.z) * m);
+      }
+    }
+    // heavy nodes of this tile: the whole CTA shares the edges of one node at a time
+    if (__syncthreads_or(heavy)) {
+      for (int hn = 0; hn < nt; ++hn) {
+        const int h0 = __ldg(col_ptr + n0 + hn), h1 = __ldg(col_ptr + n0 + hn + 1);
+        if (h1 - h0 <= kHeavy) continue;               // uniform across the CTA
+        __syncthreads();
+        if (mine && t / out_f == hn)
+#pragma unroll
+          for (int b = 0; b < NBR; ++b) Vh_s[o * NBR + b] = v[b];
+        __syncthreads();
+        const int groups = blockDim.x / out_f, grp = t / out_f, oo = t % out_f;
+        if (grp < groups) {
+          const float4* v4 = reinterpret_cast<const float4*>(Vh_s + oo * NBR);
+          for (int e = h0 + grp; e < h1; e += groups) {
+            const int4 p = __ldg(pack + e);
+            const float4* c4 = reinterpret_cast<const float4*>(coef_s + (size_t)p.y * NBR);
+            float m = 0.f;
+#pragma unroll
+            for (int b = 0; b < NBR; b += 4) {
+              const float4 c = c4[b / 4], w = v4[b / 4];
+              m = fmaf(c.x, w.x, m); m = fmaf(c.y, w.y, m); m = fmaf(c.z, w.z, m); m = fmaf(c.w, w.w, m);
+            }
+            atomicAdd(out + (size_t)p.x * out_f + oo, __int_as_float(p.z) * m);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    (void)per_tile;
+  }
+}
+
+// backward: thread (n, b) keeps V[b, n, :] and the gradient row dV[b, n, :] in registers
+//   dV[b, n, :]  = sum_{e: src = n} coef[r_e, b] * norm_e * g[dst_e, :]          (plain store, once)
+//   dcoef[r, b] += sum_e norm_e * <V[b, n, :], g[dst_e, :]>   (shared-memory table, flushed per CTA)
+// V / dV tiles go through shared memory ([b][nt*out_f] runs, odd pitch) so that global traffic is
+// whole contiguous runs while the lanes of a warp walk b.
+template <int OF>
+__global__ void __launch_bounds__(1024)
+basis_id_src_bwd_kernel(const float* __restrict__ V, const float* __restrict__ coef, const float* __restrict__ g,
+                        const int* __restrict__ col_ptr, const int4* __restrict__ pack, int n_src, int R, int NB,
+                        int out_f, int NT, float* __restrict__ dV, float* __restrict__ dcoef) {
+  extern __shared__ __align__(16) float sm[];
+  const int pitch = (NT * out_f) | 1;                  // odd: lanes over b hit distinct banks
+  float* coef_s = sm;                                  // [R][NB]
+  float* dc_s = coef_s + (size_t)R * NB;               // [R][NB]
+  float* T_s = dc_s + (size_t)R * NB;                  // [NB][pitch]  V tile, then dV tile
+  for (int i = threadIdx.x; i < R * NB; i += blockDim.x) {
+    coef_s[i] = __ldg(coef + i);
+    dc_s[i] = 0.f;
+  }
+  const int t = threadIdx.x;
+  const int nl = t / NB, b = t - nl * NB;              // thread (node slot, basis)
+  for (int n0 = blockIdx.x * NT; n0 < n_src; n0 += gridDim.x * NT) {
+    const int nt = min(NT, n_src - n0), run = nt * out_f;
+    __syncthreads();                                   // previous tile written out; tables ready
+    for (int i = t; i < NB * run; i += blockDim.x) {
+      const int bb = i / run, j = i - bb * run;
+      T_s[bb * pitch + j] = __ldg(V + ((size_t)bb * n_src + n0) * out_f + j);
+    }
+    __syncthreads();
+    const bool mine = nl < nt;
+    float v[OF], acc[OF];
+#pragma unroll
+    for (int o = 0; o < OF; ++o) {
+      v[o] = (mine && o < out_f) ? T_s[b * pitch + nl * out_f + o] : 0.f;
+      acc[o] = 0.f;
+    }
+    int e0 = 0, e1 = 0;
+    if (mine) { e0 = __ldg(col_ptr + n0 + nl); e1 = __ldg(col_ptr + n0 + nl + 1); }
+    const bool heavy = e1 - e0 > kHeavy;
+    auto edge = [&](int e) {
+      const int4 p = __ldg(pack + e);                  // {dst, etype, norm, edge}: one address per node
+      const float nv = __int_as_float(p.z);
+      const float* gr = g + (size_t)p.x * out_f;
+      const float c = nv * coef_s[p.y * NB + b];
+      float d = 0.f;
+#pragma unroll
+      for (int o = 0; o < OF; ++o) {
+        if (o < out_f) {
+          const float gv = __ldg(gr + o);
+          d = fmaf(v[o], gv, d);
+          acc[o] = fmaf(c, gv, acc[o]);
+        }
+      }
+      atomicAdd(dc_s + p.y * NB + b, nv * d);
+    };
+    if (!heavy)
+      for (int e = e0; e < e1; ++e) edge(e);
+    const bool any_heavy = __syncthreads_or(heavy);    // also: every thread holds its V row
+    if (!any_heavy) {
+      if (mine)
+#pragma unroll
+        for (int o = 0; o < OF; ++o)
+          if (o < out_f) T_s[b * pitch + nl * out_f + o] = acc[o];
+    } else {
+      // tile with hub nodes: gradient rows are accumulated in shared memory instead
+      if (mine)
+#pragma unroll
+        for (int o = 0; o < OF; ++o)
+          if (o < out_f) T_s[b * pitch + nl * out_f + o] = heavy ? 0.f : acc[o];
+      const int slots = blockDim.x / NB;
+      for (int hn = 0; hn < nt; ++hn) {
+        const int h0 = __ldg(col_ptr + n0 + hn), h1 = __ldg(col_ptr + n0 + hn + 1);
+        if (h1 - h0 <= kHeavy) continue;               // uniform across the CTA
+        __syncthreads();
+        if (nl < slots) {
+          // every slot takes the hub's V row for its basis and a strided share of its edges
+          const float* vsrc = V + ((size_t)b * n_src + n0 + hn) * out_f;
+#pragma unroll
+          for (int o = 0; o < OF; ++o) {
+            v[o] = o < out_f ? __ldg(vsrc + o) : 0.f;
+            acc[o] = 0.f;
+          }
+          for (int e = h0 + nl; e < h1; e += slots) edge(e);
+#pragma unroll
+          for (int o = 0; o < OF; ++o)
+            if (o < out_f) atomicAdd(T_s + b * pitch + hn * out_f + o, acc[o]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = t; i < NB * run; i += blockDim.x) {
+      const int bb = i / run, j = i - bb * run;
+      dV[((size_t)bb * n_src + n0) * out_f + j] = T_s[bb * pitch + j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * NB; i += blockDim.x)
+    if (dc_s[i] != 0.f) atomicAdd(dcoef + i, dc_s[i]);
+}
+
+// node-tile size and CTA size of the source-tiled id kernels; 0 when the shape does not fit
+struct SrcPlan {
+  int nt, threads;
+  size_t smem_fwd, smem_bwd;
+  int nbr;
+};
+SrcPlan src_plan(int R, int NB, int out_f) {
+  SrcPlan p{0, 0, 0, 0, 0};
+  if (NB > 64 || out_f > 16 || NB < 2) return p;
+  p.nbr = NB <= 16 ? 16 : NB <= 32 ? 32 : NB <= 48 ? 48 : 64;
+  p.nt = 640 / NB;                                     // backward: NT * NB threads
+  if (p.nt > 32) p.nt = 32;
+  if (p.nt < 1) return SrcPlan{0, 0, 0, 0, 0};
+  p.threads = (p.nt * NB + 31) / 32 * 32;
+  p.smem_fwd = sizeof(float) * ((size_t)R * p.nbr + (size_t)out_f * p.nbr);
+  p.smem_bwd = sizeof(float) * ((size_t)2 * R * NB + (size_t)NB * ((p.nt * out_f) | 1));
+  if (p.smem_fwd > 100 * 1024 || p.smem_bwd > 100 * 1024) return SrcPlan{0, 0, 0, 0, 0};
+  return p;
+}
+
 // ------------------------------------------------------------------------------------------
 // dense features over relation-sorted edges; CTA = edge chunk x column tile [c0, c0 + cw) of W_r
 //   forward : out[dst, c] += norm * sum_i x[src, i] W_r[i, c]
@@ -213,6 +418,67 @@ extern "C" int kg_basis_id_bwd(const float* V, const float* coef, const int32_t*
   const int warps = kg_div_up(n_edges, 32);
   basis_id_bwd_kernel<<<kg_div_up((long long)warps * 32, kThreads), kThreads, 0, kg_stream(stream)>>>(
       V, coef, ids, g, reinterpret_cast<const int4*>(rel_pack), n_edges, n_in, num_bases, out_feat, dV, dcoef);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+
+// 1 when kg_basis_id_src_fwd / kg_basis_id_src_bwd cover this shape (identity ids, composed basis)
+extern "C" int kg_basis_id_src_eligible(int num_rels, int num_bases, int out_feat) {
+  return src_plan(num_rels, num_bases, out_feat).nt > 0 ? 1 : 0;
+}
+
+// Source-tiled forward for ids == arange(n_src) and coef != NULL: out (holding the self-loop term or
+// zeros) += messages; col_ptr / bwd_pack: the src-major list of kg_graph_index.
+extern "C" int kg_basis_id_src_fwd(const float* V, const float* coef, const int32_t* col_ptr, const void* bwd_pack,
+                                   int n_src, int num_rels, int num_bases, int out_feat, float* out, void* stream) {
+  KG_REQUIRE(V && coef && col_ptr && bwd_pack && out, "basis id src fwd: null argument");
+  const SrcPlan pl = src_plan(num_rels, num_bases, out_feat);
+  KG_REQUIRE(pl.nt > 0, "basis id src fwd: shape not covered (num_bases <= 64, out_feat <= 16)");
+  if (n_src == 0) return KG_OK;
+  // forward tile: as many nodes as give <= 512 (node, column) threads
+  int nt = 512 / out_feat;
+  if (nt > 48) nt = 48;
+  const int threads = (nt * out_feat + 31) / 32 * 32;
+  const int tiles = kg_div_up(n_src, nt);
+  const int grid = tiles < 8 * kg_sm_count() ? tiles : 8 * kg_sm_count();
+  cudaStream_t st = kg_stream(stream);
+  const int4* pack = reinterpret_cast<const int4*>(bwd_pack);
+#define KG_SRC_FWD(NBR_)                                                                                          \
+  if (pl.nbr == NBR_) {                                                                                           \
+    KG_CUDA(cudaFuncSetAttribute(basis_id_src_fwd_kernel<NBR_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)pl.smem_fwd));                                                              \
+    basis_id_src_fwd_kernel<NBR_><<<grid, threads, pl.smem_fwd, st>>>(V, coef, col_ptr, pack, n_src, num_rels,    \
+                                                                      num_bases, out_feat, nt, out);              \
+  }
+  KG_SRC_FWD(16) KG_SRC_FWD(32) KG_SRC_FWD(48) KG_SRC_FWD(64)
+#undef KG_SRC_FWD
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+// Source-tiled backward: dV [NB, n_src, out] is WRITTEN (every row, no zero-fill needed); dcoef
+// [R, NB] is accumulated into (zero-filled by the caller).
+extern "C" int kg_basis_id_src_bwd(const float* V, const float* coef, const float* g, const int32_t* col_ptr,
+                                   const void* bwd_pack, int n_src, int num_rels, int num_bases, int out_feat,
+                                   float* dV, float* dcoef, void* stream) {
+  KG_REQUIRE(V && coef && g && col_ptr && bwd_pack && dV && dcoef, "basis id src bwd: null argument");
+  const SrcPlan pl = src_plan(num_rels, num_bases, out_feat);
+  KG_REQUIRE(pl.nt > 0, "basis id src bwd: shape not covered (num_bases <= 64, out_feat <= 16)");
+  if (n_src == 0) return KG_OK;
+  const int tiles = kg_div_up(n_src, pl.nt);
+  const int grid = tiles < 2 * kg_sm_count() ? tiles : 2 * kg_sm_count();
+  cudaStream_t st = kg_stream(stream);
+  const int4* pack = reinterpret_cast<const int4*>(bwd_pack);
+  if (out_feat <= 12) {
+    KG_CUDA(cudaFuncSetAttribute(basis_id_src_bwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd));
+    basis_id_src_bwd_kernel<12><<<grid, pl.threads, pl.smem_bwd, st>>>(V, coef, g, col_ptr, pack, n_src, num_rels,
+                                                                       num_bases, out_feat, pl.nt, dV, dcoef);
+  } else {
+    KG_CUDA(cudaFuncSetAttribute(basis_id_src_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd));
+    basis_id_src_bwd_kernel<16><<<grid, pl.threads, pl.smem_bwd, st>>>(V, coef, g, col_ptr, pack, n_src, num_rels,
+                                                                       num_bases, out_feat, pl.nt, dV, dcoef);
+  }
   KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -153,6 +153,17 @@ int kg_basis_id_fwd(const float* V, const float* coef, const int32_t* ids, const
 int kg_basis_id_bwd(const float* V, const float* coef, const int32_t* ids, const float* g,
                     const void* rel_pack, int n_edges, int n_in, int num_bases, int out_feat,
                     float* dV, float* dcoef, void* stream);
+/* Source-tiled variants for the reference's featureless input layer (ids == arange(num_nodes),
+ * kgvae/entity_classify.py:63) with a composed basis (coef != NULL): a CTA takes consecutive source
+ * nodes, so V is read once in contiguous runs and dV is WRITTEN once without atomics or zero-fill;
+ * col_ptr / bwd_pack are the src-major list of kg_graph_index ({dst, etype, bits(norm), edge}).
+ * kg_basis_id_src_eligible: 1 when the shape is covered (num_bases <= 64, out_feat <= 16). */
+int kg_basis_id_src_eligible(int num_rels, int num_bases, int out_feat);
+int kg_basis_id_src_fwd(const float* V, const float* coef, const int32_t* col_ptr, const void* bwd_pack,
+                        int n_src, int num_rels, int num_bases, int out_feat, float* out, void* stream);
+int kg_basis_id_src_bwd(const float* V, const float* coef, const float* g, const int32_t* col_ptr,
+                        const void* bwd_pack, int n_src, int num_rels, int num_bases, int out_feat,
+                        float* dV, float* dcoef, void* stream);
 int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int in_feat,
                        int out_feat, float* out, void* stream);
 int kg_basis_dense_bwd(const float* x, const float* g, const void* rel_pack, int n_edges, const float* W,

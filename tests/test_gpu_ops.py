@@ -243,10 +243,19 @@ def test_bdd_layer_fast_shapes_and_tiled_order(B, si, so, tiled, monkeypatch):
 
 @pytest.mark.parametrize("kind,n,e,r,nb,fin,fout,loop", [("dense", 80, 700, 6, 3, 10, 11, True), ("dense", 80, 700, 5, 5, 16, 8, False),
                                                       ("dense", 50, 400, 9, 4, 300, 70, True), ("ids", 90, 900, 7, 3, 90, 10, True),
-                                                      ("ids", 90, 900, 6, 6, 90, 12, False), ("ids", 40, 0, 3, 2, 40, 5, True)])
+                                                      ("ids", 90, 900, 6, 6, 90, 12, False), ("ids", 40, 0, 3, 2, 40, 5, True),
+                                                      # ids = arange: the source-tiled kernels (rgcn_basis.cu), incl.
+                                                      # ragged last tile, 16 columns, hub nodes (> 512 out-edges)
+                                                      ("arange", 90, 900, 7, 3, 90, 10, True),
+                                                      ("arange", 333, 6000, 50, 40, 333, 10, False),
+                                                      ("arange", 130, 2000, 70, 33, 130, 16, True),
+                                                      ("arange_hub", 70, 4000, 9, 4, 70, 10, True),
+                                                      ("arange", 40, 0, 3, 2, 40, 5, True)])
 def test_basis_layer_fwd_bwd(kind, n, e, r, nb, fin, fout, loop):
     """RelGraphConv("basis") on dense and on integer-id features (kgvae/entity_classify.py:30-43)."""
     src, dst, et, norm = _rand_graph(5, n, e, r)
+    if kind == "arange_hub":                    # two hubs own most edges; node 5 keeps a light share
+        src = np.where(np.arange(e) % 3 == 0, 69, np.where(np.arange(e) % 3 == 1, 3, src)).astype(src.dtype)
     g = torch.Generator().manual_seed(n + e + nb)
     V = (torch.randn(nb, fin, fout, generator=g) * 0.3).requires_grad_(True)
     wc = torch.randn(r, nb, generator=g).requires_grad_(True) if nb < r else None
@@ -254,7 +263,8 @@ def test_basis_layer_fwd_bwd(kind, n, e, r, nb, fin, fout, loop):
     bias = torch.randn(fout, generator=g).requires_grad_(True)
     mask = (torch.rand(n, fout, generator=g) < 0.8).float() / 0.8
     gout = torch.randn(n, fout, generator=g)
-    x = torch.randperm(n, generator=g) if kind == "ids" else torch.randn(n, fin, generator=g).requires_grad_(True)
+    x = (torch.randperm(n, generator=g) if kind == "ids" else torch.arange(n) if kind.startswith("arange")
+         else torch.randn(n, fin, generator=g).requires_grad_(True))
     graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
     want = O.rgcn_basis_layer(x, graph, V, wc, bias, lw, torch.relu, mask)
     want.backward(gout)
@@ -271,7 +281,7 @@ def test_basis_layer_fwd_bwd(kind, n, e, r, nb, fin, fout, loop):
     gr = K.Graph()
     gr.add_nodes(n)
     gr.add_edges(src, dst)
-    xc = x.to(DEV) if kind == "ids" else x.detach().to(DEV).requires_grad_(True)
+    xc = x.to(DEV) if kind != "dense" else x.detach().to(DEV).requires_grad_(True)
     out = layer(gr, xc, torch.from_numpy(et).to(DEV), torch.from_numpy(norm.reshape(-1, 1)).to(DEV))
     out.backward(gout.to(DEV))
     assert_close(out, want, RTOL, "basis out")
