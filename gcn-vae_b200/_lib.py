@@ -39,8 +39,8 @@ _SIGNATURES = {
     "kg_basis_id_src_eligible": (_I, [_I, _I, _I]),
     "kg_basis_id_src_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "kg_basis_id_src_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
-    "kg_basis_dense_fwd": (_I, [_P, _P, _I, _P, _I, _I, _P, _P]),
-    "kg_basis_dense_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "kg_basis_dense_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
+    "kg_basis_dense_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),
     "kg_colsum_workspace_bytes": (_Z, [_I, _I]),
     "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),

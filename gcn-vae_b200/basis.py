@@ -134,7 +134,7 @@ class BasisDenseConvFn(torch.autograd.Function):
         R, in_f, out_f = W.shape
         n = x.shape[0]
         agg = torch.zeros((n, out_f), dtype=torch.float32, device=x.device)
-        L.call("kg_basis_dense_fwd", L.f32(x), L.i32(gi.rel_pack), gi.n_edges, L.f32(W), in_f, out_f, L.f32(agg),
+        L.call("kg_basis_dense_fwd", L.f32(x), L.i32(gi.rel_pack), gi.n_edges, L.f32(W), R, in_f, out_f, L.f32(agg),
                L.stream())
         mask = None if drop_mask is None else _c(drop_mask)
         out = torch.empty_like(agg)
@@ -156,7 +156,7 @@ class BasisDenseConvFn(torch.autograd.Function):
         gpre = _tail_bwd(g, out, mask, ctx.act)
         dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
         dW = torch.zeros_like(W)
-        L.call("kg_basis_dense_bwd", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges, L.f32(W), in_f, out_f,
+        L.call("kg_basis_dense_bwd", L.f32(x), L.f32(gpre), L.i32(gi.rel_pack), gi.n_edges, L.f32(W), R, in_f, out_f,
                L.f32(dx), L.f32(dW), L.stream())
         dloop = None
         if loop_weight is not None:

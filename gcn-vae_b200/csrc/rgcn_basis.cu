@@ -384,6 +384,146 @@ basis_dense_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
       atomicAdd(dW + ((size_t)cur * in_f + t / cn) * out_f + c0 + t % cn, A_s[(t / cn) * cw + t % cn]);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// dense features, SMALL layers (in_feat, out_feat <= 16: the entity-classification hidden / output
+// layers, e.g. 10 -> 11 at the AM shape): every W_r ([R, in, out], 58 KB at AM) sits in shared
+// memory, ONE THREAD PER EDGE does the whole in x out product from registers - no per-edge CTA
+// barrier, lanes of a warp read the same W_r (relation-sorted records: a broadcast).
+//   forward  out[dst, o] += sum_i (norm x[src, i]) W_r[i, o]                (W transposed + padded)
+//   backward dx[src, i]  += norm sum_o W_r[i, o] g[dst, o]
+//            dW_r[i, o]  += sum_e norm x[src, i] g[dst, o]: warp-reduced over the 32 edges of a
+//            batch, accumulated per warp in shared memory, flushed when the relation changes
+// ------------------------------------------------------------------------------------------
+constexpr int kSmall = 16;          // register rows: in_feat, out_feat <= 16
+constexpr int kSmallRange = 2048;   // consecutive edges per warp visit (backward)
+
+__device__ __forceinline__ void load_row16(float (&v)[kSmall], const float* __restrict__ row, int n, float s) {
+#pragma unroll
+  for (int i = 0; i < kSmall; ++i) v[i] = i < n ? s * __ldg(row + i) : 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+basis_small_fwd_kernel(const float* __restrict__ x, const int4* __restrict__ pack, int E, const float* __restrict__ W,
+                       int R, int in_f, int out_f, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];          // Wt_s[R][out_f][ips]
+  const int ips = (in_f + 3) & ~3;
+  for (int idx = threadIdx.x; idx < R * out_f * ips; idx += blockDim.x) {
+    const int i = idx % ips, ro = idx / ips, o = ro % out_f, r = ro / out_f;
+    sm[idx] = i < in_f ? __ldg(W + ((size_t)r * in_f + i) * out_f + o) : 0.f;
+  }
+  __syncthreads();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const int4 p = __ldg(pack + e);                    // {src, dst, etype, norm}
+    float xv[kSmall];
+    load_row16(xv, x + (size_t)p.x * in_f, in_f, __int_as_float(p.w));
+    const float* wr = sm + (size_t)p.z * out_f * ips;
+    float* orow = out + (size_t)p.y * out_f;
+    for (int o = 0; o < out_f; ++o) {
+      const float4* w4 = reinterpret_cast<const float4*>(wr + o * ips);
+      float m = 0.f;
+#pragma unroll
+      for (int q = 0; q < kSmall / 4; ++q)
+        if (4 * q < ips) {
+          const float4 w = w4[q];
+          m = fmaf(xv[4 * q], w.x, m); m = fmaf(xv[4 * q + 1], w.y, m);
+          m = fmaf(xv[4 * q + 2], w.z, m); m = fmaf(xv[4 * q + 3], w.w, m);
+        }
+      atomicAdd(orow + o, m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+basis_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const int4* __restrict__ pack, int E,
+                       const float* __restrict__ W, int R, int in_f, int out_f, float* __restrict__ dx,
+                       float* __restrict__ dW) {
+  extern __shared__ __align__(16) float sm[];          // W_s[R][in_f][ops], then dW_w[warps][in_f * out_f]
+  const int ops = (out_f + 3) & ~3, io = in_f * out_f;
+  float* acc_all = sm + (size_t)R * in_f * ops;
+  for (int idx = threadIdx.x; idx < R * in_f * ops; idx += blockDim.x) {
+    const int o = idx % ops, ri = idx / ops;
+    sm[idx] = o < out_f ? __ldg(W + (size_t)ri * out_f + o) : 0.f;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  float* acc = acc_all + warp * io;
+  for (int idx = lane; idx < io; idx += 32) acc[idx] = 0.f;
+  __syncthreads();
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      __syncwarp();
+      for (int idx = lane; idx < io; idx += 32) {
+        const float v = acc[idx];
+        if (v != 0.f) atomicAdd(dW + (size_t)cur * io + idx, v);
+        acc[idx] = 0.f;
+      }
+      __syncwarp();
+    }
+  };
+  const long long n_ranges = ((long long)E + kSmallRange - 1) / kSmallRange;
+  for (long long rg = (long long)blockIdx.x * warps + warp; rg < n_ranges; rg += (long long)gridDim.x * warps) {
+    const long long r0 = rg * kSmallRange, r1 = r0 + kSmallRange < E ? r0 + kSmallRange : E;
+    for (long long b0 = r0; b0 < r1; b0 += 32) {
+      const long long e = b0 + lane;
+      const bool valid = e < r1;
+      const int4 p = valid ? __ldg(pack + e) : make_int4(0, 0, -1, 0);
+      const float nv = __int_as_float(p.w);
+      float xv[kSmall], gv[kSmall];
+      load_row16(xv, x + (size_t)p.x * in_f, valid ? in_f : 0, nv);
+      load_row16(gv, g + (size_t)p.y * out_f, valid ? out_f : 0, 1.f);
+      if (dx != nullptr && valid) {
+        const float* wr = sm + (size_t)p.z * in_f * ops;
+        float* drow = dx + (size_t)p.x * in_f;
+        for (int i = 0; i < in_f; ++i) {
+          const float4* w4 = reinterpret_cast<const float4*>(wr + i * ops);
+          float m = 0.f;
+#pragma unroll
+          for (int q = 0; q < kSmall / 4; ++q)
+            if (4 * q < ops) {
+              const float4 w = w4[q];
+              m = fmaf(gv[4 * q], w.x, m); m = fmaf(gv[4 * q + 1], w.y, m);
+              m = fmaf(gv[4 * q + 2], w.z, m); m = fmaf(gv[4 * q + 3], w.w, m);
+            }
+          atomicAdd(drow + i, nv * m);
+        }
+      }
+      // weight gradient: one pass per distinct relation in the batch (sorted records: usually one)
+      unsigned pending = __ballot_sync(0xffffffffu, valid);
+      while (pending) {
+        const int r = __shfl_sync(0xffffffffu, p.z, __ffs(pending) - 1);
+        if (r != cur) {
+          flush();
+          cur = r;
+        }
+        const bool mine = valid && p.z == r;
+#pragma unroll
+        for (int i = 0; i < kSmall; ++i)
+          if (i < in_f) {
+            const float xi = mine ? xv[i] : 0.f;
+#pragma unroll
+            for (int o = 0; o < kSmall; ++o)
+              if (o < out_f) {
+                const float t = kg_warp_sum(xi * gv[o]);
+                if (lane == 0) acc[i * out_f + o] += t;
+              }
+          }
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+  }
+  flush();
+}
+
+// shared memory of the small-layer kernels; 0 when the layer does not qualify
+size_t small_smem(int R, int in_f, int out_f, bool backward) {
+  if (in_f > kSmall || out_f > kSmall) return 0;
+  const int ips = (in_f + 3) & ~3, ops = (out_f + 3) & ~3;
+  const size_t bytes = backward ? sizeof(float) * ((size_t)R * in_f * ops + (size_t)(kThreads / 32) * in_f * out_f)
+                                : sizeof(float) * (size_t)R * out_f * ips;
+  return bytes <= 160 * 1024 ? bytes : 0;
+}
+
 int col_tile(int in_f, int out_f, int arrays) {
   // widest column tile whose `arrays` [in_f][cw] shared arrays stay under 96 KB
   long long cw = (96LL * 1024 / 4) / ((long long)arrays * in_f);
@@ -484,10 +624,18 @@ extern "C" int kg_basis_id_src_bwd(const float* V, const float* coef, const floa
 }
 
 // W [R, in, out] composed by the caller; out zero-filled (or holding the self-loop term)
-extern "C" int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int in_feat,
-                                  int out_feat, float* out, void* stream) {
-  KG_REQUIRE(n_edges >= 0 && in_feat > 0 && out_feat > 0, "basis dense fwd: bad sizes");
+extern "C" int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int num_rels,
+                                  int in_feat, int out_feat, float* out, void* stream) {
+  KG_REQUIRE(n_edges >= 0 && in_feat > 0 && out_feat > 0 && num_rels > 0, "basis dense fwd: bad sizes");
   if (n_edges == 0) return KG_OK;
+  if (const size_t smem = small_smem(num_rels, in_feat, out_feat, false)) {
+    KG_CUDA(cudaFuncSetAttribute(basis_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int want = kg_div_up(n_edges, kThreads), cap = 4 * kg_sm_count();
+    basis_small_fwd_kernel<<<want < cap ? want : cap, kThreads, smem, kg_stream(stream)>>>(
+        x, reinterpret_cast<const int4*>(rel_pack), n_edges, W, num_rels, in_feat, out_feat, out);
+    KG_LAUNCH_OK();
+    return KG_OK;
+  }
   const int cw = col_tile(in_feat, out_feat, 1);
   KG_REQUIRE(cw > 0, "basis dense fwd: in_feat too large for one shared-memory column");
   const size_t smem = sizeof(float) * ((size_t)in_feat * cw + in_feat);
@@ -501,9 +649,18 @@ extern "C" int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_ed
 
 // dx [n_src, in] (may be NULL) and dW [R, in, out] zero-filled by the caller
 extern "C" int kg_basis_dense_bwd(const float* x, const float* g, const void* rel_pack, int n_edges,
-                                  const float* W, int in_feat, int out_feat, float* dx, float* dW, void* stream) {
-  KG_REQUIRE(n_edges >= 0 && in_feat > 0 && out_feat > 0, "basis dense bwd: bad sizes");
+                                  const float* W, int num_rels, int in_feat, int out_feat, float* dx, float* dW,
+                                  void* stream) {
+  KG_REQUIRE(n_edges >= 0 && in_feat > 0 && out_feat > 0 && num_rels > 0, "basis dense bwd: bad sizes");
   if (n_edges == 0) return KG_OK;
+  if (const size_t smem = small_smem(num_rels, in_feat, out_feat, true)) {
+    KG_CUDA(cudaFuncSetAttribute(basis_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int want = kg_div_up(kg_div_up(n_edges, kSmallRange), kThreads / 32), cap = 2 * kg_sm_count();
+    basis_small_bwd_kernel<<<want < cap ? want : cap, kThreads, smem, kg_stream(stream)>>>(
+        x, g, reinterpret_cast<const int4*>(rel_pack), n_edges, W, num_rels, in_feat, out_feat, dx, dW);
+    KG_LAUNCH_OK();
+    return KG_OK;
+  }
   const int cw = col_tile(in_feat, out_feat, 2);
   KG_REQUIRE(cw > 0, "basis dense bwd: in_feat too large for one shared-memory column");
   const size_t smem = sizeof(float) * ((size_t)2 * in_feat * cw + in_feat + cw);

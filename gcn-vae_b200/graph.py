@@ -95,8 +95,9 @@ class Graph:
                                        pin(self._dst).to(device, non_blocking=True))
         return self._dev_edges[device]
 
-    def index_for(self, etypes, norm, num_etypes):
-        """ops.GraphIndex for this edge list with the given per-edge types and norms."""
+    def index_for(self, etypes, norm, num_etypes, node_major=False):
+        """ops.GraphIndex for this edge list with the given per-edge types and norms
+        (``node_major``: also build the dst-major / src-major lists in the same pass)."""
         key = (etypes.data_ptr(), etypes._version, etypes.device,
                None if norm is None else (norm.data_ptr(), norm._version), int(num_etypes))
         if self._index is not None and self._index[0] == key:
@@ -107,7 +108,7 @@ class Graph:
         src, dst = self.device_edges(dev)
         if etypes.numel() != src.numel():
             raise RuntimeError(f"etypes has {etypes.numel()} entries for {src.numel()} edges")
-        gi = ops.graph_index(src, dst, ops.as_i32(etypes), norm, self._n, int(num_etypes))
+        gi = ops.graph_index(src, dst, ops.as_i32(etypes), norm, self._n, int(num_etypes), node_major=node_major)
         # the keyed tensors are kept alive so their data_ptr cannot be recycled under the cache
         self._index = (key, gi, etypes, norm)
         return gi

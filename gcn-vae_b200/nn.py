@@ -73,7 +73,9 @@ class RelGraphConv(nn.Module):
         act_code, post = _classify_activation(self.activation)
         part = getattr(g, "partition", None)
         mask = self._keep_mask(x.shape[0], x.device)
-        gi = g.index_for(etypes, norm, self.num_rels)
+        # integer-id features walk node-major lists as well: have them built with the first index
+        id_feats = x.dim() == 1 and x.dtype in (torch.int64, torch.int32)
+        gi = g.index_for(etypes, norm, self.num_rels, node_major=id_feats)
         h_bias = self.h_bias if self.bias else None
         loop_w = self.loop_weight if self.self_loop else None
         if self.regularizer == "bdd":

@@ -164,10 +164,10 @@ int kg_basis_id_src_fwd(const float* V, const float* coef, const int32_t* col_pt
 int kg_basis_id_src_bwd(const float* V, const float* coef, const float* g, const int32_t* col_ptr,
                         const void* bwd_pack, int n_src, int num_rels, int num_bases, int out_feat,
                         float* dV, float* dcoef, void* stream);
-int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int in_feat,
-                       int out_feat, float* out, void* stream);
+int kg_basis_dense_fwd(const float* x, const void* rel_pack, int n_edges, const float* W, int num_rels,
+                       int in_feat, int out_feat, float* out, void* stream);
 int kg_basis_dense_bwd(const float* x, const float* g, const void* rel_pack, int n_edges, const float* W,
-                       int in_feat, int out_feat, float* dx, float* dW, void* stream);
+                       int num_rels, int in_feat, int out_feat, float* dx, float* dW, void* stream);
 
 /* out = dropout(act(agg + bias + loop)) tail of RelGraphConv.forward; backward of the same.
  * act: 0 identity, 1 relu.  drop_mask: [n, dim] keep-mask already scaled by 1/(1-p), or NULL. */
