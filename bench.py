@@ -517,9 +517,10 @@ def run_entity(args):
     pk = peaks()
     # algorithmic bytes of the input-layer lookup: per edge the n_bases rows
     # V[b, src, :] (4*h bytes each) + the 16-byte record + the coefficient row; per node the h-wide output
-    ab = {"kg_basis_id_fwd": E * (n_bases * 4 * n_hidden + 16 + 4 * n_bases) + 4 * N * n_hidden,
-          # backward: the same rows read-modify-written as gradient, the upstream gradient row per edge
-          "kg_basis_id_bwd": E * (3 * n_bases * 4 * n_hidden + 16 + 4 * n_hidden + 4 * n_bases)}
+    table = 4 * n_bases * N * n_hidden                # the basis table V [n_bases, N, h]: 2.67 GB
+    ab = {"kg_basis_id_src_fwd": table + E * (16 + 4 * n_hidden) + 4 * N * n_hidden,   # V once, record + out row per edge
+          # backward: V read once, dV written once, record + upstream gradient row per edge
+          "kg_basis_id_src_bwd": 2 * table + E * (16 + 4 * n_hidden)}
     roof = None
     for tag, ms in top:
         if tag in ab:
@@ -607,7 +608,27 @@ def run_gpu(args):
 
     def e2e_step():
         t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return float(step(t))                               # D2H read of the loss
+        return float(step(t).detach())                      # D2H read of the loss
+
+    prefetch = K.utils.DevicePrefetcher(dev)
+
+    def timed_e2e(n_steps):
+        """K steps through the public API with HOST inputs: every step's 52 MB of pinned inputs are copied
+        inside the timed region (step i+1's copy is submitted before step i runs, so it overlaps the
+        kernels; step 0's does not overlap anything), the loss is read back every step, and the L2 flush
+        is inside the region too.  One event pair around the whole loop."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        prefetch.submit(host)
+        for i in range(n_steps):
+            t = prefetch.take()
+            if i + 1 < n_steps:
+                prefetch.submit(host)
+            flush_buf.fill_(1)
+            float(step(t).detach())                         # D2H read of the loss
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b)
 
     def timed(fn, n_steps):
         total = 0.0
@@ -647,8 +668,9 @@ def run_gpu(args):
     sync_all()
     for _ in range(2):
         e2e_step()
+    timed_e2e(2)
     sync_all()
-    ms_e2e = max_over_ranks(timed(e2e_step, args.steps))
+    ms_e2e = max_over_ranks(timed_e2e(args.steps))
     sync_all()
 
     # ---- evaluation: encoder on the test graph + all-entity ranks -----------------------------
@@ -759,7 +781,9 @@ def run_gpu(args):
                    "timed": "graph index + fwd + loss + bwd + clip + Adam; per-step CUDA events",
                    "l2": "flushed between steps (256 MiB write)"},
         "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "how": "pinned host inputs copied every step inside the timed region (double-buffered on a side "
+                       "stream: step i+1's copy overlaps step i), loss read back every step, L2 flush inside"},
         "eval": {"value": T * args.steps / (ms_eval * 1e-3), "unit": "triples/s", "test_triples": T,
                  "candidates": data.num_nodes, "ms": ms_eval / args.steps, "setting": "raw, both directions",
                  "e2e_value": T * args.steps / (ms_eval_e2e * 1e-3), "roofline": eval_roof},

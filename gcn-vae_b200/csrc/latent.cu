@@ -75,11 +75,15 @@ __global__ void prior_prepare_kernel(const float* __restrict__ z_pre, int k, int
 }
 
 // A warp takes kKlWarpRows consecutive rows at a time so that every prior value it fetches
-// (3 arrays x k mixtures per column) is applied to several rows: 3 + 3k / kKlWarpRows loads per
-// element instead of 3 + 3k.
-static constexpr int kKlWarpRows = 4;
+// (3 arrays x k mixtures per column) is applied to several rows.  V = 4: a lane owns float4 column
+// groups (h % 4 == 0, 16-byte aligned rows), every load is 128-bit.  The per-element work is kept to
+// the essentials: -t^2/(2v) with one approximate division, log(sqrt(v)) = 0.5 log v, and for the
+// mixture terms only fma(-(z-m_i)^2, 1/(2 v_i), .): the sum of log(sqrt(v_i)) + log(sqrt(2 pi)) over
+// the columns does not depend on the row and is accumulated once per warp.
+static constexpr int kKlWarpRows = 2;
 
-__global__ void __launch_bounds__(kThreads)
+template <int KM, int V>
+__global__ void __launch_bounds__(128, 4)
 kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
                   const float* __restrict__ zv, const float* __restrict__ z_pre,
                   const float* __restrict__ ws, int n, int h, int k, float* __restrict__ kl_rows,
@@ -89,55 +93,84 @@ kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
   if (row0 >= n) return;
   const float* inv2v = ws + (size_t)k * h;
   const float* lsq = ws + (size_t)2 * k * h;
-  float a[kKlWarpRows], b[kKlWarpRows][kMaxMix];
+  float a[kKlWarpRows], b[kKlWarpRows][KM], lsum[KM];
+#pragma unroll
+  for (int i = 0; i < KM; ++i) lsum[i] = 0.f;
 #pragma unroll
   for (int q = 0; q < kKlWarpRows; ++q) {
     a[q] = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxMix; ++i) b[q][i] = 0.f;
+    for (int i = 0; i < KM; ++i) b[q][i] = 0.f;
   }
-  for (int d = lane; d < h; d += 32) {
-    float zc[kKlWarpRows];
+  for (int d = lane * V; d < h; d += 32 * V) {
+    float zc[kKlWarpRows][V];
 #pragma unroll
     for (int q = 0; q < kKlWarpRows; ++q) {
-      const int row = min(row0 + q, n - 1);                  // rows past the end repeat the last one (not stored)
-      zc[q] = z[(size_t)row * h + d];
-      const float t = zc[q] - zm[(size_t)row * h + d];
-      const float v = zv[(size_t)row * h + d];
-      a[q] += -(t * t) / (2.f * v) - logf(sqrtf(v)) - KG_LOG_SQRT_2PI;      // utils.py:396
+      const size_t off = (size_t)min(row0 + q, n - 1) * h + d;      // rows past the end repeat the last one (not stored)
+      float mc[V], vc[V];
+      if (V == 4) {
+        const float4 t0 = *reinterpret_cast<const float4*>(z + off), t1 = *reinterpret_cast<const float4*>(zm + off),
+                     t2 = *reinterpret_cast<const float4*>(zv + off);
+        zc[q][0] = t0.x; zc[q][1] = t0.y; zc[q][V / 2] = t0.z; zc[q][V - 1] = t0.w;
+        mc[0] = t1.x; mc[1 % V] = t1.y; mc[V / 2] = t1.z; mc[V - 1] = t1.w;
+        vc[0] = t2.x; vc[1 % V] = t2.y; vc[V / 2] = t2.z; vc[V - 1] = t2.w;
+      } else {
+        zc[q][0] = z[off]; mc[0] = zm[off]; vc[0] = zv[off];
+      }
+#pragma unroll
+      for (int c = 0; c < V; ++c) {
+        const float t = zc[q][c] - mc[c];
+        a[q] += -__fdividef(t * t, 2.f * vc[c]) - 0.5f * __logf(vc[c]) - KG_LOG_SQRT_2PI;      // utils.py:396
+      }
     }
 #pragma unroll
-    for (int i = 0; i < kMaxMix; ++i)
+    for (int i = 0; i < KM; ++i)
       if (i < k) {
-        const float pm = __ldg(z_pre + (size_t)i * h + d), iv = __ldg(inv2v + (size_t)i * h + d),
-                    ls = __ldg(lsq + (size_t)i * h + d);
-#pragma unroll
-        for (int q = 0; q < kKlWarpRows; ++q) {
-          const float u = zc[q] - pm;
-          b[q][i] += -(u * u) * iv - ls - KG_LOG_SQRT_2PI;
+        const size_t po = (size_t)i * h + d;
+        float pm[V], iv[V];
+        if (V == 4) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(z_pre + po)),
+                       t1 = __ldg(reinterpret_cast<const float4*>(inv2v + po)),
+                       t2 = __ldg(reinterpret_cast<const float4*>(lsq + po));
+          pm[0] = t0.x; pm[1 % V] = t0.y; pm[V / 2] = t0.z; pm[V - 1] = t0.w;
+          iv[0] = t1.x; iv[1 % V] = t1.y; iv[V / 2] = t1.z; iv[V - 1] = t1.w;
+          lsum[i] += (t2.x + t2.y) + (t2.z + t2.w);
+        } else {
+          pm[0] = __ldg(z_pre + po); iv[0] = __ldg(inv2v + po);
+          lsum[i] += __ldg(lsq + po);
         }
+#pragma unroll
+        for (int q = 0; q < kKlWarpRows; ++q)
+#pragma unroll
+          for (int c = 0; c < V; ++c) {
+            const float u = zc[q][c] - pm[c];
+            b[q][i] = fmaf(-(u * u), iv[c], b[q][i]);
+          }
       }
   }
+  float cst[KM];                                       // sum_d [log(sqrt(v_i)) + log(sqrt(2 pi))]
+#pragma unroll
+  for (int i = 0; i < KM; ++i) cst[i] = i < k ? kg_warp_sum(lsum[i]) + (float)h * KG_LOG_SQRT_2PI : 0.f;
 #pragma unroll
   for (int q = 0; q < kKlWarpRows; ++q) {
     const int row = row0 + q;
     const float aq = kg_warp_sum(a[q]);
     float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kMaxMix; ++i)
+    for (int i = 0; i < KM; ++i)
       if (i < k) {
-        b[q][i] = kg_warp_sum(b[q][i]);
+        b[q][i] = kg_warp_sum(b[q][i]) - cst[i];
         mx = fmaxf(mx, b[q][i]);
       }
     float se = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxMix; ++i)
+    for (int i = 0; i < KM; ++i)
       if (i < k) se += expf(b[q][i] - mx);
     const float lse = mx + logf(se);                                        // utils.py:413-415
     if (row < n) {
       if (lane == 0) kl_rows[row] = aq - (lse - logf((float)k));            // utils.py:428, model.py:86
 #pragma unroll
-      for (int i = 0; i < kMaxMix; ++i)
+      for (int i = 0; i < KM; ++i)
         if (i < k && lane == (i & 31)) resp[(size_t)row * k + i] = expf(b[q][i] - lse);
     }
   }
@@ -199,8 +232,20 @@ extern "C" int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z
   prior_prepare_kernel<<<kg_div_up((long long)k * h, kThreads), kThreads, 0, st>>>(z_pre, k, h, prior_ws);
   KG_LAUNCH_OK();
   if (n == 0) return KG_OK;
-  kl_mog_fwd_kernel<<<kg_div_up((long long)kg_div_up(n, kKlWarpRows) * 32, kThreads), kThreads, 0, st>>>(
-      z, z_mean, z_var, z_pre, prior_ws, n, h, k, kl_rows, resp);
+  const int grid = kg_div_up((long long)kg_div_up(n, kKlWarpRows) * 32, 128);
+  const bool vec = h % 4 == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(z_mean) |
+                                   reinterpret_cast<uintptr_t>(z_var) | reinterpret_cast<uintptr_t>(z_pre) |
+                                   reinterpret_cast<uintptr_t>(prior_ws)) & 15) == 0;
+#define KG_KL_FWD(KM_)                                                                                          \
+  do {                                                                                                          \
+    if (vec) kl_mog_fwd_kernel<KM_, 4><<<grid, 128, 0, st>>>(z, z_mean, z_var, z_pre, prior_ws, n, h, k, kl_rows, resp); \
+    else kl_mog_fwd_kernel<KM_, 1><<<grid, 128, 0, st>>>(z, z_mean, z_var, z_pre, prior_ws, n, h, k, kl_rows, resp);     \
+  } while (0)
+  if (k <= 4) KG_KL_FWD(4);
+  else if (k <= 8) KG_KL_FWD(8);
+  else if (k <= 12) KG_KL_FWD(12);
+  else KG_KL_FWD(16);
+#undef KG_KL_FWD
   KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -188,16 +188,24 @@ basis_id_src_fwd_kernel(const float* __restrict__ V, const float* __restrict__ c
 // backward: thread (n, b) keeps V[b, n, :] and the gradient row dV[b, n, :] in registers
 //   dV[b, n, :]  = sum_{e: src = n} coef[r_e, b] * norm_e * g[dst_e, :]          (plain store, once)
 //   dcoef[r, b] += sum_e norm_e * <V[b, n, :], g[dst_e, :]>   (shared-memory table, flushed per CTA)
-// V / dV tiles go through shared memory ([b][nt*out_f] runs, odd pitch) so that global traffic is
-// whole contiguous runs while the lanes of a warp walk b.
+// Global traffic is whole contiguous runs: the V tile ([b][nt*out_f] runs, odd pitch so that lanes
+// walking b hit distinct banks) and the dV tile go through shared memory.  The tile's out-edges are
+// one contiguous range of the src-major list: they are staged in chunks - record + norm-scaled
+// g[dst] row, every load of a chunk in flight at once - and the (n, b) threads then walk their
+// node's share of the chunk from shared memory, so the dependent latencies (col_ptr -> record ->
+// g row) are paid once per chunk, not once per edge; hub nodes are simply many chunks.
+constexpr int kEdgeChunk = 128;
+
 template <int OF>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(320, 3)
 basis_id_src_bwd_kernel(const float* __restrict__ V, const float* __restrict__ coef, const float* __restrict__ g,
                         const int* __restrict__ col_ptr, const int4* __restrict__ pack, int n_src, int R, int NB,
                         int out_f, int NT, float* __restrict__ dV, float* __restrict__ dcoef) {
   extern __shared__ __align__(16) float sm[];
-  const int pitch = (NT * out_f) | 1;                  // odd: lanes over b hit distinct banks
-  float* coef_s = sm;                                  // [R][NB]
+  const int pitch = (NT * out_f) | 1;
+  float* G_s = sm;                                     // [kEdgeChunk][OF] norm * g[dst] (16-byte aligned rows)
+  int4* E_s = reinterpret_cast<int4*>(G_s + kEdgeChunk * OF);   // [kEdgeChunk] records
+  float* coef_s = reinterpret_cast<float*>(E_s + kEdgeChunk);   // [R][NB]
   float* dc_s = coef_s + (size_t)R * NB;               // [R][NB]
   float* T_s = dc_s + (size_t)R * NB;                  // [NB][pitch]  V tile, then dV tile
   for (int i = threadIdx.x; i < R * NB; i += blockDim.x) {
@@ -208,72 +216,54 @@ basis_id_src_bwd_kernel(const float* __restrict__ V, const float* __restrict__ c
   const int nl = t / NB, b = t - nl * NB;              // thread (node slot, basis)
   for (int n0 = blockIdx.x * NT; n0 < n_src; n0 += gridDim.x * NT) {
     const int nt = min(NT, n_src - n0), run = nt * out_f;
+    const bool mine = nl < nt;
     __syncthreads();                                   // previous tile written out; tables ready
     for (int i = t; i < NB * run; i += blockDim.x) {
       const int bb = i / run, j = i - bb * run;
       T_s[bb * pitch + j] = __ldg(V + ((size_t)bb * n_src + n0) * out_f + j);
     }
+    const int e_lo = __ldg(col_ptr + n0), e_hi = __ldg(col_ptr + n0 + nt);
+    int e0 = 0, e1 = 0;
+    if (mine) { e0 = __ldg(col_ptr + n0 + nl); e1 = __ldg(col_ptr + n0 + nl + 1); }
     __syncthreads();
-    const bool mine = nl < nt;
     float v[OF], acc[OF];
 #pragma unroll
     for (int o = 0; o < OF; ++o) {
       v[o] = (mine && o < out_f) ? T_s[b * pitch + nl * out_f + o] : 0.f;
       acc[o] = 0.f;
     }
-    int e0 = 0, e1 = 0;
-    if (mine) { e0 = __ldg(col_ptr + n0 + nl); e1 = __ldg(col_ptr + n0 + nl + 1); }
-    const bool heavy = e1 - e0 > kHeavy;
-    auto edge = [&](int e) {
-      const int4 p = __ldg(pack + e);                  // {dst, etype, norm, edge}: one address per node
-      const float nv = __int_as_float(p.z);
-      const float* gr = g + (size_t)p.x * out_f;
-      const float c = nv * coef_s[p.y * NB + b];
-      float d = 0.f;
+    for (int c0 = e_lo; c0 < e_hi; c0 += kEdgeChunk) { // uniform across the CTA
+      const int cn = min(kEdgeChunk, e_hi - c0);
+      __syncthreads();                                 // previous chunk consumed
+      for (int j = t; j < cn; j += blockDim.x) {
+        const int4 p = __ldg(pack + c0 + j);           // {dst, etype, norm, edge}
+        E_s[j] = p;
+        const float nv = __int_as_float(p.z);
+        const float* gr = g + (size_t)p.x * out_f;
 #pragma unroll
-      for (int o = 0; o < OF; ++o) {
-        if (o < out_f) {
-          const float gv = __ldg(gr + o);
-          d = fmaf(v[o], gv, d);
-          acc[o] = fmaf(c, gv, acc[o]);
-        }
+        for (int o = 0; o < OF; ++o) G_s[j * OF + o] = o < out_f ? nv * __ldg(gr + o) : 0.f;
       }
-      atomicAdd(dc_s + p.y * NB + b, nv * d);
-    };
-    if (!heavy)
-      for (int e = e0; e < e1; ++e) edge(e);
-    const bool any_heavy = __syncthreads_or(heavy);    // also: every thread holds its V row
-    if (!any_heavy) {
-      if (mine)
+      __syncthreads();
+      const int a0 = max(e0, c0) - c0, a1 = min(e1, c0 + cn) - c0;
+      for (int e = a0; e < a1; ++e) {
+        const int r = E_s[e].y;
+        const float c = coef_s[r * NB + b];
+        float d = 0.f;
 #pragma unroll
-        for (int o = 0; o < OF; ++o)
-          if (o < out_f) T_s[b * pitch + nl * out_f + o] = acc[o];
-    } else {
-      // tile with hub nodes: gradient rows are accumulated in shared memory instead
-      if (mine)
-#pragma unroll
-        for (int o = 0; o < OF; ++o)
-          if (o < out_f) T_s[b * pitch + nl * out_f + o] = heavy ? 0.f : acc[o];
-      const int slots = blockDim.x / NB;
-      for (int hn = 0; hn < nt; ++hn) {
-        const int h0 = __ldg(col_ptr + n0 + hn), h1 = __ldg(col_ptr + n0 + hn + 1);
-        if (h1 - h0 <= kHeavy) continue;               // uniform across the CTA
-        __syncthreads();
-        if (nl < slots) {
-          // every slot takes the hub's V row for its basis and a strided share of its edges
-          const float* vsrc = V + ((size_t)b * n_src + n0 + hn) * out_f;
-#pragma unroll
-          for (int o = 0; o < OF; ++o) {
-            v[o] = o < out_f ? __ldg(vsrc + o) : 0.f;
-            acc[o] = 0.f;
-          }
-          for (int e = h0 + nl; e < h1; e += slots) edge(e);
-#pragma unroll
-          for (int o = 0; o < OF; ++o)
-            if (o < out_f) atomicAdd(T_s + b * pitch + hn * out_f + o, acc[o]);
+        for (int o = 0; o < OF; o += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(G_s + e * OF + o);
+          d = fmaf(v[o], gv.x, d); d = fmaf(v[o + 1], gv.y, d); d = fmaf(v[o + 2], gv.z, d); d = fmaf(v[o + 3], gv.w, d);
+          acc[o] = fmaf(c, gv.x, acc[o]); acc[o + 1] = fmaf(c, gv.y, acc[o + 1]);
+          acc[o + 2] = fmaf(c, gv.z, acc[o + 2]); acc[o + 3] = fmaf(c, gv.w, acc[o + 3]);
         }
+        atomicAdd(dc_s + r * NB + b, d);
       }
     }
+    __syncthreads();                                   // every thread holds its V row: the tile becomes dV
+    if (mine)
+#pragma unroll
+      for (int o = 0; o < OF; ++o)
+        if (o < out_f) T_s[b * pitch + nl * out_f + o] = acc[o];
     __syncthreads();
     for (int i = t; i < NB * run; i += blockDim.x) {
       const int bb = i / run, j = i - bb * run;
@@ -295,12 +285,12 @@ SrcPlan src_plan(int R, int NB, int out_f) {
   SrcPlan p{0, 0, 0, 0, 0};
   if (NB > 64 || out_f > 16 || NB < 2) return p;
   p.nbr = NB <= 16 ? 16 : NB <= 32 ? 32 : NB <= 48 ? 48 : 64;
-  p.nt = 640 / NB;                                     // backward: NT * NB threads
+  p.nt = 320 / NB;                                     // backward: NT * NB threads
   if (p.nt > 32) p.nt = 32;
   if (p.nt < 1) return SrcPlan{0, 0, 0, 0, 0};
   p.threads = (p.nt * NB + 31) / 32 * 32;
   p.smem_fwd = sizeof(float) * ((size_t)R * p.nbr + (size_t)out_f * p.nbr);
-  p.smem_bwd = sizeof(float) * ((size_t)2 * R * NB + (size_t)NB * ((p.nt * out_f) | 1));
+  p.smem_bwd = sizeof(float) * ((size_t)kEdgeChunk * (16 + 4) + (size_t)2 * R * NB + (size_t)NB * ((p.nt * out_f) | 1));
   if (p.smem_fwd > 100 * 1024 || p.smem_bwd > 100 * 1024) return SrcPlan{0, 0, 0, 0, 0};
   return p;
 }
@@ -607,7 +597,7 @@ extern "C" int kg_basis_id_src_bwd(const float* V, const float* coef, const floa
   KG_REQUIRE(pl.nt > 0, "basis id src bwd: shape not covered (num_bases <= 64, out_feat <= 16)");
   if (n_src == 0) return KG_OK;
   const int tiles = kg_div_up(n_src, pl.nt);
-  const int grid = tiles < 2 * kg_sm_count() ? tiles : 2 * kg_sm_count();
+  const int grid = tiles < 6 * kg_sm_count() ? tiles : 6 * kg_sm_count();
   cudaStream_t st = kg_stream(stream);
   const int4* pack = reinterpret_cast<const int4*>(bwd_pack);
   if (out_feat <= 12) {

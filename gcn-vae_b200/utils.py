@@ -233,3 +233,30 @@ def log_mean_exp(x, dim):
 
 def log_normal_mixture(z, m, v):
     return log_mean_exp(log_normal(z.unsqueeze(1), m, v), dim=-1)
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging of step inputs (the ``.cuda()`` copies of
+    kgvae/link_predict.py:217-220) on a side stream: ``submit`` starts the copies of a dict of
+    pinned host tensors, ``take`` hands the device tensors to the current stream once they have
+    landed.  Submitting step i+1 before running step i hides the copy behind the step's kernels."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._pending = []
+
+    def submit(self, host_tensors):
+        with torch.cuda.stream(self.stream):
+            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_tensors.items()}
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._pending.append((dev, done))
+
+    def take(self):
+        dev, done = self._pending.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        for t in dev.values():
+            t.record_stream(cur)          # allocated on the side stream, consumed on this one
+        return dev
