@@ -21,8 +21,11 @@
 // so there is no CTA-wide barrier in the loop.  dX and dW share one kernel (both need the gathered
 // dagg row).  Summation order across CTAs is not fixed: results are reproducible to fp32 rounding.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "rgcn_bdd_own.cuh"
 #include "rgcn_bdd_tile.cuh"
+#include "rgcn_bdd_warp.cuh"
 
 namespace {
 
@@ -436,6 +439,16 @@ bool fast_shape(int B, int si, int so) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// KG_BDD_WARP=0 selects the CTA-synchronised block-owner kernels (rgcn_bdd_own.cuh) instead of the
+// warp-autonomous ones (rgcn_bdd_warp.cuh): an A/B switch for profiling, read once.
+bool warp_kernels() {
+  static const bool on = [] {
+    const char* v = getenv("KG_BDD_WARP");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace
 
 #define KG_BDD_DISPATCH(FN, SI_, SO_, ...) \
@@ -457,6 +470,10 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(weight) && aligned16(agg)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
+    if (warp_kernels()) {
+      if (so == 5) return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+      return bddwarp::launch_fwd<5, 10, 2, 2, 8>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    }
     if (so == 5) return bddown::launch_fwd<5, 5, 4, 1>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
     return bddown::launch_fwd<5, 10, 2, 2>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
   }
@@ -492,6 +509,11 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(dagg) && aligned16(weight) &&
       aligned16(dx) && aligned16(dweight)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
+    if (warp_kernels()) {
+      if (so == 5)
+        return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+      return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    }
     if (so == 5)
       return bddown::launch_bwd<5, 5, 4, 1>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
     return bddown::launch_bwd<5, 10, 2, 2>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);

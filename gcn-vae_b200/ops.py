@@ -4,6 +4,8 @@ Each Function is one fused operator of the link-prediction path and names the re
 code it replaces.  All tensors are CUDA, fp32 / int32, contiguous; PyTorch supplies device
 memory, the stream and autograd bookkeeping only.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -74,7 +76,7 @@ class GraphIndex:
 
 # Rows that message passing reduces into (agg[dst] forward, x[src] + dx[src] backward) are kept
 # L2-resident: graphs whose reduced matrix exceeds this budget are walked tile by tile.
-L2_TILE_BYTES = 32 << 20
+L2_TILE_BYTES = int(os.environ.get("KG_L2_TILE_MB", "32")) << 20   # reduced rows of one node tile (tuning knob)
 L2_RESIDENT_BYTES = 96 << 20        # a reduced matrix up to this size is left untiled (126 MB L2)
 L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read with evict-first
 HINT_STREAM_X, HINT_STREAM_D, HINT_TILE_RESIDENT = 1, 2, 4
