@@ -238,25 +238,44 @@ def log_normal_mixture(z, m, v):
 class DevicePrefetcher:
     """Double-buffered host -> device staging of step inputs (the ``.cuda()`` copies of
     kgvae/link_predict.py:217-220) on a side stream: ``submit`` starts the copies of a dict of
-    pinned host tensors, ``take`` hands the device tensors to the current stream once they have
-    landed.  Submitting step i+1 before running step i hides the copy behind the step's kernels."""
+    pinned host tensors into one of ``depth`` persistent device buffer sets, ``take`` hands that
+    set to the current stream once the copies have landed.  Submitting step i+1 before running
+    step i hides the copy behind the step's kernels.  A set is overwritten only after the work
+    that was enqueued on the consumer stream before the following ``take`` has finished with it."""
 
-    def __init__(self, device):
+    def __init__(self, device, depth=2):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
+        self._slots = [None] * depth
+        self._free = [None] * depth        # event: the slot's last consumer work is enqueued up to here
+        self._count = 0
         self._pending = []
+        self._last = None
 
     def submit(self, host_tensors):
+        slot = self._count % len(self._slots)
+        self._count += 1
+        if self._free[slot] is not None:
+            self.stream.wait_event(self._free[slot])
         with torch.cuda.stream(self.stream):
-            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_tensors.items()}
+            bufs = self._slots[slot]
+            if bufs is None or any(k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype
+                                   for k, v in host_tensors.items()):
+                bufs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_tensors.items()}
+                self._slots[slot] = bufs
+            for k, v in host_tensors.items():
+                bufs[k].copy_(v, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.stream)
-        self._pending.append((dev, done))
+        self._pending.append((slot, done))
 
     def take(self):
-        dev, done = self._pending.pop(0)
+        slot, done = self._pending.pop(0)
         cur = torch.cuda.current_stream(self.device)
+        if self._last is not None:         # everything enqueued so far may still read the previous set
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._free[self._last] = ev
+        self._last = slot
         cur.wait_event(done)
-        for t in dev.values():
-            t.record_stream(cur)          # allocated on the side stream, consumed on this one
-        return dev
+        return {k: self._slots[slot][k] for k in self._slots[slot]}

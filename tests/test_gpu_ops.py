@@ -597,3 +597,28 @@ def test_rank_filtered():
     dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
     got = ops.distmult_rank(emb.to(DEV), w.to(DEV), dv(a), dv(r), dv(b), filt_ptr=dv(ptr), filt_idx=dv(idx))
     assert torch.equal(got.cpu().long(), want)
+
+
+# ------------------------------------------------------------------------------ host -> device staging
+def test_device_prefetcher_double_buffering():
+    """utils.DevicePrefetcher: each take() returns the tensors of the matching submit(), also when the
+    host buffers are rewritten between steps and the consumer is still busy with the previous set."""
+    pf = K.utils.DevicePrefetcher(DEV)
+    host = {"a": torch.zeros(1 << 20, dtype=torch.int32).pin_memory(), "b": torch.zeros(7, 3).pin_memory()}
+    sums = []
+    host["a"].fill_(0)
+    pf.submit(host)
+    for i in range(6):
+        t = pf.take()
+        torch.cuda.current_stream().synchronize()       # the copy of step i has landed: the host buffer may change
+        if i + 1 < 6:
+            host["a"].fill_(i + 1)
+            host["b"].fill_(float(i + 1))
+            pf.submit(host)
+        x = t["a"].float()
+        for _ in range(20):                             # keep the consumer busy while the next copy flies
+            x = x * 1.0000001
+        sums.append((int(t["a"][123]), float(t["b"][2, 1]), x))
+    torch.cuda.synchronize()
+    assert [s[0] for s in sums] == list(range(6))
+    assert [s[1] for s in sums] == [float(i) for i in range(6)]
