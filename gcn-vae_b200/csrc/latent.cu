@@ -176,7 +176,7 @@ kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
   }
 }
 
-static constexpr int kKlRows = 64;   // rows per CTA in the backward kernel
+static constexpr int kKlRows = 32;   // rows per CTA in the backward kernel
 
 __global__ void __launch_bounds__(128)
 kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
@@ -195,6 +195,7 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
     gpm[i] = 0.f;
     gpv[i] = 0.f;
   }
+#pragma unroll 2
   for (int row = r0; row < r1; ++row) {
     const size_t off = (size_t)row * h + d;
     const float zc = z[off], v = zv[off];

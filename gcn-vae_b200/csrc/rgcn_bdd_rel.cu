@@ -510,6 +510,11 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
       aligned16(dx) && aligned16(dweight)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
     if (warp_kernels()) {
+      if (hints & kHintStreamD) {             // dagg streams from HBM: partner warps share one gather of it
+        if (so == 5)
+          return bddwarp::launch_bwd_paired<5, 5, 4, 1, 6>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+        return bddwarp::launch_bwd_paired<5, 10, 2, 2, 8>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+      }
       if (so == 5)
         return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
       return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);

@@ -13,6 +13,10 @@
 //   forward   warp = (edge share, half of the blocks): x[src] slice -> out[dst] slice
 //   backward  input-gradient warps: dagg[dst] slice -> dx[src] slice (bulk reduce-add)
 //             weight-gradient warps: x[src] slice + dagg[dst] slice -> dW_r in registers
+//             Two variants: fully independent warps (every matrix L2-resident: FB15k-237 / WN18
+//             shapes; fastest there, 0.39 vs 0.49 ms) and PAIRED warps that share one ring so that
+//             dagg[dst] crosses HBM once per edge (streaming regime, wikikg2 shape: the independent
+//             warps drift apart and fetched it twice - 148 GB instead of 103 GB of DRAM traffic).
 #pragma once
 #include "rgcn_bdd_own.cuh"
 
@@ -311,6 +315,181 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// fused backward, PAIRED variant for the streaming regime (dagg larger than L2)
+// ------------------------------------------------------------------------------------------
+// The input-gradient warp i and the weight-gradient warp i of a slot own the SAME blocks, hence the
+// same slice of dagg[dst]: they are PARTNERS on one ring (stage = dagg slice + x slice, gathered
+// once by the pair's issuer).  `full[stage]` is waited on by both; `empty[stage]` collects one
+// arrival per partner before the issuer refills the stage, so the partners stay within DEPTH edges
+// of each other and the dagg row crosses HBM / L2 once per edge, not once per role.
+template <int SI, int SO, int TB, int WPR>
+struct PairedLayout {
+  static constexpr int XN = TB * SI, DN = TB * SO, WPS = 2 * WPR, SLOTS = kWarps / WPS, PAIRS = kWarps / 2;
+  int lpw, xoff, stage_f;
+  __host__ __device__ PairedLayout(int B) {
+    lpw = lanes_per_warp(B / TB, WPR, XN);                     // whole 16-byte pieces of dx per warp
+    xoff = round4(lpw * DN) + 4;                               // dagg slice, then x slice
+    stage_f = xoff + round4(lpw * XN) + 4;
+  }
+  __host__ __device__ int pair_f(int depth) const { return depth * stage_f + 2 * 32 * XN; }   // ring + parked dx
+  __host__ size_t smem(int depth) const {
+    return sizeof(float) * ((size_t)4 * kChunk + (size_t)PAIRS * pair_f(depth)) + sizeof(uint64_t) * 2 * PAIRS * depth;
+  }
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int SI, int SO, int TB, int WPR, int DEPTH>
+__global__ void __launch_bounds__(kCta)
+bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
+           const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
+  constexpr int XN = TB * SI, DN = TB * SO, WN = TB * SI * SO, WPS = 2 * WPR, SLOTS = kWarps / WPS, PAIRS = kWarps / 2;
+  extern __shared__ __align__(16) float sm[];
+  const PairedLayout<SI, SO, TB, WPR> L(B);
+  const int in_w = B * SI, out_w = B * SO, per = B / TB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp / WPS, wsl = warp % WPS;
+  const bool xrole = wsl < WPR;               // warp-uniform: input-gradient warps come first
+  const int wr_i = xrole ? wsl : wsl - WPR;   // warp index inside its role = pair index inside the slot
+  const int pair = slot * WPR + wr_i;
+  const bool have_dx = dx != nullptr;
+  const bool issuer = have_dx ? xrole : !xrole;               // who gathers for the pair
+  int4* P_s = reinterpret_cast<int4*>(sm);
+  float* ring = sm + 4 * kChunk + pair * L.pair_f(DEPTH);
+  float* tbuf = ring + DEPTH * L.stage_f;     // [2][32 * XN] parked input gradients
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + 4 * kChunk + PAIRS * L.pair_f(DEPTH)) + pair * 2 * DEPTH;
+  uint64_t* empty = full + DEPTH;
+  const int e0 = blockIdx.x * kChunk, n = min(E - e0, kChunk);
+  for (int i = threadIdx.x; i < n; i += kCta) P_s[i] = __ldg(pack + e0 + i);
+  if (issuer && lane == 0) {
+    for (int i = 0; i < DEPTH; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, have_dx ? 2 : 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                            // the only CTA-wide barrier
+  const int share = (n + SLOTS - 1) / SLOTS;
+  const int k_lo = slot * share, n_my = max(0, min(n - k_lo, share));
+  const int g_lo = wr_i * L.lpw, cnt = max(0, min(L.lpw, per - g_lo));
+  if (n_my == 0 || cnt == 0 || (xrole && !have_dx)) return;
+  const int4* rec = P_s + k_lo;
+  const Span ds = make_span(g_lo * DN, cnt * DN), xsp = make_span(g_lo * XN, cnt * XN);
+  const uint64_t pol_x = x.parts != nullptr ? l2_policy(false) : (hints & 4) ? l2_policy_last(true) : l2_policy(hints & 1);
+  const uint64_t pol_d = l2_policy(hints & 2);
+  const uint64_t pol_red = l2_policy_last(hints & 4);
+  auto gather = [&](int k, int st) {          // issuer lane 0: both slices of the pair's stage
+    const int4 p = rec[k];
+    mbar_expect_tx(full + st, ds.bytes + xsp.bytes);
+    bulk_g2s(ring + st * L.stage_f, row_at(dagg, p.y, out_w) + ds.start, ds.bytes, full + st, pol_d);
+    bulk_g2s(ring + st * L.stage_f + L.xoff, x.row(p.x, in_w) + xsp.start, xsp.bytes, full + st, pol_x);
+  };
+  // after this warp has consumed stage st for edge k: tell the pair, and (issuer) refill it for edge k + DEPTH
+  auto release = [&](int k, int st) {         // lane 0
+    mbar_arrive(empty + st);
+    if (issuer && k + DEPTH < n_my) {
+      mbar_wait(empty + st, (k / DEPTH) & 1); // the partner is done with it as well
+      gather(k + DEPTH, st);
+    }
+  };
+  if (issuer && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k)
+      if (k < n_my) gather(k, k);
+  }
+  const int gl = min(lane, cnt - 1);          // idle lanes shadow the last owner (never stored)
+  const bool owner = lane < cnt;
+  const float* dg = ring + ds.skip + gl * DN;
+  const float* xg = ring + L.xoff + xsp.skip + gl * XN;
+  const size_t KW = (size_t)B * SI * SO;
+  const float* w_g = weight + (size_t)(g_lo + gl) * WN;
+  float* dW_g = dW + (size_t)(g_lo + gl) * WN;
+  float* dx_w = dx + g_lo * XN;
+  const uint32_t warp_bytes = (uint32_t)cnt * XN * 4;
+  float r[WN];                                // dX role: my blocks of W_r; dW role: their gradient
+#pragma unroll
+  for (int i = 0; i < WN; ++i) r[i] = 0.f;
+
+  if (xrole) {                                // warp-uniform: one loop per role keeps the live ranges apart
+    int cur = -1;
+    _Pragma("unroll 1") for (int k = 0; k < n_my; ++k) {
+      const int st = k % DEPTH;
+      mbar_wait(full + st, (k / DEPTH) & 1);
+      const int4 p = rec[k];
+      const float nv = __int_as_float(p.w);
+      if (p.z != cur) {
+        cur = p.z;
+        const float4* wr = reinterpret_cast<const float4*>(w_g + (size_t)(unsigned)cur * KW);
+#pragma unroll
+        for (int i = 0; i < WN / 4; ++i) {
+          const float4 t = __ldg(wr + i);
+          r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+        }
+      }
+      float dv[DN], m[XN];
+      lds_vec<DN>(dv, dg + st * L.stage_f);
+#pragma unroll
+      for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+        for (int i = 0; i < SI; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int o = 0; o < SO; ++o) a = fmaf(dv[tb * SO + o], r[(tb * SI + i) * SO + o], a);
+          m[tb * SI + i] = nv * a;
+        }
+      float* tb_cur = tbuf + (k & 1) * 32 * XN;
+      bulk_wait_read<1>();
+      __syncwarp();
+      park_raw<XN>(tb_cur + lane * XN, m);
+      fence_async_smem();
+      __syncwarp();                           // gradients parked; every lane has consumed ring stage st
+      if (lane == 0) {
+        bulk_red_add(const_cast<float*>(row_at(dx_w, p.x, in_w)), tb_cur, warp_bytes, pol_red);
+        bulk_commit();
+        release(k, st);
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  } else {
+    auto flush = [&](int rel) {               // owners only
+      float* dst = dW_g + (size_t)(unsigned)rel * KW;
+#pragma unroll
+      for (int i = 0; i < WN; i += 4) {
+        if (owner) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+        r[i] = r[i + 1] = r[i + 2] = r[i + 3] = 0.f;
+      }
+    };
+    int k = 0;
+    _Pragma("unroll 1") while (k < n_my) {    // one relation run at a time: the accumulators start from zero
+      const int rel = rec[k].z;
+      _Pragma("unroll 1") do {
+        const int st = k % DEPTH;
+        mbar_wait(full + st, (k / DEPTH) & 1);
+        const float nv = __int_as_float(rec[k].w);
+        float dv[DN], xv[XN];
+        lds_vec<DN>(dv, dg + st * L.stage_f);
+        lds_vec<XN>(xv, xg + st * L.stage_f);
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+          for (int i = 0; i < SI; ++i) {
+            const float xs = nv * xv[tb * SI + i];
+#pragma unroll
+            for (int o = 0; o < SO; ++o)
+              r[(tb * SI + i) * SO + o] = fmaf(xs, dv[tb * SO + o], r[(tb * SI + i) * SO + o]);
+          }
+        __syncwarp();                         // every lane has consumed ring stage st
+        if (lane == 0) release(k, st);
+        ++k;
+      } while (k < n_my && rec[k].z == rel);
+      flush(rel);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 template <int FI, int FO, int TB, int WPS, int DEPTH>
@@ -329,6 +508,18 @@ int launch_bwd(RowSource x, const float* dagg, const void* pack, int E, const fl
                float* dx, float* dW, cudaStream_t st) {
   const size_t smem = BwdLayout<SI, SO, TB, WPR>(B).smem(DEPTH);
   auto kern = bwd_kernel<SI, SO, TB, WPR, DEPTH>;
+  KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
+                                                 dx, dW);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+template <int SI, int SO, int TB, int WPR, int DEPTH>
+int launch_bwd_paired(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
+                      float* dx, float* dW, cudaStream_t st) {
+  const size_t smem = PairedLayout<SI, SO, TB, WPR>(B).smem(DEPTH);
+  auto kern = bwd_paired_kernel<SI, SO, TB, WPR, DEPTH>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
                                                  dx, dW);
