@@ -447,10 +447,23 @@ def run_entity(args):
     params = [p for p in model.parameters() if p.requires_grad]
     feats = model.create_features()
 
+    graphs = {}
+
+    def graph_of(t):
+        """The graph object is built ONCE, before the epoch loop, as in the reference
+        (kgvae/entity_classify.py:80-82); its device edge index is built on first use and reused by every
+        epoch.  (The e2e leg hands over freshly copied tensors each step, so there the index is rebuilt.)"""
+        key = t["src"].data_ptr()
+        if key not in graphs:
+            gr = K.Graph()
+            gr._n = N
+            gr._dev_edges[dev] = (t["src"], t["dst"])
+            graphs.clear()
+            graphs[key] = gr
+        return graphs[key]
+
     def step(t):
-        gr = K.Graph()                                      # fresh graph: the index is rebuilt every step
-        gr._n = N
-        gr._dev_edges[dev] = (t["src"], t["dst"])
+        gr = graph_of(t)
         opt.zero_grad(set_to_none=True)
         logits = model(gr, feats, t["etype"], t["norm"])
         loss = F.cross_entropy(logits[t["train_idx"]], t["labels"][t["train_idx"]])
@@ -540,7 +553,8 @@ def run_entity(args):
                    "classes": data.num_classes, "n_hidden": n_hidden, "n_bases": n_bases, "l2norm": l2norm,
                    "train_nodes": len(data.train_idx), "scale": args.scale,
                    "parallelism": f"replicas x{world} (grad all-reduce)",
-                   "timed": "graph index + fwd + cross-entropy + bwd + Adam; per-step CUDA events",
+                   "timed": "fwd + cross-entropy + bwd + Adam (graph built once before the epochs, as in the reference); "
+                            "per-step CUDA events",
                    "l2": "inputs (2.67 GB basis table) far larger than L2"},
         "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

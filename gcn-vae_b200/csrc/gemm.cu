@@ -58,6 +58,22 @@ gemm_kernel(TileLoader<A_KC> la, TileLoader<B_KC> lb, int K, int k_chunk, Epilog
   }
 }
 
+// K = 0: the epilogue alone, one thread per element (narrow outputs would waste a 128 x 128 tile)
+__global__ void __launch_bounds__(256)
+epilogue_only_kernel(Epilogue ep) {
+  const long long total = (long long)ep.M * ep.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / ep.N), n = (int)(i - (long long)m * ep.N);
+    const size_t off = (size_t)m * ep.ldc + n;
+    float v = ep.bias ? __ldg(ep.bias + n) : 0.f;
+    if (ep.addend) v += __ldg(ep.addend + off);
+    if (ep.relu) v = fmaxf(v, 0.f);
+    if (ep.mask) v *= __ldg(ep.mask + off);
+    if (ep.accumulate) v += ep.C[off];
+    ep.C[off] = v;
+  }
+}
+
 template <bool A_KC, bool B_KC>
 static int launch(const float* A, int lda, const float* B, int ldb, int M, int N, int K, int splits,
                   int k_chunk, Epilogue ep, cudaStream_t st) {
@@ -85,6 +101,13 @@ extern "C" int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B,
   KG_REQUIRE(C && (K == 0 || (A && B)), "gemm: null operand");
   if (M == 0 || N == 0) return KG_OK;
   cudaStream_t st = kg_stream(stream);
+  if (K == 0) {
+    Epilogue ep{C, ldc, M, N, bias, addend, mask, relu, accumulate, 0};
+    const long long blocks = ((long long)M * N + 255) / 256, cap = 16LL * kg_sm_count();
+    epilogue_only_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(ep);
+    KG_LAUNCH_OK();
+    return KG_OK;
+  }
   if (kg_gemm_tc_eligible(M, N, K))
     return kg_gemm_tc_run(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, addend, relu, mask,
                           accumulate, workspace, workspace_bytes, st);

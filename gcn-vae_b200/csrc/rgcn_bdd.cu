@@ -131,6 +131,26 @@ __global__ void colsum_stage2(const float* __restrict__ partial, int cols, int c
   out[col] = s;
 }
 
+// narrow matrices (cols <= 32, e.g. the 10 / 11 columns of the entity-classification layers):
+// consecutive threads walk the matrix as one flat array (coalesced), thread t owns column t % cols
+__global__ void __launch_bounds__(256)
+colsum_narrow(const float* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[256];
+  const int tpr = 256 / cols;                            // rows per block pass
+  const int rig = threadIdx.x / cols, col = threadIdx.x - rig * cols;
+  float s = 0.f;
+  if (rig < tpr)
+    for (long long r = (long long)blockIdx.x * tpr + rig; r < rows; r += (long long)gridDim.x * tpr)
+      s += x[(size_t)r * cols + col];
+  red[threadIdx.x] = rig < tpr ? s : 0.f;
+  __syncthreads();
+  if (threadIdx.x < cols) {
+    float tot = 0.f;
+    for (int g = 0; g < tpr; ++g) tot += red[g * cols + threadIdx.x];
+    atomicAdd(out + threadIdx.x, tot);
+  }
+}
+
 extern "C" size_t kg_colsum_workspace_bytes(int rows, int cols) {
   return kg_align_up((size_t)colsum_chunks(rows) * (cols > 0 ? cols : 1) * sizeof(float));
 }
@@ -141,6 +161,13 @@ extern "C" int kg_colsum(const float* x, int rows, int cols, float* out, void* w
   cudaStream_t st = kg_stream(stream);
   if (rows == 0) {
     KG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+    return KG_OK;
+  }
+  if (cols <= 32 && rows >= 4096) {
+    KG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+    const int want = kg_div_up(rows, (256 / cols) * 16), cap = 8 * kg_sm_count();
+    colsum_narrow<<<want < cap ? want : cap, 256, 0, st>>>(x, rows, cols, out);
+    KG_LAUNCH_OK();
     return KG_OK;
   }
   const int chunks = colsum_chunks(rows);
