@@ -197,7 +197,7 @@ basis_id_src_fwd_kernel(const float* __restrict__ V, const float* __restrict__ c
 constexpr int kEdgeChunk = 128;
 
 template <int OF>
-__global__ void __launch_bounds__(320, 3)
+__global__ void __launch_bounds__(640, 2)
 basis_id_src_bwd_kernel(const float* __restrict__ V, const float* __restrict__ coef, const float* __restrict__ g,
                         const int* __restrict__ col_ptr, const int4* __restrict__ pack, int n_src, int R, int NB,
                         int out_f, int NT, float* __restrict__ dV, float* __restrict__ dcoef) {
@@ -285,7 +285,7 @@ SrcPlan src_plan(int R, int NB, int out_f) {
   SrcPlan p{0, 0, 0, 0, 0};
   if (NB > 64 || out_f > 16 || NB < 2) return p;
   p.nbr = NB <= 16 ? 16 : NB <= 32 ? 32 : NB <= 48 ? 48 : 64;
-  p.nt = 320 / NB;                                     // backward: NT * NB threads
+  p.nt = 640 / NB;                                     // backward: NT * NB threads
   if (p.nt > 32) p.nt = 32;
   if (p.nt < 1) return SrcPlan{0, 0, 0, 0, 0};
   p.threads = (p.nt * NB + 31) / 32 * 32;

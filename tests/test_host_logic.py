@@ -105,3 +105,28 @@ def test_filter_csr():
     assert ptr.tolist() == [0, 2, 3, 3] and idx.tolist() == [1, 2, 0]
     ptr, idx = K.utils.build_filter(allt, [1, 2], [0, 0], 2, "subject", "cpu")
     assert ptr.tolist() == [0, 2, 3] and idx.tolist() == [0, 4, 0]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU oracle port on the host cores) prints ONE JSON line with the keys the
+    driver reads; runs without a GPU.  The non-zero ranks of a torchrun launch print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "fb15k237-full"
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
