@@ -622,3 +622,31 @@ def test_device_prefetcher_double_buffering():
     torch.cuda.synchronize()
     assert [s[0] for s in sums] == list(range(6))
     assert [s[1] for s in sums] == [float(i) for i in range(6)]
+
+
+@pytest.mark.parametrize("B,si,so", [(100, 5, 5), (100, 5, 10), (25, 20, 40)])
+@pytest.mark.parametrize("tiled", [False, True])
+def test_bdd_layer_weight_gradient_only(B, si, so, tiled, monkeypatch):
+    """The layer input does not require a gradient (dx = NULL at the C boundary): the input-gradient warps
+    retire at once and the weight-gradient warps gather for themselves - independent and paired variants."""
+    if tiled:
+        monkeypatch.setattr(ops, "L2_TILE_BYTES", 40 * 4 * B * so)
+        monkeypatch.setattr(ops, "L2_RESIDENT_BYTES", 0)
+        monkeypatch.setattr(ops, "L2_STREAM_BYTES", 0)
+    n, e, r = 300, 6000, 11
+    src, dst, et, norm = _rand_graph(9, n, e, r)
+    g = torch.Generator().manual_seed(B + so)
+    x = torch.randn(n, B * si, generator=g)
+    weight = (torch.randn(r, B * si * so, generator=g) * 0.3).requires_grad_(True)
+    loop = torch.randn(B * si, B * so, generator=g) * 0.05
+    bias = torch.randn(B * so, generator=g)
+    gout = torch.randn(n, B * so, generator=g)
+    graph = {"num_nodes": n, "src": src, "dst": dst, "etype": et, "edge_norm": norm.reshape(-1, 1)}
+    want = O.rgcn_bdd_layer(x, graph, weight, bias, loop, B, None, None)
+    want.backward(gout)
+    gi = _index(src, dst, et, norm, n, r)
+    cw = weight.detach().to(DEV).requires_grad_(True)
+    out = ops.BddConvFn.apply(x.to(DEV), cw, loop.to(DEV), bias.to(DEV), gi, B, 0, None)
+    out.backward(gout.to(DEV))
+    assert_close(out, want, RTOL, "bdd out")
+    assert_close(cw.grad, weight.grad, RTOL, "bdd dW")
