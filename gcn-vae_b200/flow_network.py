@@ -90,7 +90,13 @@ class MADE(nn.Module):
         log_det = None
         n_pass = len(self.m)
         for p, mult in enumerate(self._col_mult):
-            out = self._run_net(x, weights)
+            if p == 0:
+                # the reference starts from x = 0 (flow_network.py:91): every row of the first pass sees the
+                # same input, so net(0) is ONE row - 5 one-row products instead of 5 N-row GEMMs, and in the
+                # backward the expand turns the N-row gradient into its column sum before the network
+                out = self._run_net(x[:1], weights).expand(z.shape[0], -1)
+            else:
+                out = self._run_net(x, weights)
             x, log_det = ops.IafUpdateFn.apply(z, out, x, mult, p + 1 == n_pass)
         return x, log_det
 
