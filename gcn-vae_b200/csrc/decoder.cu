@@ -396,8 +396,12 @@ distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, con
       }
       dot = kg_warp_sum(dot);
       const float xv = dot + shift, y = __ldg(labels + rc.w);
-      loss += fmaxf(xv, 0.f) - xv * y + log1pf(expf(-fabsf(xv)));     // F.binary_cross_entropy_with_logits
-      g = (kg_sigmoid(xv) - y) * inv_S;
+      // F.binary_cross_entropy_with_logits and its derivative from ONE fast exponential: t = e^{-|x|},
+      // softplus(-|x|) = log(1 + t), sigmoid(x) = x >= 0 ? 1 / (1 + t) : t / (1 + t).  (Every lane computes
+      // this per triplet, so it is kept to ~10 instructions; errors ~1e-7, far inside the 1e-4 bar.)
+      const float t = __expf(-fabsf(xv)), inv1t = __frcp_rn(1.f + t);
+      loss += fmaxf(xv, 0.f) - xv * y + __logf(1.f + t);
+      g = ((xv >= 0.f ? inv1t : t * inv1t) - y) * inv_S;
       gsum += g;
       if (lane == 0) {
         g_out[rc.w] = g;
