@@ -32,9 +32,21 @@ split_rows_kernel(const float* __restrict__ src, int ld, int rows, int K, int Kp
   amax = warp_max(amax);
   const float s = split_scale(amax);
   __half* row = cat + (size_t)r * 2 * Kp;
-  for (int k = lane; k < Kp; k += 32) {
-    if (k < K) split_store(__ldg(x + k), s, row + k, row + Kp + k);
-    else { row[k] = __float2half_rn(0.f); row[Kp + k] = __float2half_rn(0.f); }
+  const bool vec2 = (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+  for (int k = 2 * lane; k < Kp; k += 64) {          // two columns per lane: half2 stores, 128 B per warp and term
+    float x0 = 0.f, x1 = 0.f;
+    if (vec2 && k + 1 < K) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(x + k));
+      x0 = t.x; x1 = t.y;
+    } else {
+      if (k < K) x0 = __ldg(x + k);
+      if (k + 1 < K) x1 = __ldg(x + k + 1);
+    }
+    x0 *= s; x1 *= s;
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    *reinterpret_cast<__half2*>(row + k) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(row + Kp + k) =
+        __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
   }
   if (lane == 0) inv_scale[r] = 1.f / s;
 }
@@ -58,24 +70,29 @@ colmax_kernel(const float* __restrict__ src, int ld, int K, int rows, int k_chun
   }
 }
 
-// pass 2: 32(k) x 32(r) tiles through shared memory; writes hi|lo rows, zero padding up to Kp
+// pass 2: 64(k) x 32(r) tiles through shared memory; writes hi|lo rows as half2 pairs (a warp stores
+// 128 contiguous bytes per row and term), zero padding up to Kp (Kp is a multiple of 64)
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int ld, int K, int rows, int Kp,
                        const unsigned* __restrict__ amax_bits, __half* __restrict__ cat,
                        float* __restrict__ inv_scale) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;     // K (up to millions of nodes) on grid.x
-  for (int i = threadIdx.y; i < 32; i += 8) {
+  __shared__ float tile[64][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 64;     // K (up to millions of nodes) on grid.x
+  for (int i = threadIdx.y; i < 64; i += 8) {
     const int k = k0 + i, r = r0 + threadIdx.x;
     tile[i][threadIdx.x] = (k < K && r < rows) ? __ldg(src + (size_t)k * ld + r) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, k = k0 + threadIdx.x;
+    const int r = r0 + i;
     if (r >= rows) continue;
     const float s = split_scale(__uint_as_float(__ldg(amax_bits + r)));
-    __half* row = cat + (size_t)r * 2 * Kp;
-    split_store(tile[threadIdx.x][i], s, row + k, row + Kp + k);
+    const float x0 = tile[2 * threadIdx.x][i] * s, x1 = tile[2 * threadIdx.x + 1][i] * s;
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    __half* row = cat + (size_t)r * 2 * Kp + k0 + 2 * threadIdx.x;
+    *reinterpret_cast<__half2*>(row) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(row + Kp) =
+        __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
     if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[r] = 1.f / s;
   }
 }
@@ -239,7 +256,7 @@ int convert_operand(const float* src, int ld, bool k_contig, int rows, int K, in
     const int k_chunk = 512;
     colmax_kernel<<<dim3(kg_div_up(rows, 32), kg_div_up(K, k_chunk)), dim3(32, 8), 0, st>>>(src, ld, K, rows, k_chunk, amax);
     KG_LAUNCH_OK();
-    split_transpose_kernel<<<dim3(Kp / 32, kg_div_up(rows, 32)), dim3(32, 8), 0, st>>>(src, ld, K, rows, Kp, amax, cat, inv_scale);
+    split_transpose_kernel<<<dim3(Kp / 64, kg_div_up(rows, 32)), dim3(32, 8), 0, st>>>(src, ld, K, rows, Kp, amax, cat, inv_scale);
     KG_LAUNCH_OK();
   }
   return KG_OK;
