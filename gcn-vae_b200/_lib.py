@@ -42,6 +42,7 @@ _SIGNATURES = {
     "kg_basis_dense_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _P, _P]),
     "kg_basis_dense_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "kg_act_dropout_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P]),
+    "kg_act_dropout_bwd_colsum": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "kg_colsum_workspace_bytes": (_Z, [_I, _I]),
     "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     "kg_gemm_f32_workspace_bytes": (_Z, [_I, _I, _I]),
@@ -89,7 +90,7 @@ def lib():
 
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
-    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2,
+    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 2,
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
 }
 launches = 0          # running count of kernels launched through this binding

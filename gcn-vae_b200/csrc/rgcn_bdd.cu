@@ -95,6 +95,71 @@ extern "C" int kg_act_dropout_bwd(const float* grad_out, const float* out, const
   return KG_OK;
 }
 
+// the same, plus the bias gradient in the same pass: colsum[c] += sum_r grad_pre[r, c]  (colsum zero-filled
+// here; a thread owns 4 consecutive columns, a warp 512 contiguous bytes of a row, a block 64 rows)
+__global__ void __launch_bounds__(256)
+act_dropout_bwd_colsum_kernel(const float* __restrict__ go, const float* __restrict__ out,
+                              const float* __restrict__ mask, int act, int rows, int cols,
+                              float* __restrict__ gp, float* __restrict__ colsum) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols)
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const size_t off = (size_t)r * cols + c;
+      float4 g = *reinterpret_cast<const float4*>(go + off);
+      if (mask) {
+        const float4 m = *reinterpret_cast<const float4*>(mask + off);
+        g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+      }
+      if (act == 1) {
+        const float4 o = *reinterpret_cast<const float4*>(out + off);
+        if (!(o.x > 0.f)) g.x = 0.f;
+        if (!(o.y > 0.f)) g.y = 0.f;
+        if (!(o.z > 0.f)) g.z = 0.f;
+        if (!(o.w > 0.f)) g.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(gp + off) = g;
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 t = red[w][lane];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(colsum + c, acc.x);
+    atomicAdd(colsum + c + 1, acc.y);
+    atomicAdd(colsum + c + 2, acc.z);
+    atomicAdd(colsum + c + 3, acc.w);
+  }
+}
+
+// grad_pre and the column sums of grad_pre (the bias gradient) in one pass; cols % 4 == 0 and 16-byte
+// aligned tensors take the fused kernel, anything else the two separate ones
+extern "C" int kg_act_dropout_bwd_colsum(const float* grad_out, const float* out, const float* drop_mask, int act,
+                                         int rows, int cols, float* grad_pre, float* colsum, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  KG_REQUIRE(rows >= 0 && cols > 0 && (act == 0 || act == 1), "act_dropout_bwd_colsum: bad arguments");
+  cudaStream_t st = kg_stream(stream);
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(out) |
+                         reinterpret_cast<uintptr_t>(drop_mask) | reinterpret_cast<uintptr_t>(grad_pre);
+  if (rows > 0 && cols % 4 == 0 && (bits & 15) == 0) {
+    KG_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, st));
+    act_dropout_bwd_colsum_kernel<<<dim3(kg_div_up(cols, 128), kg_div_up(rows, 64)), 256, 0, st>>>(
+        grad_out, out, drop_mask, act, rows, cols, grad_pre, colsum);
+    KG_LAUNCH_OK();
+    return KG_OK;
+  }
+  int rc = kg_act_dropout_bwd(grad_out, out, drop_mask, act, (long long)rows * cols, grad_pre, stream);
+  if (rc != KG_OK) return rc;
+  return kg_colsum(grad_pre, rows, cols, colsum, workspace, workspace_bytes, stream);
+}
+
 // ------------------------------------------------------------------------------------------
 // column sums, two deterministic stages
 // ------------------------------------------------------------------------------------------

@@ -163,6 +163,21 @@ def colsum(x):
     return out
 
 
+def act_dropout_bwd(g, out, mask, act, want_colsum=False):
+    """grad wrt the pre-activation of out = dropout(act(pre)); with ``want_colsum`` also its column sums
+    (the bias gradient) from the same pass."""
+    gpre = torch.empty_like(out)
+    if not want_colsum:
+        L.call("kg_act_dropout_bwd", L.f32(g), L.f32(out), L.f32(mask), act, out.numel(), L.f32(gpre), L.stream())
+        return gpre, None
+    rows, cols = out.shape
+    dbias = torch.empty(cols, dtype=torch.float32, device=out.device)
+    ws = L.workspace(L.lib().kg_colsum_workspace_bytes(rows, cols), out.device)
+    L.call("kg_act_dropout_bwd_colsum", L.f32(g), L.f32(out), L.f32(mask), act, rows, cols, L.f32(gpre), L.f32(dbias),
+           L.ptr(ws), ws.numel(), L.stream())
+    return gpre, dbias
+
+
 def _reduce(name, x):
     out = torch.empty((), dtype=torch.float32, device=x.device)
     ws = L.workspace(L.lib().kg_reduce_workspace_bytes(x.numel()), x.device)
@@ -272,9 +287,7 @@ class BddConvFn(torch.autograd.Function):
         gi, B, si, so, peer = ctx.gi, ctx.num_bases, ctx.si, ctx.so, ctx.peer
         g = _c(g)
         x_own = x if ctx.dst_lo < 0 else x[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
-        gpre = torch.empty_like(out)
-        L.call("kg_act_dropout_bwd", L.f32(g), L.f32(out), L.f32(mask), ctx.act, out.numel(),
-               L.f32(gpre), L.stream())
+        gpre, dbias_fused = act_dropout_bwd(g, out, mask, ctx.act, want_colsum=ctx.has_bias)
         dx = dw = dloop = dbias = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if peer is not None:       # source rows are still in the peers' blocks (published in forward)
@@ -307,7 +320,7 @@ class BddConvFn(torch.autograd.Function):
             dloop = torch.empty_like(loop_weight)
             gemm(x_own, gpre, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            dbias = colsum(gpre)
+            dbias = dbias_fused
         return dx, dw, dloop, dbias, None, None, None, None, None, None, None, None
 
 
@@ -395,10 +408,9 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
         g = _c(g)
-        if ctx.relu:
-            gp = torch.empty_like(g)
-            L.call("kg_act_dropout_bwd", L.f32(g), L.f32(y), None, 1, g.numel(), L.f32(gp), L.stream())
-            g = gp
+        db_fused = None
+        if ctx.relu:                 # ReLU backward and the bias gradient in one pass over g
+            g, db_fused = act_dropout_bwd(g, y, None, 1, want_colsum=ctx.has_bias and ctx.needs_input_grad[2])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -407,7 +419,7 @@ class LinearFn(torch.autograd.Function):
             dw = torch.empty_like(w)
             gemm(g, x, dw, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(g)
+            db = db_fused if db_fused is not None else colsum(g)
         return dx, dw, db, None
 
 

@@ -173,6 +173,12 @@ int kg_basis_dense_bwd(const float* x, const float* g, const void* rel_pack, int
  * act: 0 identity, 1 relu.  drop_mask: [n, dim] keep-mask already scaled by 1/(1-p), or NULL. */
 int kg_act_dropout_bwd(const float* grad_out, const float* out, const float* drop_mask, int act,
                        long long numel, float* grad_pre, void* stream);
+/* The same with the bias gradient fused in: colsum[c] = sum_r grad_pre[r, c] (the `h_bias` / MaskedLinear
+ * bias gradients autograd derives for kgvae/model.py:54-59 and kgvae/flow_network.py:15); workspace as for
+ * kg_colsum (used only on the unfused path: cols % 4 != 0 or unaligned tensors). */
+int kg_act_dropout_bwd_colsum(const float* grad_out, const float* out, const float* drop_mask, int act,
+                              int rows, int cols, float* grad_pre, float* colsum, void* workspace,
+                              size_t workspace_bytes, void* stream);
 /* column sums of a [rows, cols] matrix (h_bias / MaskedLinear bias gradients); deterministic.
  * workspace: kg_colsum_workspace_bytes(rows, cols) */
 size_t kg_colsum_workspace_bytes(int rows, int cols);

@@ -650,3 +650,19 @@ def test_bdd_layer_weight_gradient_only(B, si, so, tiled, monkeypatch):
     out.backward(gout.to(DEV))
     assert_close(out, want, RTOL, "bdd out")
     assert_close(cw.grad, weight.grad, RTOL, "bdd dW")
+
+
+@pytest.mark.parametrize("rows,cols,act,masked", [(1000, 500, 1, True), (77, 1000, 1, False), (300, 11, 1, True),
+                                                  (64, 8, 0, True), (1, 4, 1, False)])
+def test_act_dropout_bwd_with_fused_column_sums(rows, cols, act, masked):
+    """kg_act_dropout_bwd_colsum = kg_act_dropout_bwd followed by kg_colsum (fused when cols % 4 == 0)."""
+    g = torch.Generator().manual_seed(rows + cols)
+    go = torch.randn(rows, cols, generator=g)
+    out = torch.relu(torch.randn(rows, cols, generator=g))
+    mask = (torch.rand(rows, cols, generator=g) < 0.8).float() / 0.8 if masked else None
+    want = go * (mask if masked else 1.0)
+    if act == 1:
+        want = want * (out > 0).float()
+    gp, db = ops.act_dropout_bwd(go.to(DEV), out.to(DEV), None if mask is None else mask.to(DEV), act, want_colsum=True)
+    assert torch.equal(gp.cpu(), want)
+    assert_close(db, want.double().sum(0).float(), 1e-5, "fused column sums")
