@@ -116,7 +116,7 @@ constexpr int kHeavy = 512;
 // forward: thread (n, o) keeps the column V[0..NB, n, o] in registers; per out-edge NB FMAs against
 // the relation's coefficient row (shared memory) and one atomic add into out[dst, o]
 template <int NBR>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 2)
 basis_id_src_fwd_kernel(const float* __restrict__ V, const float* __restrict__ coef, const int* __restrict__ col_ptr,
                         const int4* __restrict__ pack, int n_src, int R, int NB, int out_f, int NT,
                         float* __restrict__ out) {
@@ -566,9 +566,9 @@ extern "C" int kg_basis_id_src_fwd(const float* V, const float* coef, const int3
   const SrcPlan pl = src_plan(num_rels, num_bases, out_feat);
   KG_REQUIRE(pl.nt > 0, "basis id src fwd: shape not covered (num_bases <= 64, out_feat <= 16)");
   if (n_src == 0) return KG_OK;
-  // forward tile: as many nodes as give <= 512 (node, column) threads
-  int nt = 512 / out_feat;
-  if (nt > 48) nt = 48;
+  // forward tile: as many nodes as give <= 256 (node, column) threads (two CTAs share an SM)
+  int nt = 256 / out_feat;
+  if (nt > 32) nt = 32;
   const int threads = (nt * out_feat + 31) / 32 * 32;
   const int tiles = kg_div_up(n_src, nt);
   const int grid = tiles < 8 * kg_sm_count() ? tiles : 8 * kg_sm_count();
