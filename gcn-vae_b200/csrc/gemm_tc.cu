@@ -15,9 +15,11 @@ using namespace splitpipe;
 
 namespace {
 
-constexpr int EPI_PITCH = 36;                                   // padded row of a 32 x 32 transpose block (16-byte aligned)
+constexpr int EPI_WARPS = 8;                                    // two per 32-row quadrant: columns [0,128) and [128,256)
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_PITCH = 20;                                   // padded row of a 32 x 16 transpose block (16-byte aligned)
 constexpr int EPI_T = 32 * EPI_PITCH;
-constexpr int SMEM_BYTES = PIPE_SMEM + 1024 + 2 * 2 * BN * 4 + 4 * EPI_T * 4;   // + [2][BN] inv_sb, [2][BN] spare, 4 transpose blocks
+constexpr int SMEM_BYTES = PIPE_SMEM + 1024 + 2 * 2 * BN * 4 + EPI_WARPS * EPI_T * 4;   // + [2][BN] inv_sb, [2][BN] spare, transpose blocks
 
 // ------------------------------------------------------------------------------------------
 // operand conversion
@@ -125,21 +127,22 @@ __device__ __forceinline__ float finish(float v, const GemmArgs& g, int n, size_
   return v;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b);
+  const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b, EPI_WARPS);
   float* sb_s = reinterpret_cast<float*>(P.scratch);      // [2][BN] column scales
-  float* epi_t = sb_s + 2 * 2 * BN;                       // [4][32 x 36] epilogue transpose blocks
+  float* epi_t = sb_s + 2 * 2 * BN;                       // [8][32 x 20] epilogue transpose blocks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = g.tmap.total();
 
   if (warp == 0) {
-    pipe_producer(P, &tm_a, &tm_b, g.tmap, g.Kp);
+    pipe_producer_wide(P, &tm_a, &tm_b, g.tmap, g.Kp);
   } else if (warp == 1) {
-    pipe_mma(P, g.tmap);
+    pipe_mma_wide(P, g.tmap);
   } else {
-    const int quad = warp & 3, etid = threadIdx.x - 64;
+    // TMEM lanes are reachable by warp id % 4: warps 2..5 take columns [0, 128) of their quadrant, 6..9 [128, 256)
+    const int quad = warp & 3, etid = threadIdx.x - 64, half = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       int m0, n0, split, ks0, nks;
@@ -147,10 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int buf = it & 1;
       float* sb = sb_s + buf * BN;
       sb[etid] = __ldg(g.inv_sb + n0 + etid);
-      sb[etid + 128] = __ldg(g.inv_sb + n0 + etid + 128);
       const int m = m0 + quad * 32 + lane;
       const float sa = m < g.M ? __ldg(g.inv_sa + m) : 0.f;
-      epi_barrier();
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps: column scales staged
       const uint32_t taddr = epi_acquire(P, it);
       float* out = g.partial ? g.partial + ((size_t)split * g.M + m) * g.N : g.C + (size_t)m * g.ldc;
       const int ld_out = g.partial ? g.N : g.ldc;
@@ -159,49 +161,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                        (!g.addend || (reinterpret_cast<uintptr_t>(g.addend) & 15) == 0) &&
                        (!g.mask || (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0) &&
                        (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
-      float* T = epi_t + quad * EPI_T;
+      float* T = epi_t + (warp - 2) * EPI_T;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c * 32, v);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
         if (vec && nb < g.N) {
           // The accumulator arrives one ROW per lane.  Written out that way a warp store is 32 strided
-          // 16-byte pieces; instead the warp parks the 32 x 32 block in shared memory and walks it with
-          // 8 lanes per row (4 columns each): every access to C / addend / mask is four whole 128-byte lines.
+          // 16-byte pieces; instead the warp parks 32 x 16 blocks in shared memory and walks them with
+          // 4 lanes per row (4 columns each): C / addend / mask are touched in whole 64-byte runs.
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
-            *reinterpret_cast<float4*>(T + lane * EPI_PITCH + j) =
-                make_float4(__uint_as_float(v[j]) * sa * s4.x, __uint_as_float(v[j + 1]) * sa * s4.y,
-                            __uint_as_float(v[j + 2]) * sa * s4.z, __uint_as_float(v[j + 3]) * sa * s4.w);
-          }
-          __syncwarp();
-          const int n = nb + 4 * (lane & 7);
-          if (n < g.N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g.bias && !g.partial) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+          for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rl = 4 * i + (lane >> 3), mm = m0 + quad * 32 + rl;
-              if (mm < g.M) {
-                float4 r = *reinterpret_cast<const float4*>(T + rl * EPI_PITCH + 4 * (lane & 7));
-                if (g.partial) {
-                  *reinterpret_cast<float4*>(g.partial + ((size_t)split * g.M + mm) * g.N + n) = r;
-                } else {
-                  const size_t off = (size_t)mm * g.ldc + n;
-                  r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
-                  if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
-                  if (g.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                  if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r.x *= k.x; r.y *= k.y; r.z *= k.z; r.w *= k.w; }
-                  if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-                  *reinterpret_cast<float4*>(g.C + off) = r;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + 16 * hh + j);
+              *reinterpret_cast<float4*>(T + lane * EPI_PITCH + j) = make_float4(
+                  __uint_as_float(v[16 * hh + j]) * sa * s4.x, __uint_as_float(v[16 * hh + j + 1]) * sa * s4.y,
+                  __uint_as_float(v[16 * hh + j + 2]) * sa * s4.z, __uint_as_float(v[16 * hh + j + 3]) * sa * s4.w);
+            }
+            __syncwarp();
+            const int n = nb + 16 * hh + 4 * (lane & 3);
+            if (n < g.N) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g.bias && !g.partial) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rl = 8 * i + (lane >> 2), mm = m0 + quad * 32 + rl;
+                if (mm < g.M) {
+                  float4 r = *reinterpret_cast<const float4*>(T + rl * EPI_PITCH + 4 * (lane & 3));
+                  if (g.partial) {
+                    *reinterpret_cast<float4*>(g.partial + ((size_t)split * g.M + mm) * g.N + n) = r;
+                  } else {
+                    const size_t off = (size_t)mm * g.ldc + n;
+                    r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+                    if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
+                    if (g.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                    if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r.x *= k.x; r.y *= k.y; r.z *= k.z; r.w *= k.w; }
+                    if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                    *reinterpret_cast<float4*>(g.C + off) = r;
+                  }
                 }
               }
             }
+            __syncwarp();                                   // the block is consumed before the next one is parked
           }
-          __syncwarp();                                     // the block is consumed before the next one is parked
         } else if (m < g.M && nb < g.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -357,7 +362,7 @@ int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb
   g.Kp = L.Kp;
   const int total = g.tmap.total();
   const int grid = total < kg_sm_count() ? total : kg_sm_count();
-  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, g);
+  gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, g);
   KG_LAUNCH_OK();
   if (partial) {
     const long long n = (long long)M * N;

@@ -51,7 +51,8 @@ struct Pipe {
 };
 
 // all 192 threads; returns after TMEM is allocated and barriers are initialised
-__device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap* tm_a, const CUtensorMap* tm_b) {
+__device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
+                                           int epi_warps = 4) {
   Pipe P;
   P.smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(P.smem + STAGES * STAGE_BYTES);
@@ -73,7 +74,7 @@ __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap*
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(P.tfull + i, 1);
-      mbar_init(P.tempty + i, 4);     // one arrival per epilogue warp
+      mbar_init(P.tempty + i, epi_warps);     // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -135,6 +136,75 @@ __device__ __forceinline__ void pipe_mma(const Pipe& P, const TileMap& tmap) {
         mma_f16_ss(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
       mma_commit(P.empty + stage);        // frees the smem stage once these MMAs have read it
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    mma_commit(P.tfull + buf);            // accumulator complete
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// "Wide" variant of the producer / MMA pair (dense GEMM): one 96 KB stage per k-step holds
+// A_hi | A_lo | B_hi | B_lo, so every operand tile crosses L2 -> shared memory ONCE per k-step and
+// the three products  lo*hi + hi*lo + hi*hi  are issued from it (12 MMAs per stage).  The term-major
+// pair above streams 6 tiles per k-step; at K = 500 that traffic, not the tensor pipe, bounded the
+// GEMM.  Two stages fit the same shared memory as the four 48 KB ones (barriers full[0..1],
+// empty[0..1] of the same Pipe).
+// ------------------------------------------------------------------------------------------
+constexpr int WIDE_STAGES = 2;
+constexpr int WIDE_STAGE_BYTES = 2 * STAGE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+static_assert(WIDE_STAGES * WIDE_STAGE_BYTES <= STAGES * STAGE_BYTES, "wide stages must fit the pipe's shared memory");
+
+// warp 0
+__device__ __forceinline__ void pipe_producer_wide(const Pipe& P, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
+                                                   const TileMap& tmap, int Kp) {
+  if (!elect_one()) return;
+  int stage = 0;
+  uint32_t phase = 0;
+  const int total = tmap.total();
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    int m0, n0, split, ks0, nks;
+    tmap.decode(tile, m0, n0, split, ks0, nks);
+    for (int ks = ks0; ks < ks0 + nks; ++ks) {
+      mbar_wait(P.empty + stage, phase ^ 1);
+      uint8_t* st = P.smem + stage * WIDE_STAGE_BYTES;
+      mbar_arrive_expect_tx(P.full + stage, WIDE_STAGE_BYTES);
+      tma_load_2d(st, tm_a, P.full + stage, ks * BK, m0);                              // A_hi
+      tma_load_2d(st + A_BYTES, tm_a, P.full + stage, Kp + ks * BK, m0);               // A_lo
+      tma_load_2d(st + 2 * A_BYTES, tm_b, P.full + stage, ks * BK, n0);                // B_hi
+      tma_load_2d(st + 2 * A_BYTES + B_BYTES, tm_b, P.full + stage, Kp + ks * BK, n0); // B_lo
+      if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
+// warp 1
+__device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap) {
+  if (!elect_one()) return;
+  constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  const int total = tmap.total();
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    int m0, n0, split, ks0, nks;
+    tmap.decode(tile, m0, n0, split, ks0, nks);
+    const int buf = it & 1;
+    mbar_wait(P.tempty + buf, ((it >> 1) & 1) ^ 1);
+    fence_after_thread_sync();
+    const uint32_t tacc = P.tmem_base + buf * BN;
+    for (int ks = 0; ks < nks; ++ks) {
+      mbar_wait(P.full + stage, phase);
+      fence_after_thread_sync();
+      const uint32_t sa = smem_u32(P.smem + stage * WIDE_STAGE_BYTES);
+      const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + A_BYTES);
+      const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * A_BYTES), b_lo = smem_desc_k_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);   // small terms first
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
+      mma_commit(P.empty + stage);        // frees the stage once these MMAs have read it
+      if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
     }
     mma_commit(P.tfull + buf);            // accumulator complete
   }
