@@ -153,6 +153,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int m = m0 + quad * 32 + lane;
       const float sa = m < g.M ? __ldg(g.inv_sa + m) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps: column scales staged
+      // while the accumulator is still being produced: pull this warp's lines of addend / mask / C towards L2
+      if (!g.partial && m < g.M && (g.addend || g.mask || g.accumulate)) {
+        const size_t off0 = (size_t)m * g.ldc + n0 + half * (BN / 2);
+#pragma unroll
+        for (int q = 0; q < BN / 2; q += 32) {
+          if (n0 + half * (BN / 2) + q < g.N) {
+            if (g.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.addend + off0 + q));
+            if (g.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.mask + off0 + q));
+            if (g.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.C + off0 + q));
+          }
+        }
+      }
       const uint32_t taddr = epi_acquire(P, it);
       float* out = g.partial ? g.partial + ((size_t)split * g.M + m) * g.N : g.C + (size_t)m * g.ldc;
       const int ld_out = g.partial ? g.N : g.ldc;
