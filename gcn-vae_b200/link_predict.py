@@ -151,16 +151,24 @@ def main(args):
         model.load_state_dict(checkpoint["state_dict"])
         epoch = checkpoint["epoch"]
 
+    train_dev = None
     while True:
         model.train()
         epoch += 1
-        g, node_id, edge_type, node_norm, batch, labels = utils.generate_sampled_graph_and_labels(
-            train_data, args.graph_batch_size, args.graph_split_size, num_rels, adj_list, degrees,
-            args.negative_sample, args.edge_sampler)
-        node_id = torch.from_numpy(node_id).view(-1, 1).long().to(device)
-        edge_type = torch.from_numpy(edge_type).to(device)
-        edge_norm = node_norm_to_edge_norm(g, torch.from_numpy(node_norm).view(-1, 1)).to(device)
-        batch, labels = torch.from_numpy(batch).to(device), torch.from_numpy(labels).to(device)
+        if getattr(args, "device_sampler", False) and args.edge_sampler == "uniform":
+            # opt-in: the same sampling procedure drawn on the GPU (not numpy's random stream)
+            if train_dev is None:
+                train_dev = torch.from_numpy(np.asarray(train_data)).to(device)
+            g, node_id, edge_type, edge_norm, batch, labels = utils.generate_sampled_graph_and_labels_device(
+                train_dev, args.graph_batch_size, args.graph_split_size, num_rels, args.negative_sample)
+        else:
+            g, node_id, edge_type, node_norm, batch, labels = utils.generate_sampled_graph_and_labels(
+                train_data, args.graph_batch_size, args.graph_split_size, num_rels, adj_list, degrees,
+                args.negative_sample, args.edge_sampler)
+            node_id = torch.from_numpy(node_id).view(-1, 1).long().to(device)
+            edge_type = torch.from_numpy(edge_type).to(device)
+            edge_norm = node_norm_to_edge_norm(g, torch.from_numpy(node_norm).view(-1, 1)).to(device)
+            batch, labels = torch.from_numpy(batch).to(device), torch.from_numpy(labels).to(device)
 
         torch.cuda.synchronize()
         t0 = time.time()
@@ -230,6 +238,9 @@ def build_parser():
     p.add_argument("--model-class", type=str, default="KGVAE")
     p.add_argument("--load", type=bool, default=False)
     p.add_argument("--generate", type=bool, default=False)
+    p.add_argument("--device-sampler", action="store_true",
+                   help="(new) draw the uniform edge sample, the negatives and the graph split on the GPU; same "
+                        "procedure as the reference's host sampler, not its numpy random stream")
     return p
 
 

@@ -132,6 +132,52 @@ def generate_sampled_graph_and_labels(triplets, sample_size, split_size, num_rel
     return g, uniq_v, rel, norm, samples, labels
 
 
+def generate_sampled_graph_and_labels_device(triplets, sample_size, split_size, num_rels, negative_rate,
+                                             generator=None):
+    """Opt-in DEVICE form of ``generate_sampled_graph_and_labels`` with the uniform edge sampler
+    (kgvae/utils.py:79-124,158-171): ``sample_size`` training triples without replacement, nodes
+    relabelled to 0..n-1 in ascending id order, ``negative_rate`` corruptions per positive (subject
+    where u > 0.5, else object, replacement drawn among the n sampled nodes), ``split_size`` of the
+    sampled edges kept as graph structure, bidirectional graph with 1 / in-degree norms.
+
+    Everything stays on the GPU (torch's device generator + ``kg_graph_build``), so the step needs
+    neither the host sampler nor the ~50 MB of host -> device copies.  The draws follow the same
+    procedure but NOT numpy's random stream: use the host function when sampled indices must match
+    the reference bit for bit.  ``triplets``: int tensor [T, 3] on the device.
+
+    Returns (g, node_id [n, 1] int64, edge_type int32 [E], edge_norm f32 [E, 1], samples int32
+    [S, 3], labels f32 [S]) - the arguments of ``model(g, node_id, edge_type, edge_norm)`` and
+    ``model.get_loss(g, embed, samples, labels)``."""
+    if not triplets.is_cuda:
+        raise RuntimeError("generate_sampled_graph_and_labels_device needs the triples on a CUDA device")
+    dev = triplets.device
+    B, rate = int(sample_size), int(negative_rate)
+    picked = torch.randperm(triplets.shape[0], device=dev, generator=generator)[:B]
+    tri = triplets[picked].long()
+    uniq_v, inv = torch.unique(torch.cat([tri[:, 0], tri[:, 2]]), return_inverse=True)
+    n = int(uniq_v.numel())
+    src, rel, dst = inv[:B], tri[:, 1], inv[B:]
+    pos = torch.stack([src, rel, dst], dim=1)
+    neg = pos.repeat(rate, 1)
+    values = torch.randint(n, (B * rate,), device=dev, generator=generator)
+    head = torch.rand(B * rate, device=dev, generator=generator) > 0.5
+    neg[:, 0] = torch.where(head, values, neg[:, 0])
+    neg[:, 2] = torch.where(head, neg[:, 2], values)
+    samples = torch.cat([pos, neg]).to(torch.int32).contiguous()
+    labels = torch.zeros(B * (rate + 1), dtype=torch.float32, device=dev)
+    labels[:B] = 1
+    keep = torch.randperm(B, device=dev, generator=generator)[:int(B * split_size)]
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    gi = ops.graph_build(i32(src[keep]), i32(rel[keep]), i32(dst[keep]), n, int(num_rels))
+    g = Graph()
+    g._n = n
+    g._dev_edges[dev] = (gi.e_src, gi.e_dst)
+    edge_type = gi.e_type
+    edge_norm = gi.node_norm[gi.e_dst.long()].view(-1, 1).contiguous()
+    g.adopt_index(gi, edge_type, edge_norm, 2 * int(num_rels))
+    return g, uniq_v.view(-1, 1), edge_type, edge_norm, samples, labels
+
+
 # --------------------------------------------------------------------------------------------
 # evaluation (kgvae/utils.py:180-221,293-314)
 # --------------------------------------------------------------------------------------------

@@ -666,3 +666,49 @@ def test_act_dropout_bwd_with_fused_column_sums(rows, cols, act, masked):
     gp, db = ops.act_dropout_bwd(go.to(DEV), out.to(DEV), None if mask is None else mask.to(DEV), act, want_colsum=True)
     assert torch.equal(gp.cpu(), want)
     assert_close(db, want.double().sum(0).float(), 1e-5, "fused column sums")
+
+
+# ------------------------------------------------------------------------------ device sampler
+def test_device_sampler_structure_and_train_step():
+    """utils.generate_sampled_graph_and_labels_device follows the reference's sampling procedure
+    (kgvae/utils.py:85-124,158-171) on the GPU: checked structurally (it does not reproduce numpy's
+    random stream - the host sampler does), then one training step runs on its outputs."""
+    n_ent, n_rel, B, rate = 500, 12, 600, 4
+    data = K.datasets.synthetic_kg("toy", seed=1)
+    tri = torch.from_numpy(data.train).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    g, node_id, etype, enorm, samples, labels = K.utils.generate_sampled_graph_and_labels_device(
+        tri, B, 0.5, n_rel, rate, generator=gen)
+    n, E = node_id.shape[0], etype.numel()
+    nid = node_id.view(-1).cpu()
+    assert torch.equal(nid, torch.unique(nid)) and len(g) == n          # ascending, duplicate-free relabelling
+    pos = samples[:B].cpu().long()
+    orig = torch.stack([nid[pos[:, 0]], pos[:, 1], nid[pos[:, 2]]], 1)    # back to entity ids
+    train_set = {tuple(r) for r in data.train.tolist()}
+    assert all(tuple(r) in train_set for r in orig.tolist())
+    assert len({tuple(r) for r in orig.tolist()}) >= B - 5               # without replacement (toy data has few duplicates)
+    assert labels.shape[0] == B * (rate + 1) and float(labels[:B].min()) == 1.0 and float(labels[B:].max()) == 0.0
+    neg = samples[B:].cpu().long().view(rate, B, 3)
+    same_s, same_o = neg[:, :, 0] == pos[:, 0], neg[:, :, 2] == pos[:, 2]
+    assert bool((neg[:, :, 1] == pos[:, 1]).all()) and bool((same_s | same_o).all())      # exactly one end is redrawn
+    assert 0.3 < float((~same_s).float().mean()) < 0.7                   # subject / object about evenly
+    assert int(samples[:, [0, 2]].max()) < n and int(samples[:, [0, 2]].min()) >= 0
+    # graph: B/2 kept edges + their reverses, (dst, src, rel) order, 1 / in-degree norms
+    assert E == 2 * int(B * 0.5)
+    src, dst = (t.cpu().long() for t in g._dev_edges[torch.device(DEV)])
+    et = etype.cpu().long()
+    key = (dst * n + src) * (2 * n_rel) + et
+    assert bool((key[1:] >= key[:-1]).all())
+    half = {(int(s), int(r), int(d)) for s, r, d in zip(src, et, dst) if r < n_rel}
+    assert half <= {tuple(r) for r in pos.tolist()}
+    assert {(d, r + n_rel, s) for s, r, d in half} == {(int(s), int(r), int(d)) for s, r, d in zip(src, et, dst) if r >= n_rel}
+    deg = torch.bincount(dst, minlength=n).float()
+    assert_close(enorm.view(-1), (1.0 / deg)[dst], 1e-6, "edge norm")
+    # one training step on the sampled batch
+    torch.manual_seed(0)
+    model = K.LinkPredict(K.KGVAE, n_ent, 40, n_rel, num_bases=8, dropout=0.2, use_cuda=True, reg_param=0.01,
+                          kl_param=1e-3, k=4, n_flows=1).to(DEV)
+    embed = model(g, node_id, etype, enorm)
+    loss, _, _, _ = model.get_loss(g, embed, samples, labels)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(model.w_relation.grad).all()
