@@ -764,6 +764,12 @@ def run_gpu(args):
                     "ms_per_launch": per_launch_ms, "algorithmic_bytes": ab,
                     "share_of_step": ms / total_ops,
                     "regime": "L2-resident gathers (z, h are 29 MB): algorithmic GB/s can exceed HBM peak"}
+            if tag == "kg_distmult_bce_fwd":
+                # what actually bounds this launch: per scored triplet one streamed 2 KB row of z read from L2
+                # and one 2 KB row reduced into dz in L2 (the (r, a) rows stay in registers over a run)
+                l2_bytes = S * 2 * 4 * H
+                roof["l2_traffic_bytes"] = l2_bytes
+                roof["l2_gbs"] = l2_bytes / (per_launch_ms * 1e-3) / 1e9
             break
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if roof and os.path.exists(traffic_file):
