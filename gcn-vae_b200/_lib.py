@@ -90,7 +90,9 @@ def lib():
 
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
-    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 2,
+    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 1,
+    "kg_gemm_f32": 4,        # operand conversions (1-2 kernels each) + the product (+ split-K finish): a lower bound
+   
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
 }
 launches = 0          # running count of kernels launched through this binding
