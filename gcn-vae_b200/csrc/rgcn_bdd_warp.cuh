@@ -55,11 +55,10 @@ __device__ __forceinline__ void park_raw(float* mine, const float (&v)[N]) {
 template <int FI, int FO, int TB, int WPS>
 struct FwdLayout {
   static constexpr int XN = TB * FI, CN = TB * FO;
-  int lpw, stage_f, warp_f;
+  int lpw, stage_f;
   __host__ __device__ FwdLayout(int B) {
     lpw = lanes_per_warp(B / TB, WPS, CN);
     stage_f = round4(lpw * XN) + 4;
-    warp_f = 0;
   }
   __host__ __device__ int per_warp(int depth) const { return depth * stage_f + 2 * 32 * CN; }
   __host__ size_t smem(int depth) const {
