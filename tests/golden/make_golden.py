@@ -221,6 +221,50 @@ def made_case():
     print(f"made_block -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def entity_case():
+    """Entity classification (config 4, row a4): the reference's ``EntityClassify`` (kgvae/entity_classify.py
+    :23-43, imported verbatim) - basis RelGraphConv on integer node ids, one hidden layer, softmax output -
+    one full-graph training step as in its main() (:106-113): logits, cross-entropy on the training
+    nodes, every gradient."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        import entity_classify as ref_ec       # reference, verbatim
+        from dgl import DGLGraph
+    rng = np.random.default_rng(21)
+    torch.manual_seed(21)
+    n, R, E, h, C, bases = 120, 9, 900, 10, 4, 4
+    src = rng.integers(0, n, E)
+    dst = rng.integers(0, n - 2, E)                      # the last nodes stay without in-edges
+    et = rng.integers(0, R, E)
+    key = dst.astype(np.int64) * R + et                  # the loader's norm: 1 / same-type edges into dst
+    _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    norm = (1.0 / cnt[inv]).astype(np.float32)
+    labels = rng.integers(0, C, n)
+    train_idx = rng.permutation(n)[:40]
+    g = DGLGraph()
+    g.add_nodes(n)
+    g.add_edges(src, dst)
+    model = ref_ec.EntityClassify(len(g), h, C, R, num_bases=bases, num_hidden_layers=1, dropout=0,
+                                  use_self_loop=True, use_cuda=False)
+    with torch.no_grad():
+        for layer in model.layers:
+            layer.h_bias.normal_(0, 0.1)
+    feats = torch.arange(n)
+    logits = model(g, feats, torch.from_numpy(et), torch.from_numpy(norm).unsqueeze(1))
+    import torch.nn.functional as F
+    loss = F.cross_entropy(logits[train_idx], torch.from_numpy(labels).view(-1)[train_idx])
+    loss.backward()
+    out = {"cfg": np.array([n, R, E, h, C, bases], dtype=np.int64), "src": src, "dst": dst, "etype": et,
+           "norm": norm, "labels": labels, "train_idx": train_idx, "logits": logits.detach().numpy(),
+           "loss": loss.detach().numpy()}
+    for key_, val in model.state_dict().items():
+        out["param/" + key_] = val.detach().numpy()
+    for key_, val in model.named_parameters():
+        out["grad/" + key_] = val.grad.detach().numpy()
+    path = os.path.join(HERE, "entity_classify_toy.npz")
+    np.savez_compressed(path, **out)
+    print(f"entity_classify_toy: loss={float(loss):.6f} layers={len(model.layers)} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     kgvae_case("kgvae_tiny_noflow", n_ent=150, n_rel=5, h=20, bases=4, k=3, n_flows=0,
                n_train=600, batch=240, neg=3, kl_param=1e-2, dropout=0.2, seed=1)
@@ -231,3 +275,4 @@ if __name__ == "__main__":
     sampling_case()
     rank_case()
     made_case()
+    entity_case()

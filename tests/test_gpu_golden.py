@@ -146,3 +146,28 @@ def test_fb15k_step_shape_against_oracle():
     for name, p in model.named_parameters():
         if p.grad is not None and params[name].grad is not None:
             assert_close(p.grad, params[name].grad, RTOL, f"grad {name}")
+
+
+def test_entity_classify_against_reference_golden(golden):
+    """Row a4 end to end on the GPU: EntityClassify (basis RelGraphConv on integer ids -> dense hidden layer ->
+    softmax output) with the reference's parameters reproduces the reference's logits, loss and gradients
+    (tests/golden/entity_classify_toy.npz, produced by kgvae/entity_classify.py imported verbatim)."""
+    from gcn_vae_b200 import entity_classify as EC
+    gv = golden("entity_classify_toy")
+    n, R, E, h, C, bases = (int(v) for v in gv["cfg"])
+    g = K.Graph()
+    g.add_nodes(n)
+    g.add_edges(gv["src"], gv["dst"])
+    model = EC.EntityClassify(len(g), h, C, R, num_bases=bases, num_hidden_layers=1, dropout=0.0,
+                              use_self_loop=True, use_cuda=True)
+    model.load_state_dict({key[len("param/"):]: torch.from_numpy(val) for key, val in gv.items() if key.startswith("param/")})
+    model = model.to(DEV)
+    feats = model.create_features()
+    logits = model(g, feats, torch.from_numpy(gv["etype"]).to(DEV), torch.from_numpy(gv["norm"]).unsqueeze(1).to(DEV))
+    assert_close(logits, gv["logits"], RTOL, "logits")
+    idx = torch.from_numpy(gv["train_idx"]).to(DEV)
+    loss = torch.nn.functional.cross_entropy(logits[idx], torch.from_numpy(gv["labels"]).to(DEV)[idx])
+    assert_close(loss, gv["loss"], RTOL, "loss")
+    loss.backward()
+    for name, p in model.named_parameters():
+        assert_close(p.grad, gv["grad/" + name], RTOL, f"grad {name}")

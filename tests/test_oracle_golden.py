@@ -170,3 +170,25 @@ def test_made_is_autoregressive():
         conn = m @ conn
     conn = masks[-1][:D] @ conn
     assert float(torch.triu(conn, diagonal=0).abs().sum()) == 0.0   # out_j sees only in_{<j}
+
+
+def test_entity_classify_against_reference(golden):
+    """Row a4: the oracle's basis layers reproduce the reference's EntityClassify (entity_classify.py:23-43,
+    imported verbatim by make_golden.py): logits, cross-entropy on the training nodes, every gradient."""
+    gv = golden("entity_classify_toy")
+    n, R, E, h, C, bases = (int(v) for v in gv["cfg"])
+    graph = {"num_nodes": n, "src": gv["src"], "dst": gv["dst"], "etype": gv["etype"],
+             "edge_norm": gv["norm"].reshape(-1, 1)}
+    p = {k[len("param/"):]: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in gv.items() if k.startswith("param/")}
+    acts = [torch.relu, torch.relu, lambda t: torch.softmax(t, dim=1)]
+    x = torch.arange(n)
+    for i, act in enumerate(acts):
+        x = O.rgcn_basis_layer(x, graph, p[f"layers.{i}.weight"], p[f"layers.{i}.w_comp"], p[f"layers.{i}.h_bias"],
+                               p[f"layers.{i}.loop_weight"], act)
+    assert_close(x, gv["logits"], 2e-6, "logits")
+    idx = torch.from_numpy(gv["train_idx"])
+    loss = torch.nn.functional.cross_entropy(x[idx], torch.from_numpy(gv["labels"])[idx])
+    assert_close(loss, gv["loss"], 2e-6, "loss")
+    loss.backward()
+    for name, t in p.items():
+        assert_close(t.grad, gv["grad/" + name], 2e-5, f"grad {name}")
