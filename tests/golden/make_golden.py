@@ -265,6 +265,27 @@ def entity_case():
     print(f"entity_classify_toy: loss={float(loss):.6f} layers={len(model.layers)} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def neighbor_sampler_case():
+    """The reference's neighbourhood edge sampler (kgvae/utils.py:33-76) on a seeded graph: its picks are a
+    function of the legacy global numpy stream only, so they must be reproduced integer for integer."""
+    rng = np.random.default_rng(31)
+    n_ent, n_rel, n_train, sample = 300, 7, 2000, 250
+    train = synthetic_triples(rng, n_ent, n_rel, n_train)
+    adj_list, degrees = ref_utils.get_adj_and_degrees(n_ent, train)
+    np.random.seed(5)
+    edges = ref_utils.sample_edge_neighborhood(adj_list, degrees, n_train, sample)
+    np.random.seed(6)
+    g, node_id, edge_type, node_norm, data, labels = ref_utils.generate_sampled_graph_and_labels(
+        train, sample, 0.5, n_rel, adj_list, degrees, 3, "neighbor")
+    out = {"cfg": np.array([n_ent, n_rel, n_train, sample], dtype=np.int64), "train_triples": train,
+           "edges": np.asarray(edges, dtype=np.int64), "node_id": node_id.astype(np.int64),
+           "edge_type": edge_type.astype(np.int64), "samples": data.astype(np.int64),
+           "g_src": g._src.numpy().astype(np.int64), "g_dst": g._dst.numpy().astype(np.int64)}
+    path = os.path.join(HERE, "neighbor_sampler_seed5.npz")
+    np.savez_compressed(path, **out)
+    print(f"neighbor_sampler_seed5: picked={len(edges)} nodes={len(node_id)} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     kgvae_case("kgvae_tiny_noflow", n_ent=150, n_rel=5, h=20, bases=4, k=3, n_flows=0,
                n_train=600, batch=240, neg=3, kl_param=1e-2, dropout=0.2, seed=1)
@@ -276,3 +297,4 @@ if __name__ == "__main__":
     rank_case()
     made_case()
     entity_case()
+    neighbor_sampler_case()

@@ -130,3 +130,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_neighbor_sampler_matches_reference_golden(golden):
+    """utils.sample_edge_neighborhood and the "neighbor" mode of generate_sampled_graph_and_labels reproduce
+    the reference's picks integer for integer (kgvae/utils.py:33-124 on the legacy global numpy stream;
+    fixture produced by the unmodified reference)."""
+    gv = golden("neighbor_sampler_seed5")
+    n_ent, n_rel, n_train, sample = (int(v) for v in gv["cfg"])
+    train = gv["train_triples"]
+    adj, deg = K.utils.get_adj_and_degrees(n_ent, train)
+    np.random.seed(5)
+    edges = K.utils.sample_edge_neighborhood(adj, deg, n_train, sample)
+    assert np.array_equal(np.asarray(edges, dtype=np.int64), gv["edges"])
+    np.random.seed(6)
+    g, node_id, edge_type, node_norm, data, labels = K.utils.generate_sampled_graph_and_labels(
+        train, sample, 0.5, n_rel, adj, deg, 3, "neighbor")
+    assert np.array_equal(node_id, gv["node_id"]) and np.array_equal(edge_type, gv["edge_type"])
+    assert np.array_equal(data, gv["samples"])
+    assert np.array_equal(g._src, gv["g_src"]) and np.array_equal(g._dst, gv["g_dst"])
