@@ -286,6 +286,35 @@ def neighbor_sampler_case():
     print(f"neighbor_sampler_seed5: picked={len(edges)} nodes={len(node_id)} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def mmd_case():
+    """The MMD term (row a8; on in the README run, --mmd-param=1): KGVAE.get_mmd (kgvae/model.py:89-102) with
+    python's ``random`` seeded and the prior noise preset - 200 prior samples pushed through the flow against
+    200 posterior rows; value and gradients wrt z, the prior parameters and the flow."""
+    import random
+    torch.manual_seed(17)
+    n_ent, n_rel, h, bases, k, n_flows, N = 260, 6, 20, 4, 10, 1, 260
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref_lp.LinkPredict(ref_model.KGVAE, n_ent, h, n_rel, num_bases=bases, num_hidden_layers=2,
+                                   dropout=0.0, use_cuda=False, reg_param=0.01, kl_param=1e-3, mmd_param=1.0,
+                                   k=k, n_flows=n_flows)
+    z = torch.randn(N, h, requires_grad=True)
+    eps = torch.randn(200, h)
+    random.seed(9)
+    with preset_randn(eps):
+        mmd = model.encoder.get_mmd(z)
+    mmd.backward()
+    out = {"cfg": np.array([n_ent, n_rel, h, bases, k, n_flows, N], dtype=np.int64), "z": z.detach().numpy(),
+           "eps": eps.numpy(), "mmd": mmd.detach().numpy(), "grad_z": z.grad.numpy()}
+    for key, val in model.state_dict().items():
+        out["param/" + key] = val.detach().numpy()
+    for key, val in model.named_parameters():
+        if val.grad is not None:
+            out["grad/" + key] = val.grad.detach().numpy()
+    path = os.path.join(HERE, "mmd_term.npz")
+    np.savez_compressed(path, **out)
+    print(f"mmd_term: mmd={float(mmd):.6f} grads={sorted(k_ for k_ in out if k_.startswith('grad/'))[:3]}... -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     kgvae_case("kgvae_tiny_noflow", n_ent=150, n_rel=5, h=20, bases=4, k=3, n_flows=0,
                n_train=600, batch=240, neg=3, kl_param=1e-2, dropout=0.2, seed=1)
@@ -298,3 +327,4 @@ if __name__ == "__main__":
     made_case()
     entity_case()
     neighbor_sampler_case()
+    mmd_case()

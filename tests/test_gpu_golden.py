@@ -171,3 +171,28 @@ def test_entity_classify_against_reference_golden(golden):
     loss.backward()
     for name, p in model.named_parameters():
         assert_close(p.grad, gv["grad/" + name], RTOL, f"grad {name}")
+
+
+def test_mmd_term_against_reference_golden(golden, monkeypatch):
+    """Row a8 (the README run has --mmd-param=1): KGVAE.get_mmd with python's ``random`` seeded and the prior
+    noise preset reproduces the reference's value and gradients (tests/golden/mmd_term.npz, produced by
+    kgvae/model.py:89-102 imported verbatim).  The 200 prior samples go through the CUDA flow."""
+    import random
+    gv = golden("mmd_term")
+    n_ent, n_rel, h, bases, k, n_flows, N = (int(v) for v in gv["cfg"])
+    model = K.LinkPredict(K.KGVAE, n_ent, h, n_rel, num_bases=bases, num_hidden_layers=2, dropout=0.0, use_cuda=True,
+                          reg_param=0.01, kl_param=1e-3, mmd_param=1.0, k=k, n_flows=n_flows)
+    model.load_state_dict({key[len("param/"):]: torch.from_numpy(val) for key, val in gv.items() if key.startswith("param/")})
+    model = model.to(DEV)
+    z = torch.from_numpy(gv["z"]).to(DEV).requires_grad_(True)
+    eps = torch.from_numpy(gv["eps"]).to(DEV)
+    monkeypatch.setattr(torch, "randn_like", lambda t, *a, **kw: eps.clone())
+    random.seed(9)
+    mmd = model.encoder.get_mmd(z)
+    mmd.backward()
+    assert_close(mmd, gv["mmd"], RTOL, "mmd")
+    # gradients of a difference of three kernel means: compare on the scale of the largest gradient entry
+    assert_close(z.grad, gv["grad_z"], 1e-3, "d mmd / d z")
+    for name, p in model.named_parameters():
+        if "grad/" + name in gv and p.grad is not None:
+            assert_close(p.grad, gv["grad/" + name], 1e-3, f"grad {name}")
