@@ -47,3 +47,12 @@ def test_driver_test_mode_loads_the_checkpoint(tmp_path, capsys):
     out = capsys.readouterr().out
     assert "start testing" in out and "Using best epoch: 2" in out and "MRR (raw)" in out
     assert 0.0 < mrr <= 1.0
+
+
+def test_driver_readme_configuration_terms(tmp_path, capsys):
+    """The README run's loss terms together (kgvae/README.md:5-6: --n-flows 3 --mmd-param 1 --mog-k 10), at toy size."""
+    np.random.seed(2)
+    torch.manual_seed(2)
+    best = K.link_predict.main(_args(tmp_path, "--n-flows", "3", "--mmd-param", "1", "--mog-k", "10", "--n-epochs", "2"))
+    out = capsys.readouterr().out
+    assert "Epoch 0002" in out and "mmd" in out and 0.0 < best <= 1.0
