@@ -54,45 +54,86 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port on the host cores
+# the workload both arms run: one dict, built by one function, so the two JSON lines name the same config
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=100, log=None, shape="FB15k-237"):
-    """Times oracle/kgvae_oracle.py (the CPU restatement of the reference path) on a bounded
-    sample: the reference's default step (20 000 sampled edges of the same graph, h=500, 100
-    blocks) and `eval_queries` test triples in both directions against all 14 541 entities."""
-    from oracle import kgvae_oracle as O
+def workload_config(args, data, n_nodes, n_edges, n_triplets, world):
+    return {"workload": args.workload, "entities": int(data.num_nodes), "relations": int(data.num_rels),
+            "train_triples": int(len(data.train)), "graph_edges": int(n_edges), "scored_triplets": int(n_triplets),
+            "nodes": int(n_nodes), "h": H, "bases": BASES, "mog_k": MOG_K, "n_flows": args.n_flows, "negative_rate": NEG,
+            "parallelism": f"replicas x{world} (grad all-reduce), eval entity-sharded; the CPU arm runs one replica",
+            "timed": "one train step = (device edge index on the GPU arm) + fwd + loss + bwd + grad clip + Adam",
+            "l2": "GPU arm: flushed between steps (256 MiB write); CPU arm: not applicable"}
+
+
+def load_datasets_module():
+    """gcn-vae_b200/datasets.py without importing the package (the reference arm loads no kernels)."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("kg_datasets", os.path.join(ROOT, "gcn-vae_b200", "datasets.py"))
     datasets = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(datasets)          # synthetic triples only; no kernels, no package import
+    spec.loader.exec_module(datasets)
+    return datasets
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rates(steps, warmup, n_flows, sample_edges, eval_queries=100, log=None, shape="FB15k-237",
+                     anomaly_steps=1, warmup_edges=20000):
+    """Times oracle/kgvae_oracle.py (the CPU restatement of the reference path, the reference's own op
+    sequence) on the host cores, on the SAME workload as the GPU arm: `sample_edges` sampled train edges per
+    step (all of them for the *-full workloads: 272 114 graph edges, 2 993 265 scored triplets at the
+    FB15k-237 shape), h = 500, 100 blocks, and the same timed region: forward + loss + backward + gradient
+    clipping + Adam (kgvae/link_predict.py:223-228).  Warm-up steps run the reference's default 20 000-edge
+    sample (they only warm the thread pool and the allocator).  The reference turns autograd anomaly
+    detection on at import (kgvae/model.py:10); `value` is measured with it OFF (the faster, fairer
+    figure) and `anomaly_steps` extra steps with it ON give the faithful one.  Evaluation: `eval_queries`
+    test triples in both directions against all entities."""
+    from oracle import kgvae_oracle as O
+    datasets = load_datasets_module()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     data = datasets.synthetic_kg(shape, seed=0)
     params = O.init_params(data.num_nodes, H, data.num_rels, BASES, MOG_K, n_flows, seed=0)
     for p in params.values():
         p.requires_grad_(True)
-    times = []
-    for it in range(warmup + steps):
+    leaves = [p for p in params.values() if p.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+
+    def one_step(it, n_sample):
         np.random.seed(100 + it)
         graph, node_id, samples, labels = O.generate_sampled_graph_and_labels(
-            data.train, sample_edges, 0.5, data.num_rels, NEG)
-        etype = graph["etype"]
+            data.train, n_sample, 0.5, data.num_rels, NEG)
         n = len(node_id)
         eps = torch.randn(n, H)
         masks = tuple((torch.rand(n, w) < 1 - DROPOUT).float() / (1 - DROPOUT) for w in (H, 2 * H))
         t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
         enc = O.kgvae_encode(params, graph, node_id, eps, BASES, n_flows, masks)
         out = O.kgvae_loss(params, enc, samples, labels, REG, KL, n_flows)
         out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_([p for p in leaves if p.grad is not None], 1.0)
+        opt.step()
         dt = time.perf_counter() - t0
-        for p in params.values():
-            p.grad = None
-        if it >= warmup:
+        return dt, len(graph["etype"]), len(labels)
+
+    times, edges = [], sample_edges
+    for it in range(warmup + steps):
+        warm = it < warmup
+        dt, edges_it, trip_it = one_step(it, warmup_edges if warm else sample_edges)
+        if not warm:
             times.append(dt)
+            edges = edges_it
         if log:
-            log(f"[cpu oracle] step {it}: {dt:.2f}s ({len(etype)} edges, {len(labels)} triplets)")
-    edges = sample_edges  # 2 * (sample_edges / 2) directed edges
-    train_rate = edges / (sum(times) / len(times))
+            log(f"[cpu oracle] {'warm-up' if warm else 'step'} {it}: {dt:.2f}s ({edges_it} edges, {trip_it} triplets)")
+    anomaly_times = []
+    if anomaly_steps > 0:
+        with torch.autograd.set_detect_anomaly(True):
+            for it in range(anomaly_steps):
+                dt, _, _ = one_step(warmup + steps + it, sample_edges)
+                anomaly_times.append(dt)
+                if log:
+                    log(f"[cpu oracle] anomaly-detection ON step: {dt:.2f}s")
+    step_s = sum(times) / len(times)
     # evaluation sample
     with torch.no_grad():
         emb = params["encoder.input_layer.embedding.weight"].detach()
@@ -100,11 +141,18 @@ def cpu_oracle_rates(steps, warmup, n_flows, sample_edges=20000, eval_queries=10
         t0 = time.perf_counter()
         O.calc_mrr(emb, params["w_relation"].detach(), t, eval_bz=eval_queries, policy="reference")
         eval_dt = time.perf_counter() - t0
-    return {"train_edges_per_s": train_rate, "step_s": sum(times) / len(times), "cores": cores,
-            "eval_triples_per_s": eval_queries / eval_dt,
-            "sample": f"reference default step: {sample_edges} sampled edges ({sample_edges * (NEG + 1)} scored "
-                      f"triplets) of the same graph, fwd+loss+bwd, {len(times)} timed steps; eval: "
-                      f"{eval_queries} test triples x 2 directions x {data.num_nodes} candidates"}
+    res = {"train_edges_per_s": edges / step_s, "step_s": step_s, "cores": cores, "edges": edges,
+           "eval_triples_per_s": eval_queries / eval_dt,
+           "sample": f"same workload as the GPU arm: {edges} graph edges, {trip_it} scored triplets per step, "
+                     f"fwd+loss+bwd+clip+Adam, {len(times)} timed steps (autograd anomaly detection off; warm-up "
+                     f"steps on a {warmup_edges}-edge sample); eval: {eval_queries} test triples x 2 directions "
+                     f"x {data.num_nodes} candidates"}
+    if anomaly_times:
+        a = sum(anomaly_times) / len(anomaly_times)
+        res["anomaly_on"] = {"edges_per_s": edges / a, "step_s": a, "steps": len(anomaly_times),
+                             "note": "torch.autograd.set_detect_anomaly(True) as the reference sets at import "
+                                     "(kgvae/model.py:10)"}
+    return res
 
 
 def run_reference(args):
@@ -117,18 +165,26 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": f"no bounded CPU sample for workload {args.workload}"}))
         return
     shape = "wn18" if args.workload.startswith("wn18") else "FB15k-237"
-    r = cpu_oracle_rates(args.steps, args.warmup, args.n_flows, log=lambda m: print(m, file=sys.stderr), shape=shape)
+    log = lambda m: print(m, file=sys.stderr, flush=True)
+    datasets = load_datasets_module()
+    data = datasets.synthetic_kg(shape, seed=0)
+    batch = 20000 if args.workload.endswith("-step") else len(data.train)
+    r = cpu_oracle_rates(args.steps, args.warmup, args.n_flows, sample_edges=batch, log=log, shape=shape)
+    # the sizes the GPU arm reports for the same sampler call (seed 0): nodes after relabelling, 2 * batch // 2 edges
+    from oracle import kgvae_oracle as O
+    np.random.seed(0)
+    graph, node_id, samples, labels = O.generate_sampled_graph_and_labels(data.train, batch, 0.5, data.num_rels, NEG)
+    cfg = workload_config(args, data, len(node_id), len(graph["etype"]), len(labels), args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["train_edges_per_s"], "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["step_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "n_flows": args.n_flows, "h": H, "bases": BASES},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"],
-                         "kind": "port", "sample": r["sample"]},
+                         "kind": "port", "sample": r["sample"], "anomaly_on": r.get("anomaly_on"),
+                         "eval_triples_per_s": r["eval_triples_per_s"]},
         "e2e": {"value": r["train_edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "eval": {"value": r["eval_triples_per_s"], "unit": "triples/s"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -201,6 +257,32 @@ def algorithmic_bytes(tag, shp):
     if tag == "kg_distmult_bwd_dz":                     # each triplet seen from both ends: w row + other row + record
         return 2 * S * (2 * 4 * h + 16 + 4) + 4 * N * h
     return None
+
+
+def measure_l2_peak(dev, rows, row_floats, n_ops=3_000_000, reps=5):
+    """kg_probe_l2 on two L2-resident [rows, row_floats] fp32 matrices: GB/s of whole-row random reads, of
+    whole-row random reductions (red.global.add.v4.f32), and of both at once (bytes of both directions
+    counted) - best of `reps` launches each, CUDA events on the launching stream."""
+    from gcn_vae_b200 import _lib as L
+    src = torch.randn(rows, row_floats, device=dev)
+    dst = torch.zeros(rows, row_floats, device=dev)
+    sink = torch.zeros(4, device=dev)
+    out = {"rows": rows, "row_bytes": 4 * row_floats, "ops": n_ops}
+    for name, mode in (("read", 1), ("reduce", 2), ("mixed", 3)):
+        best = None
+        for it in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L.call("kg_probe_l2", L.f32(src), L.f32(dst), rows, row_floats, n_ops, mode, L.f32(sink), L.stream())
+            b.record()
+            b.synchronize()
+            if it > 0:
+                ms = a.elapsed_time(b)
+                best = ms if best is None else min(best, ms)
+        nbytes = n_ops * 4 * row_floats * (2 if mode == 3 else 1)
+        out[name + "_gbs"] = nbytes / (best * 1e-3) / 1e9
+        out[name + "_ms"] = best
+    return out
 
 
 def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edges=32_000_000, iters=5):
@@ -692,6 +774,13 @@ def run_gpu(args):
     ms_e2e = max_over_ranks(timed_e2e(args.steps))
     sync_all()
 
+    # ---- L2 throughput of this GPU for whole-row gathers / reductions (roofline denominator) --------
+    l2_peak = None
+    if rank == 0:
+        l2_peak = measure_l2_peak(dev, N, H)
+        log(f"  [l2 probe] read {l2_peak['read_gbs']:.0f} GB/s, reduce {l2_peak['reduce_gbs']:.0f} GB/s, "
+            f"read+reduce {l2_peak['mixed_gbs']:.0f} GB/s")
+
     # ---- evaluation: encoder on the test graph + all-entity ranks -----------------------------
     model.eval()
     test = torch.from_numpy(data.test)
@@ -758,27 +847,44 @@ def run_gpu(args):
     for tag, ms in top[:14]:
         log(f"  {tag:44s} {ms / args.steps:8.3f} ms/step  {100 * ms / total_ops:5.1f}%  x{op_n[tag] // args.steps}")
     pk = peaks()
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     roof = None
     for tag, ms in top:
         ab = algorithmic_bytes(tag, shp)
-        if ab is not None:
-            per_launch_ms = ms / op_n[tag]
+        if ab is None:
+            continue
+        per_launch_ms = ms / op_n[tag]
+        if l2_peak and (N * H * 4 <= 96 << 20):
+            # Every matrix this launch gathers from / reduces into (z, dz, h: N x 500 fp32 = 29 MB) stays in the
+            # 126 MB L2 - ncu: 2 % DRAM throughput - so the bound is L2, not HBM.  achieved = the launch's
+            # algorithmic L2 bytes per second (per scored triplet one whole row of z read and one whole row reduced
+            # into dz; per message-passing edge one row gathered and one row of `out` floats reduced); peak = what
+            # kg_probe_l2 sustains for the same mix of whole-row reads and reductions on this GPU, measured in
+            # this process a moment ago.
+            if tag == "kg_distmult_bce_fwd":
+                l2_bytes, mix = S * 2 * 4 * H, "mixed"
+            elif tag.startswith("kg_bdd_rel"):
+                si, so = (int(x) for x in tag[tag.index("[") + 1:-1].split("x"))
+                l2_bytes = E * 4 * BASES * (si + so) * (2 if "bwd" in tag else 1)
+                mix = "mixed"
+            else:
+                l2_bytes, mix = ab, "read"
+            ach = l2_bytes / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": tag, "bound": "l2", "achieved": ach, "peak": l2_peak[mix + "_gbs"], "unit": "GB/s",
+                    "frac": ach / l2_peak[mix + "_gbs"], "traffic": traffic.get(tag + ":lts_bytes"),
+                    "peak_source": "kg_probe_l2, measured in this run (random whole-row reads + reductions on two "
+                                   "L2-resident 29 MB matrices)",
+                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": l2_bytes, "share_of_step": ms / total_ops,
+                    "dram_traffic": traffic.get(tag), "hbm_algorithmic_bytes": ab,
+                    "regime": "L2-resident (z, dz, h are 29 MB each; L2 is 126 MB): bounded by L2, not HBM",
+                    "l2_probe": l2_peak}
+        else:
             ach = ab / (per_launch_ms * 1e-3) / 1e9
             roof = {"kernel": tag, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": ab,
-                    "share_of_step": ms / total_ops,
-                    "regime": "L2-resident gathers (z, h are 29 MB): algorithmic GB/s can exceed HBM peak"}
-            if tag == "kg_distmult_bce_fwd":
-                # what actually bounds this launch: per scored triplet one streamed 2 KB row of z read from L2
-                # and one 2 KB row reduced into dz in L2 (the (r, a) rows stay in registers over a run)
-                l2_bytes = S * 2 * 4 * H
-                roof["l2_traffic_bytes"] = l2_bytes
-                roof["l2_gbs"] = l2_bytes / (per_launch_ms * 1e-3) / 1e9
-            break
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if roof and os.path.exists(traffic_file):
-        roof["traffic"] = json.load(open(traffic_file)).get(roof["kernel"])
+                    "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(tag), "peak_source": pk["source"],
+                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": ab, "share_of_step": ms / total_ops}
+        break
     eval_top = sorted(((t, sum(a.elapsed_time(b) for a, b in e) / len(e)) for t, e in eval_prof.items()),
                       key=lambda kv: -kv[1])
     T = len(data.test)
@@ -809,9 +915,27 @@ def run_gpu(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_rates(2, 1, args.n_flows, log=log, shape=shape)
+        r = cpu_oracle_rates(2, 1, args.n_flows, sample_edges=batch, log=log, shape=shape)
         cpu = {"value": r["train_edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": "port",
-               "sample": r["sample"], "eval_triples_per_s": r["eval_triples_per_s"]}
+               "sample": r["sample"], "eval_triples_per_s": r["eval_triples_per_s"], "anomaly_on": r.get("anomaly_on")}
+
+    # the driver's record keeps `roofline` and `config` but not free-form keys: the HBM-bound and tensor-bound
+    # launches and the evaluation figures are folded into `roofline` so that they are part of the record
+    eval_summary = {"value": T * args.steps / (ms_eval * 1e-3), "unit": "triples/s", "ms": ms_eval / args.steps,
+                    "filtered_value": T * args.steps / (ms_eval_filt * 1e-3),
+                    "setting": f"{T} test triples x 2 directions x {data.num_nodes} candidates, encoder included"}
+    if roof is not None:
+        roof["tensor"] = eval_roof
+        roof["eval"] = eval_summary
+        if streaming:
+            worst = min(((k_, v) for k_, v in streaming["kernels"]["uniform"].items()), key=lambda kv: kv[1]["frac_of_hbm_peak"])
+            roof["hbm"] = {"kernel": worst[0] + " @ wikikg2 shape (2.5 M nodes, 32 M edges)", "bound": "hbm",
+                           "achieved": worst[1]["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": worst[1]["frac_of_hbm_peak"], "traffic": traffic.get(worst[0] + ":streaming"),
+                           "peak_source": pk["source"], "ms_per_launch": worst[1]["ms"],
+                           "algorithmic_bytes": worst[1]["algorithmic_bytes"],
+                           "note": "the message-passing launch furthest below the HBM roofline in the streaming "
+                                   "regime; all four launches under rgcn_streaming"}
 
     total_edges = E * world * args.steps
     line = {
@@ -819,12 +943,7 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "entities": data.num_nodes, "relations": data.num_rels,
-                   "train_triples": len(data.train), "graph_edges": E, "scored_triplets": S, "nodes": N,
-                   "h": H, "bases": BASES, "mog_k": MOG_K, "n_flows": args.n_flows, "negative_rate": NEG,
-                   "parallelism": f"replicas x{world} (grad all-reduce), eval entity-sharded",
-                   "timed": "graph index + fwd + loss + bwd + clip + Adam; per-step CUDA events",
-                   "l2": "flushed between steps (256 MiB write)"},
+        "config": workload_config(args, data, N, E, S, world),
         "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                 "how": "pinned host inputs copied every step inside the timed region (double-buffered on a side "

@@ -323,6 +323,17 @@ int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const i
                      void* workspace, size_t workspace_bytes, int32_t* ranks, float* tc_scores,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * measurement aid (new; no reference counterpart): sustained L2 throughput of this GPU for
+ * the access pattern of kg_distmult_bce_fwd - whole fp32 rows of an L2-resident matrix read
+ * at random (mode bit 0) and reduced into at random (mode bit 1).  n_ops independent
+ * operations; the caller times the call with CUDA events; bytes through L2 =
+ * n_ops * 4 * row_floats per enabled direction.  bench.py uses it as the denominator of the
+ * "l2" roofline (MEASURED_PEAKS.json only carries HBM and tensor peaks).
+ * ---------------------------------------------------------------------------------- */
+int kg_probe_l2(const float* src, float* dst, int rows, int row_floats, long long n_ops, int mode,
+                float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
