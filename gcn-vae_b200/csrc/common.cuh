@@ -60,5 +60,7 @@ __device__ __forceinline__ int kg_warp_sum_int(int v) {
 __device__ __forceinline__ float kg_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float kg_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
-// Number of SMs of the current device (cached per process; immutable attribute).
+// Number of SMs of the current device (cached per device; immutable attribute).
 int kg_sm_count();
+// true the first time it is called for (slot, current device): guards per-device cudaFuncSetAttribute calls
+bool kg_attr_needed(int slot);

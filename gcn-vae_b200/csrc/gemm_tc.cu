@@ -361,11 +361,8 @@ int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb
   rc = make_tensor_map_2d_b16(&tm_b, bcat, N, 2 * L.Kp, row_bytes, BN);
   if (rc != KG_OK) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (kg_attr_needed(0))
     KG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   GemmArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.inv_sa = inv_sa; g.inv_sb = inv_sb;
   g.bias = bias; g.addend = addend; g.mask = mask; g.relu = relu; g.accumulate = accumulate;

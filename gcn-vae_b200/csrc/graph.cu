@@ -27,16 +27,27 @@ extern "C" const char* kg_last_error(void) { return g_err; }
 extern "C" int kg_version(void) { return 100; }
 
 int kg_sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static int cached[64] = {0};            // per device: a process may drive several GPUs
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
       return 148;
   }
-  return cached;
+  return cached[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices have it for `slot`
+bool kg_attr_needed(int slot) {
+  static unsigned long long done[8] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || slot < 0 || slot >= 8) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (done[slot] & bit) return false;
+  done[slot] |= bit;
+  return true;
 }
 
 extern "C" int kg_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -335,11 +335,8 @@ extern "C" int kg_distmult_rank(const float* emb, const float* w, const int32_t*
   rc = make_tensor_map_2d_b16(&tm_b, bcat, n_cand, 2 * L.Kp, row_bytes, BN);
   if (rc != KG_OK) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (kg_attr_needed(1))
     KG_CUDA(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   RankArgs args;
   args.q32 = q32; args.emb = emb; args.rowp = rowp; args.colp = colp; args.tgt = b; args.shift = shift;
   args.ranks = ranks; args.sqv = sqv; args.dump = tc_scores;

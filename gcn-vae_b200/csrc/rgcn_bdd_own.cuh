@@ -1,5 +1,8 @@
-// a3: RelGraphConv(regularizer="bdd") message passing, BLOCK-OWNER kernels (the reference model's
-// 5x5 and 5x10 blocks; DGL RelGraphConv as constructed at kgvae/model.py:54-59).
+// a3: RelGraphConv(regularizer="bdd") message passing, BLOCK-OWNER design (the reference model's
+// 5x5 and 5x10 blocks; DGL RelGraphConv as constructed at kgvae/model.py:54-59): the shared pieces -
+// bulk-async copy / reduction wrappers, the row source (one matrix or one block per rank over NVLink),
+// register <-> shared memory helpers, eligibility.  The kernels are in rgcn_bdd_warp.cuh (the first,
+// CTA-synchronised generation that lived here was superseded by them and has been removed).
 //
 // A thread owns TB whole diagonal blocks of the relation's weight - TB*si*so = 100 floats, read
 // straight from the DGL-layout weight row [B][si][so] (they are contiguous) - and keeps them in
@@ -27,7 +30,6 @@ namespace bddown {
 
 constexpr int kCta = 128;     // threads per CTA (4 warps)
 constexpr int kChunk = 256;   // consecutive relation-sorted edges per CTA
-constexpr int kDepth = 4;     // gathered rows in flight per slot
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -94,19 +96,6 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // order this thread's generic-proxy shared-memory writes before later async-proxy (bulk) reads
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// synchronise the WARPS warps of slot `slot` (immediate barrier ids: the CTA reserves 1 + slots)
-template <int WARPS>
-__device__ __forceinline__ void slot_sync(int slot) {
-  if (WARPS == 1) {
-    __syncwarp();
-  } else if (WARPS == 2) {
-    if (slot == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-    else asm volatile("bar.sync 2, 64;" ::: "memory");
-  } else {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-  }
-}
-
 __device__ __forceinline__ const float* row_at(const float* base, int row, int width) {
   return base + (size_t)(unsigned)row * (unsigned)width;
 }
@@ -145,313 +134,12 @@ __device__ __forceinline__ void lds_vec(float (&v)[N], const float* p) {
   }
 }
 
-// park s * v[0..N) (this lane's N consecutive output columns) in the warp's staging buffer
-template <int N>
-__device__ __forceinline__ void park(float* mine, const float (&v)[N], float s) {
-  if (N % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 4)
-      *reinterpret_cast<float4*>(mine + i) = make_float4(s * v[i], s * v[i + 1], s * v[i + 2], s * v[i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2*>(mine + i) = make_float2(s * v[i], s * v[i + 1]);
-  }
-}
-
 // owner lanes per warp when `per` groups of N columns are spread over `warps` warps; even when N * 4
 // is not a multiple of 16 so that every warp's share of a row is a whole number of 16-byte pieces
 __device__ __host__ __forceinline__ int lanes_per_warp(int per, int warps, int n_cols) {
   int lpw = (per + warps - 1) / warps;
   if ((n_cols * 4) % 16 != 0 && (lpw & 1)) ++lpw;
   return lpw;
-}
-
-// group (owned block set) of this lane, or -1
-__device__ __forceinline__ int group_of(int warp_in_role, int lane, int per, int lpw) {
-  const int g = warp_in_role * lpw + lane;
-  return (lane < lpw && g < per) ? g : -1;
-}
-
-// ------------------------------------------------------------------------------------------
-// forward: out[dst] += norm * blockdiag(W_etype) feat[src]
-// weight [R][B][FI][FO] (DGL layout); out zero-filled by the caller
-// ------------------------------------------------------------------------------------------
-template <int FI, int FO, int TB, int WPS>
-__global__ void __launch_bounds__(kCta)
-fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E,
-           const float* __restrict__ weight, int B, int hints, float* __restrict__ out) {
-  constexpr int XN = TB * FI, CN = TB * FO, WN = TB * FI * FO, SLOTS = 4 / WPS;
-  extern __shared__ __align__(16) float sm[];
-  const int width = B * FO, in_w = B * FI;
-  int4* P_s = reinterpret_cast<int4*>(sm);    // [kChunk] {src, dst, etype, norm}
-  float* X_s = sm + 4 * kChunk;               // [SLOTS][kDepth][in_w] gathered rows
-  float* T_s = X_s + SLOTS * kDepth * in_w;   // [4 warps][2][32 * CN] parked outputs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(T_s + 4 * 2 * 32 * CN);   // [SLOTS][kDepth]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = warp / WPS, wsl = warp % WPS;
-  const int e0 = blockIdx.x * kChunk, n = min(E - e0, kChunk);
-  for (int i = threadIdx.x; i < n; i += kCta) P_s[i] = __ldg(pack + e0 + i);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SLOTS * kDepth; ++i) mbar_init(bars + i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // a slot takes a contiguous share of the chunk: the relation (and so the registers) changes rarely
-  const int share = (n + SLOTS - 1) / SLOTS;
-  const int k_lo = slot * share, n_my = max(0, min(n - k_lo, share));
-  if (n_my == 0) return;
-  const int4* rec = P_s + k_lo;
-  float* ring = X_s + slot * kDepth * in_w;
-  uint64_t* full = bars + slot * kDepth;
-  // peer rows bypass the local L2 anyway; a cache hint on them only slows the copies down (measured 4x)
-  const uint64_t pol = l2_policy((hints & 1) && feat.parts == nullptr), pol_red = l2_policy_last(hints & 4);
-  const uint32_t row_bytes = (uint32_t)in_w * 4;
-  const bool leader = wsl == 0 && lane == 0;  // issues the slot's gathers
-
-  if (leader) {
-#pragma unroll
-    for (int k = 0; k < kDepth; ++k)
-      if (k < n_my) {
-        mbar_expect_tx(full + k, row_bytes);
-        bulk_g2s(ring + k * in_w, feat.row(rec[k].x, in_w), row_bytes, full + k, pol);
-      }
-  }
-
-  const int lpw = lanes_per_warp(B / TB, WPS, CN);
-  const int g = group_of(wsl, lane, B / TB, lpw);
-  const int g_lo = wsl * lpw;                                        // first group of this warp
-  const uint32_t warp_bytes = (uint32_t)max(0, min(lpw, B / TB - g_lo)) * CN * 4;   // this warp's share of a row
-  float* tbuf = T_s + warp * 2 * 32 * CN;
-  float* out_w = out + g_lo * CN;
-  const float* xg = ring + max(g, 0) * XN;
-  const float* w_g = weight + max(g, 0) * WN;
-  float w[WN];
-  int cur = -1;
-  for (int k = 0; k < n_my; k += kDepth) {
-#pragma unroll
-    for (int u = 0; u < kDepth; ++u) {
-      if (k + u < n_my) {                     // uniform across the slot
-        mbar_wait(full + u, (k / kDepth) & 1);              // row k+u has landed
-        const int4 p = rec[k + u];
-        float m[CN];
-        if (g >= 0) {
-          if (p.z != cur) {                   // relation run starts: my TB blocks of W_r
-            cur = p.z;
-            const float4* wr = reinterpret_cast<const float4*>(row_at(w_g, cur, B * FI * FO));
-#pragma unroll
-            for (int i = 0; i < WN / 4; ++i) {
-              const float4 t = __ldg(wr + i);
-              w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-            }
-          }
-          float xv[XN];
-          lds_vec<XN>(xv, xg + u * in_w);
-#pragma unroll
-          for (int tb = 0; tb < TB; ++tb)
-#pragma unroll
-            for (int o = 0; o < FO; ++o) {
-              float a = 0.f;
-#pragma unroll
-              for (int i = 0; i < FI; ++i) a = fmaf(xv[tb * FI + i], w[(tb * FI + i) * FO + o], a);
-              m[tb * FO + o] = a;
-            }
-        }
-        float* tb_cur = tbuf + (u & 1) * 32 * CN;
-        if (lane == 0) bulk_wait_read<1>();   // the reduction that read this buffer two edges ago is done with it
-        __syncwarp();
-        if (g >= 0) {
-          park<CN>(tb_cur + lane * CN, m, __int_as_float(p.w));
-          fence_async_smem();
-        }
-        slot_sync<WPS>(slot);                 // outputs parked; everybody has consumed ring stage u
-        if (lane == 0) {
-          if (warp_bytes) bulk_red_add(const_cast<float*>(row_at(out_w, p.y, width)), tb_cur, warp_bytes, pol_red);
-          bulk_commit();
-        }
-        if (leader && k + u + kDepth < n_my) {              // refill the stage just consumed
-          mbar_expect_tx(full + u, row_bytes);
-          bulk_g2s(ring + u * in_w, feat.row(rec[k + u + kDepth].x, in_w), row_bytes, full + u, pol);
-        }
-      }
-    }
-  }
-  if (lane == 0) bulk_wait_all();             // shared memory must outlive the reductions reading it
-}
-
-// ------------------------------------------------------------------------------------------
-// fused backward: dx[src] += norm * blockdiag(W_r)^T dagg[dst]
-//                 dW[r][b][i][o] += norm * x[src][b*SI+i] * dagg[dst][b*SO+o]
-// weight, dW [R][B][SI][SO]; dx, dW zero-filled by the caller; dx may be null
-// slot = WPR input-gradient warps then WPR weight-gradient warps
-// ------------------------------------------------------------------------------------------
-template <int SI, int SO, int TB, int WPR>
-__global__ void __launch_bounds__(kCta)
-bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
-           const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
-  constexpr int XN = TB * SI, DN = TB * SO, WN = TB * SI * SO, WPS = 2 * WPR, SLOTS = 4 / WPS;
-  extern __shared__ __align__(16) float sm[];
-  const int in_w = B * SI, out_w = B * SO, row_w = in_w + out_w;
-  int4* P_s = reinterpret_cast<int4*>(sm);    // [kChunk]
-  float* R_s = sm + 4 * kChunk;               // [SLOTS][kDepth][in_w + out_w]: x row then dagg row
-  float* T_s = R_s + SLOTS * kDepth * row_w;  // [4 warps][2][32 * XN] parked input gradients
-  uint64_t* bars = reinterpret_cast<uint64_t*>(T_s + 4 * 2 * 32 * XN);   // [SLOTS][kDepth]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = warp / WPS, wsl = warp % WPS;
-  const int e0 = blockIdx.x * kChunk, n = min(E - e0, kChunk);
-  for (int i = threadIdx.x; i < n; i += kCta) P_s[i] = __ldg(pack + e0 + i);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SLOTS * kDepth; ++i) mbar_init(bars + i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const int share = (n + SLOTS - 1) / SLOTS;
-  const int k_lo = slot * share, n_my = max(0, min(n - k_lo, share));
-  if (n_my == 0) return;
-  const int4* rec = P_s + k_lo;
-  float* ring = R_s + slot * kDepth * row_w;
-  uint64_t* full = bars + slot * kDepth;
-  const uint64_t pol_x = x.parts != nullptr ? l2_policy(false) : (hints & 4) ? l2_policy_last(true) : l2_policy(hints & 1);
-  const uint64_t pol_d = l2_policy(hints & 2);
-  const uint64_t pol_red = l2_policy_last(hints & 4);
-  const uint32_t x_bytes = (uint32_t)in_w * 4, d_bytes = (uint32_t)out_w * 4;
-  const bool leader = wsl == 0 && lane == 0;
-
-  auto gather = [&](int k, int stage) {       // leader only
-    const int4 p = rec[k];
-    mbar_expect_tx(full + stage, x_bytes + d_bytes);
-    bulk_g2s(ring + stage * row_w, x.row(p.x, in_w), x_bytes, full + stage, pol_x);
-    bulk_g2s(ring + stage * row_w + in_w, row_at(dagg, p.y, out_w), d_bytes, full + stage, pol_d);
-  };
-  if (leader) {
-#pragma unroll
-    for (int k = 0; k < kDepth; ++k)
-      if (k < n_my) gather(k, k);
-  }
-
-  const bool xrole = wsl < WPR;               // warp-uniform: input-gradient warps come first
-  const int lpw = lanes_per_warp(B / TB, WPR, xrole ? XN : 4);
-  const int wr_i = xrole ? wsl : wsl - WPR;   // warp index inside its role
-  const int g = (xrole && dx == nullptr) ? -1 : group_of(wr_i, lane, B / TB, lpw);
-  const int gg = max(g, 0);
-  const int g_lo = wr_i * lpw;
-  const uint32_t warp_bytes = (uint32_t)max(0, min(lpw, B / TB - g_lo)) * XN * 4;   // dx share of an x-role warp
-  float* tbuf = T_s + warp * 2 * 32 * XN;
-  float* dx_w = dx + g_lo * XN;
-  const float* xg = ring + gg * XN;
-  const float* dg = ring + in_w + gg * DN;
-  const size_t KW = (size_t)B * SI * SO;
-  float r[WN];                                // dX role: my blocks of W_r; dW role: their gradient
-#pragma unroll
-  for (int i = 0; i < WN; ++i) r[i] = 0.f;
-  int cur = -1;
-
-  auto flush = [&](int rel) {                 // dW role
-    float* dst = dW + (size_t)(unsigned)rel * KW + gg * WN;
-#pragma unroll
-    for (int i = 0; i < WN; i += 4) {
-      red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
-      r[i] = r[i + 1] = r[i + 2] = r[i + 3] = 0.f;
-    }
-  };
-
-  for (int k = 0; k < n_my; k += kDepth) {
-#pragma unroll
-    for (int u = 0; u < kDepth; ++u) {
-      if (k + u < n_my) {
-        mbar_wait(full + u, (k / kDepth) & 1);
-        const int4 p = rec[k + u];
-        const float nv = __int_as_float(p.w);
-        float* tb_cur = tbuf + (u & 1) * 32 * XN;
-        if (xrole) {                          // warp-uniform
-          float m[XN];
-          if (g >= 0) {
-            if (p.z != cur) {
-              cur = p.z;
-              const float4* wr = reinterpret_cast<const float4*>(weight + (size_t)(unsigned)cur * KW + gg * WN);
-#pragma unroll
-              for (int i = 0; i < WN / 4; ++i) {
-                const float4 t = __ldg(wr + i);
-                r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
-              }
-            }
-            float dv[DN];
-            lds_vec<DN>(dv, dg + u * row_w);
-#pragma unroll
-            for (int tb = 0; tb < TB; ++tb)
-#pragma unroll
-              for (int i = 0; i < SI; ++i) {
-                float a = 0.f;
-#pragma unroll
-                for (int o = 0; o < SO; ++o) a = fmaf(dv[tb * SO + o], r[(tb * SI + i) * SO + o], a);
-                m[tb * SI + i] = a;
-              }
-          }
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          if (g >= 0) {
-            park<XN>(tb_cur + lane * XN, m, nv);
-            fence_async_smem();
-          }
-        } else if (g >= 0) {
-          if (p.z != cur) {
-            if (cur >= 0) flush(cur);
-            cur = p.z;
-          }
-          float dv[DN], xv[XN];
-          lds_vec<DN>(dv, dg + u * row_w);
-          lds_vec<XN>(xv, xg + u * row_w);
-#pragma unroll
-          for (int tb = 0; tb < TB; ++tb)
-#pragma unroll
-            for (int i = 0; i < SI; ++i) {
-              const float xs = nv * xv[tb * SI + i];
-#pragma unroll
-              for (int o = 0; o < SO; ++o)
-                r[(tb * SI + i) * SO + o] = fmaf(xs, dv[tb * SO + o], r[(tb * SI + i) * SO + o]);
-            }
-        }
-        slot_sync<WPS>(slot);                 // gradients parked; everybody has consumed ring stage u
-        if (xrole && lane == 0) {
-          if (dx != nullptr && warp_bytes)
-            bulk_red_add(const_cast<float*>(row_at(dx_w, p.x, in_w)), tb_cur, warp_bytes, pol_red);
-          bulk_commit();
-        }
-        if (leader && k + u + kDepth < n_my) gather(k + u + kDepth, u);
-      }
-    }
-  }
-  if (g >= 0 && !xrole && cur >= 0) flush(cur);
-  if (xrole && lane == 0) bulk_wait_all();
-}
-
-// ------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------
-template <int FI, int FO, int TB, int WPS>
-int launch_fwd(RowSource feat, const void* pack, int E, const float* weight, int B, int hints, float* out,
-               cudaStream_t st) {
-  constexpr int SLOTS = 4 / WPS;
-  const size_t smem = sizeof(float) * ((size_t)4 * kChunk + (size_t)SLOTS * kDepth * B * FI + 4 * 2 * 32 * TB * FO) +
-                      sizeof(uint64_t) * SLOTS * kDepth;
-  auto kern = fwd_kernel<FI, FO, TB, WPS>;
-  KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(feat, reinterpret_cast<const int4*>(pack), E, weight, B, hints, out);
-  KG_LAUNCH_OK();
-  return KG_OK;
-}
-
-template <int SI, int SO, int TB, int WPR>
-int launch_bwd(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
-               float* dx, float* dW, cudaStream_t st) {
-  constexpr int SLOTS = 4 / (2 * WPR);
-  const size_t smem = sizeof(float) * ((size_t)4 * kChunk + (size_t)SLOTS * kDepth * B * (SI + SO) + 4 * 2 * 32 * TB * SI) +
-                      sizeof(uint64_t) * SLOTS * kDepth;
-  auto kern = bwd_kernel<SI, SO, TB, WPR>;
-  KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
-                                                 dx, dW);
-  KG_LAUNCH_OK();
-  return KG_OK;
 }
 
 // shapes the block-owner kernels cover: 5x5 blocks (4 per thread) and 5x10 blocks (2 per thread)

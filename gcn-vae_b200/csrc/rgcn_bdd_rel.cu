@@ -439,16 +439,6 @@ bool fast_shape(int B, int si, int so) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// KG_BDD_WARP=0 selects the CTA-synchronised block-owner kernels (rgcn_bdd_own.cuh) instead of the
-// warp-autonomous ones (rgcn_bdd_warp.cuh): an A/B switch for profiling, read once.
-bool warp_kernels() {
-  static const bool on = [] {
-    const char* v = getenv("KG_BDD_WARP");
-    return !(v && v[0] == '0');
-  }();
-  return on;
-}
-
 }  // namespace
 
 #define KG_BDD_DISPATCH(FN, SI_, SO_, ...) \
@@ -470,12 +460,8 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(weight) && aligned16(agg)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
-    if (warp_kernels()) {
-      if (so == 5) return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-      return bddwarp::launch_fwd<5, 10, 2, 2, 8>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    }
-    if (so == 5) return bddown::launch_fwd<5, 5, 4, 1>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    return bddown::launch_fwd<5, 10, 2, 2>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    if (so == 5) return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    return bddwarp::launch_fwd<5, 10, 2, 2, 8>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel fwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
   KG_REQUIRE(w_fwd != nullptr, "bdd rel fwd: this block shape needs the w_fwd layout (kg_bdd_weight_layouts)");
@@ -509,19 +495,15 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(dagg) && aligned16(weight) &&
       aligned16(dx) && aligned16(dweight)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
-    if (warp_kernels()) {
-      if (hints & kHintStreamD) {             // dagg streams from HBM: partner warps share one gather of it
-        if (so == 5)
-          return bddwarp::launch_bwd_paired<5, 5, 4, 1, 6>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-        return bddwarp::launch_bwd_paired<5, 10, 2, 2, 8>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-      }
-      if (so == 5)
-        return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-      return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    }
+    // dagg streams from HBM (wikikg2 shape): with 5x5 blocks the partner warps of the paired variant share one
+    // gather of dagg[dst] (103 GB of DRAM traffic instead of 148 GB, 25.0 vs 25.3 ms); with 5x10 blocks the
+    // independent warps win although they fetch the row twice (ncu: 40.1 vs 46.1 ms - the paired ring makes the
+    // 2 KB weight-gradient role wait for the 4 KB input-gradient role on every edge)
+    if ((hints & kHintStreamD) && so == 5)
+      return bddwarp::launch_bwd_paired<5, 5, 4, 1, 6>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
     if (so == 5)
-      return bddown::launch_bwd<5, 5, 4, 1>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    return bddown::launch_bwd<5, 10, 2, 2>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+      return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel bwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
   KG_REQUIRE(w_bwd != nullptr, "bdd rel bwd: this block shape needs the w_bwd layout (kg_bdd_weight_layouts)");

@@ -54,23 +54,37 @@ class Graph:
         self._index = None
 
     # ---- DGLGraph query surface ----------------------------------------------------------
+    def _ensure_host(self):
+        """Graphs built on the device (utils.generate_sampled_graph_and_labels_device, bench) carry only
+        device edge lists: the host-side queries below pull them over once instead of answering for an
+        empty graph."""
+        if self._src.shape[0] == 0 and self._dev_edges:
+            src, dst = next(iter(self._dev_edges.values()))
+            self._src = src.detach().cpu().numpy().astype(np.int64)
+            self._dst = dst.detach().cpu().numpy().astype(np.int64)
+
     def number_of_nodes(self):
         return self._n
 
     def number_of_edges(self):
+        if self._src.shape[0] == 0 and self._dev_edges:
+            return int(next(iter(self._dev_edges.values()))[0].numel())
         return int(self._src.shape[0])
 
     def __len__(self):
         return self._n
 
     def in_degrees(self, v=None):
+        self._ensure_host()
         deg = torch.from_numpy(np.bincount(self._dst, minlength=self._n))
         return deg if v is None else deg[torch.as_tensor(list(v), dtype=torch.long)]
 
     def edges(self):
+        self._ensure_host()
         return torch.from_numpy(self._src), torch.from_numpy(self._dst)
 
     def local_var(self):
+        self._ensure_host()
         g = Graph.__new__(Graph)
         g._n, g._src, g._dst = self._n, self._src, self._dst
         g.ndata, g.edata = dict(self.ndata), dict(self.edata)

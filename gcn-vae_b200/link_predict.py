@@ -74,7 +74,7 @@ class LinkPredict(nn.Module):
         torch.distributed.all_reduce(counts, group=part.group)
         z_full = parallel.AllGatherRowsFn.apply(embed, part)
         predict_loss = ops.DistMultBceFn.apply(z_full, self.w_relation, trip, lab, self._flow_shift())
-        predict_loss = predict_loss * (trip.shape[0] / float(counts.item()))
+        predict_loss = predict_loss * (float(trip.shape[0]) / counts).reshape(())      # device scalar: no host sync
         frac = part.n_local / part.n_global
         reg_loss = ops.MeanSquareFn.apply(embed) * frac + ops.MeanSquareFn.apply(self.w_relation) / part.world_size
         zero = lambda: torch.zeros(1, device=dev)
@@ -84,10 +84,12 @@ class LinkPredict(nn.Module):
                 kl = kl + self.encoder.flow_log_prob / part.world_size
         else:
             kl = zero()
-        if self.mmd_param > 0:
-            raise NotImplementedError("the MMD term is not available in destination-partitioned training")
-        loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl
-        return loss, predict_loss, kl, zero()
+        if self.mmd_param > 0:            # every rank evaluates the same term on the same 200 + 200 rows
+            mmd = self.encoder.get_mmd_partitioned(embed, part) / part.world_size
+        else:
+            mmd = zero()
+        loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl + self.mmd_param * mmd
+        return loss, predict_loss, kl, mmd
 
 
 def node_norm_to_edge_norm(g, node_norm):

@@ -74,7 +74,11 @@ class KGVAE(nn.Module):
         x = self.rconv_layer_2(g, x, r, norm)
         eps = self.preset_eps
         if eps is None:
-            eps = torch.randn((x.shape[0], self.h_dim), device=x.device)
+            part = getattr(g, "partition", None)
+            # partitioned: replicated parameters need the same seed on every rank, so the rows of different
+            # ranks would otherwise draw identical noise - each rank samples from its own generator
+            gen = None if part is None else part.noise_generator(x.device)
+            eps = torch.randn((x.shape[0], self.h_dim), device=x.device, generator=gen)
         self.z_mean, self.z_sigma, z = ops.ReparamFn.apply(x, eps)
         if self.n_flows > 0:
             log_det_sum = None
@@ -113,6 +117,36 @@ class KGVAE(nn.Module):
             for flow in self.nf:
                 z_pri, _ = flow.forward(z_pri)
         z_post = z[random.sample(range(z.shape[0]), num_sample)]
+        return (self.compute_kernel(z_pri, z_pri).mean() + self.compute_kernel(z_post, z_post).mean()
+                - 2 * self.compute_kernel(z_pri, z_post).mean())
+
+    def get_mmd_partitioned(self, z_local, part):
+        """get_mmd for destination-partitioned training (kgvae/model.py:89-102): the 200 posterior rows are
+        drawn among ALL nodes (rank 0 draws, everyone receives the ids), each rank contributes the rows it
+        owns and a differentiable sum over the ranks assembles them everywhere; the 200 prior samples use
+        noise broadcast from rank 0, so every rank computes the same value (the caller divides by the world
+        size: losses are summed over the ranks)."""
+        import torch.distributed as dist
+        from . import parallel
+        num_sample = 200
+        dev = z_local.device
+        src_rank = dist.get_global_rank(part.group, 0) if part.group is not None else 0
+        ids = torch.tensor(random.sample(range(part.n_global), num_sample), dtype=torch.int64, device=dev)
+        dist.broadcast(ids, src=src_rank, group=part.group)
+        mine = (ids >= part.lo) & (ids < part.hi)
+        rows = torch.zeros((num_sample, z_local.shape[1]), dtype=z_local.dtype, device=dev)
+        rows = rows.index_put((torch.nonzero(mine).reshape(-1),), z_local[(ids[mine] - part.lo)])
+        z_post = parallel.AllReduceSumFn.apply(rows, part.group)
+        m_mix, s_mix = utils.gaussian_parameters(self.z_pre, dim=1)
+        repeat = num_sample // self.k
+        sd = torch.cat([torch.sqrt(s_mix.squeeze())] * repeat, dim=0) if repeat > 1 else torch.sqrt(s_mix)
+        mean = torch.cat([m_mix.squeeze()] * repeat, dim=0) if repeat > 1 else m_mix
+        noise = torch.randn_like(sd)
+        dist.broadcast(noise, src=src_rank, group=part.group)
+        z_pri = mean + noise * sd
+        if self.n_flows > 0:
+            for flow in self.nf:
+                z_pri, _ = flow.forward(z_pri)
         return (self.compute_kernel(z_pri, z_pri).mean() + self.compute_kernel(z_post, z_post).mean()
                 - 2 * self.compute_kernel(z_pri, z_post).mean())
 

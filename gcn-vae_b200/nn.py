@@ -58,21 +58,22 @@ class RelGraphConv(nn.Module):
         # feed the same mask to this layer and to the oracle (CUDA Philox != CPU MT)
         self.dropout_mask = None
 
-    def _keep_mask(self, n, device):
+    def _keep_mask(self, n, device, part=None):
         if self.dropout_mask is not None:
             return self.dropout_mask
         p = self.dropout.p
         if not self.training or p == 0.0:
             return None
         keep = 1.0 - p
-        return torch.empty((n, self.out_feat), device=device).bernoulli_(keep).div_(keep)
+        gen = None if part is None else part.noise_generator(device)     # per-rank stream (see KGVAE.forward)
+        return torch.empty((n, self.out_feat), device=device).bernoulli_(keep, generator=gen).div_(keep)
 
     def forward(self, g, x, etypes, norm=None):
         if not x.is_cuda:
             raise RuntimeError("kgvae_b200.RelGraphConv runs on CUDA only (no CPU fallback)")
         act_code, post = _classify_activation(self.activation)
         part = getattr(g, "partition", None)
-        mask = self._keep_mask(x.shape[0], x.device)
+        mask = self._keep_mask(x.shape[0], x.device, part)
         # integer-id features walk node-major lists as well: have them built with the first index
         id_feats = x.dim() == 1 and x.dtype in (torch.int64, torch.int32)
         gi = g.index_for(etypes, norm, self.num_rels, node_major=id_feats)

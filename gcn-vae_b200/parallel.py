@@ -25,6 +25,15 @@ def world():
     return 0, 1
 
 
+def agree_scalar(value, op, group=None):
+    """All-reduce of one integer over the group (on the backend's device type): the ranks leave with the
+    same number, so decisions derived from it are taken identically everywhere."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=op, group=group)
+    return int(t.item())
+
+
 def block_range(n, rank, world_size):
     """Contiguous block [lo, hi) of ``n`` items owned by ``rank``; sizes differ by at most one."""
     return (n * rank) // world_size, (n * (rank + 1)) // world_size
@@ -59,6 +68,85 @@ def allreduce_mean_grads(params, group=None):
         else:
             p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+class GradBuckets:
+    """Replica training: gradients live in ONE persistent flat buffer (``p.grad`` is a view of it) cut into
+    buckets, and a bucket is all-reduced (NCCL, asynchronously, on the communicator's stream) the moment the
+    last of its parameters has received its gradient - from autograd's post-accumulate hooks, i.e. while
+    the rest of the backward pass is still running.  Replaces the post-backward ``torch.cat`` + one
+    all-reduce + copy-back of allreduce_mean_grads: no flatten, no copy back, and only the bucket that
+    becomes ready last (the entity embedding, whose gradient backward produces at the very end) is exposed.
+
+    ``buckets``: list of parameter lists in the order their gradients become ready (decoder / prior first,
+    embedding last); parameters not listed form a final bucket.  Call ``zero()`` instead of
+    ``optimizer.zero_grad()`` (one memset; the views must stay in place) and ``finish()`` after
+    ``loss.backward()``; ``average``: divide by the world size (replicas) or keep the sum (partitioned)."""
+
+    def __init__(self, params, buckets=None, group=None, average=True):
+        params = [p for p in params if p.requires_grad]
+        listed = {id(p) for b in (buckets or []) for p in b}
+        groups = [[p for p in b if p.requires_grad] for b in (buckets or [])]
+        rest = [p for p in params if id(p) not in listed]
+        if rest:
+            groups.append(rest)
+        self.groups = [g for g in groups if g]
+        self.group, self.average = group, average
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        total = sum(p.numel() for g in self.groups for p in g)
+        dev = self.groups[0][0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices, self._bucket_of, self._pending, self._handles = [], {}, [], []
+        off = 0
+        for b, g in enumerate(self.groups):
+            start = off
+            for p in g:
+                n = p.numel()
+                p.grad = self.flat[off:off + n].view_as(p)
+                self._bucket_of[id(p)] = b
+                p.register_post_accumulate_grad_hook(self._hook)
+                off += n
+            self.slices.append(self.flat[start:off])
+        self._reset()
+
+    def _reset(self):
+        self._pending = [len(g) for g in self.groups]
+        self._handles = []
+
+    def _hook(self, p):
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.world_size > 1:
+            self._launch(b)
+
+    def _launch(self, b):
+        op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") else dist.ReduceOp.SUM
+        h = dist.all_reduce(self.slices[b], op=op, group=self.group, async_op=True)
+        self._handles.append((h, b, op))
+
+    def zero(self):
+        self.flat.zero_()
+        self._reset()
+
+    def clip_(self, max_norm):
+        """torch.nn.utils.clip_grad_norm_ over all bucketed gradients (kgvae/link_predict.py:227) on the flat
+        buffer: one norm, one scale, no per-parameter launches and no host sync."""
+        total = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total
+
+    def finish(self):
+        """Wait for the bucket all-reduces (stream-ordered: the current stream waits, the host does not block
+        beyond NCCL's own enqueue) and launch any bucket whose parameters received no gradient this step."""
+        if self.world_size > 1:
+            for b, n in enumerate(self._pending):
+                if n > 0:                     # unused parameters: zeros on this rank, still part of the layout
+                    self._launch(b)
+            for h, b, op in self._handles:
+                h.wait()
+                if self.average and op == dist.ReduceOp.SUM:
+                    self.slices[b].div_(self.world_size)
+        self._reset()
 
 
 def sharded_rank_counts(count_fn, num_entities, group=None):
@@ -134,23 +222,42 @@ class Partition:
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         # uniform blocks (uniform_block_range) allow the fused peer-memory gather: the kernel finds
-        # the owner of a source row as row // blk
+        # the owner of a source row as row // blk.  Whether the blocks are uniform is a property of the
+        # whole partition, so it is AGREED across the ranks (one MIN all-reduce), not inferred per rank:
+        # ranks that disagreed would pad their all-gathers differently or issue mismatched collectives.
         blk = (self.n_global + self.world_size - 1) // self.world_size
-        uniform = (self.lo, self.hi) == uniform_block_range(self.n_global, self.rank, self.world_size)
+        mine = (self.lo, self.hi) == uniform_block_range(self.n_global, self.rank, self.world_size)
+        uniform = bool(agree_scalar(1 if mine else 0, dist.ReduceOp.MIN, group))
         self.blk = blk if uniform else None
         # None: decide per graph (use_peer_gather); True/False: forced (True still needs uniform blocks)
         self.peer_gather = None if peer_gather is None else (bool(peer_gather) and uniform)
+        self._peer_decision = None
+        self._noise_gen = None
         self._peer_rows = {}
 
     def use_peer_gather(self, n_local_edges):
         """Fused peer-memory gather or NCCL all-gather for a layer input?  Peer loads bypass the local
         L2, so the gather moves one row per EDGE whose source is remote, the all-gather one row per
-        remote NODE: gather from peers when this rank has fewer edges than the graph has nodes."""
+        remote NODE: gather from peers when a rank has, on average, fewer edges than the graph has nodes.
+        The decision is collective (one SUM all-reduce of the local edge counts on first use, then
+        cached): every rank of the job takes the same branch, whatever its own share of the edges."""
         if self.blk is None:
             return False
         if self.peer_gather is not None:
             return self.peer_gather
-        return int(n_local_edges) < self.n_global
+        if self._peer_decision is None:
+            total = agree_scalar(int(n_local_edges), dist.ReduceOp.SUM, self.group)
+            self._peer_decision = total < self.n_global * self.world_size
+        return self._peer_decision
+
+    def noise_generator(self, device):
+        """Device generator seeded ``torch.initial_seed() + 1 + rank``: the reparameterisation noise and the
+        dropout masks of a rank's node block must be independent of the other ranks' (replicated parameters
+        require the SAME default seed everywhere, which would give every block identical draws)."""
+        if self._noise_gen is None:
+            self._noise_gen = torch.Generator(device=device)
+            self._noise_gen.manual_seed((torch.initial_seed() + 1 + self.rank) % (1 << 62))
+        return self._noise_gen
 
     def peer_rows(self, key, width, device):
         """The PeerRows buffer of one layer (created collectively on first use, then reused)."""

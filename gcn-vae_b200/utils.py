@@ -285,24 +285,31 @@ class DevicePrefetcher:
     """Double-buffered host -> device staging of step inputs (the ``.cuda()`` copies of
     kgvae/link_predict.py:217-220) on a side stream: ``submit`` starts the copies of a dict of
     pinned host tensors into one of ``depth`` persistent device buffer sets, ``take`` hands that
-    set to the current stream once the copies have landed.  Submitting step i+1 before running
-    step i hides the copy behind the step's kernels.  A set is overwritten only after the work
-    that was enqueued on the consumer stream before the following ``take`` has finished with it."""
+    set to the current stream once the copies have landed.  Call order per step: ``take()`` (set i),
+    ``submit()`` (set i + 1), then run step i - the copy of step i + 1 overlaps step i's kernels.  Any
+    other order is still safe (a set is only overwritten after everything the consumer stream had enqueued
+    at ``submit`` time), it merely overlaps less."""
 
     def __init__(self, device, depth=2):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
         self._slots = [None] * depth
-        self._free = [None] * depth        # event: the slot's last consumer work is enqueued up to here
+        self._used = [False] * depth       # the set has been handed to the consumer stream at least once
         self._count = 0
         self._pending = []
-        self._last = None
 
     def submit(self, host_tensors):
         slot = self._count % len(self._slots)
         self._count += 1
-        if self._free[slot] is not None:
-            self.stream.wait_event(self._free[slot])
+        cur = torch.cuda.current_stream(self.device)
+        if self._used[slot]:
+            # the set being overwritten was handed out before: everything the consumer stream has enqueued up
+            # to NOW may still read it (whatever order take / submit / run were called in), so the copies wait
+            # for that point.  In the intended order - take(i), submit(i + 1), run step i - this is the end of
+            # step i - 1, the set's last reader; step i is not enqueued yet and overlaps the copy.
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
             bufs = self._slots[slot]
             if bufs is None or any(k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype
@@ -318,10 +325,9 @@ class DevicePrefetcher:
     def take(self):
         slot, done = self._pending.pop(0)
         cur = torch.cuda.current_stream(self.device)
-        if self._last is not None:         # everything enqueued so far may still read the previous set
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self._free[self._last] = ev
-        self._last = slot
+        self._used[slot] = True
         cur.wait_event(done)
-        return {k: self._slots[slot][k] for k in self._slots[slot]}
+        out = {k: self._slots[slot][k] for k in self._slots[slot]}
+        for t in out.values():             # allocated on the side stream, read on this one
+            t.record_stream(cur)
+        return out

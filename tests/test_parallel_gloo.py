@@ -39,6 +39,22 @@ def _worker(rank, port, out):
         parallel.allreduce_mean_grads(params)
         res["grads"] = [p.grad.clone() for p in params]
 
+        # --- replicas, bucketed: gradients are views of one flat buffer, buckets all-reduced from hooks ------
+        torch.manual_seed(1)
+        bp = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(6)), torch.nn.Parameter(torch.randn(2))]
+        buckets = parallel.GradBuckets(bp, buckets=[[bp[1]], [bp[0]]])      # bp[2] lands in the trailing bucket
+        for it in range(2):
+            buckets.zero()
+            scale = float(rank + 1 + it)
+            (bp[0].sum() * scale + (bp[1] * bp[1]).sum() * scale).backward()       # bp[2] unused: zeros
+            buckets.finish()
+        norm_before = float(buckets.flat.norm())
+        buckets.clip_(0.5)
+        res["bucket_grads"] = [p.grad.clone() for p in bp]
+        res["bucket_views"] = all(p.grad.data_ptr() >= buckets.flat.data_ptr() and
+                                  p.grad.data_ptr() < buckets.flat.data_ptr() + 4 * buckets.flat.numel() for p in bp)
+        res["bucket_norms"] = (norm_before, float(buckets.flat.norm()), [x.detach().clone() for x in bp])
+
         # --- entity-sharded evaluation: shard counts add up ----------------------------------
         rng = np.random.default_rng(5)
         V, h, M = 101, 16, 37
@@ -82,9 +98,17 @@ def _worker(rank, port, out):
         uparts = parallel.partition_by_destination(src, dst, et, None, N, WORLD, uniform=True)
         um = uparts[rank]
         upart = parallel.Partition(um["lo"], um["hi"], N)
-        res["uniform"] = (um["lo"], um["hi"], upart.blk,
-                          upart.use_peer_gather(N - 1) and not upart.use_peer_gather(N) and not part.use_peer_gather(1),
-                          part.blk)
+        # the gather / all-gather choice is COLLECTIVE: ranks with very different edge counts (and peer_gather
+        # left to None) must come out with the same answer - average edges per rank < nodes -> peer gather
+        few = parallel.Partition(um["lo"], um["hi"], N)
+        many = parallel.Partition(um["lo"], um["hi"], N)
+        d_few = few.use_peer_gather(5 if rank == 0 else 40)          # 45 < 2 * 23
+        d_many = many.use_peer_gather(5 if rank == 0 else 60)        # 65 >= 46
+        d_cached = few.use_peer_gather(10 ** 6)                      # cached: no second collective, same answer
+        # blocks are uniform only if EVERY rank's block is: rank 1 hands over a shorter block here
+        ragged = parallel.Partition(um["lo"], um["hi"] - (1 if rank == 1 else 0), N)
+        res["collective"] = (d_few, d_many, d_cached, ragged.blk, ragged.use_peer_gather(1))
+        res["uniform"] = (um["lo"], um["hi"], upart.blk, not part.use_peer_gather(1), part.blk)
         ufull = parallel.allgather_rows(feats[um["lo"]:um["hi"]], N, uniform=True)
         res["uniform_gathered_ok"] = bool(torch.equal(ufull, feats))
         contrib = torch.arange(WORLD * upart.blk * 3, dtype=torch.float32).view(-1, 3) * (rank + 1)
@@ -109,6 +133,14 @@ def test_two_rank_host_logic():
         assert torch.equal(res[r]["grads"][2], torch.zeros(2, 2))
         assert torch.equal(res[r]["ranks"].long(), res[r]["want_ranks"])
         assert res[r]["gathered_ok"]
+    # bucketed replicas: second iteration's scales are rank + 2 -> mean 2.5 over the two ranks
+    for r in range(WORLD):
+        nb, na, bp = res[r]["bucket_norms"]
+        want = [torch.full((4, 3), 2.5), 2 * bp[1] * 2.5, torch.zeros(2)]
+        coef = min(1.0, 0.5 / (nb + 1e-6))
+        for got, w_ in zip(res[r]["bucket_grads"], want):
+            assert torch.allclose(got, w_ * coef, rtol=1e-5, atol=1e-6)
+        assert res[r]["bucket_views"] and abs(na - min(nb, 0.5)) < 1e-4
     # all-gather backward = sum over ranks of the gradient rows; all-reduce backward = sum of upstream grads
     wsum = torch.arange(23 * 3, dtype=torch.float32).view(23, 3) * sum(r + 1 for r in range(WORLD))
     for r in range(WORLD):
@@ -120,6 +152,7 @@ def test_two_rank_host_logic():
     for r in range(WORLD):
         lo, hi, blk, peer_ok, blk_nonuniform = res[r]["uniform"]
         assert (lo, hi, blk) == ((0, 12, 12) if r == 0 else (12, 23, 12)) and peer_ok and blk_nonuniform is None
+        assert res[r]["collective"] == (True, False, True, None, False), res[r]["collective"]
         assert res[r]["uniform_gathered_ok"]
         assert torch.equal(res[r]["rs_rows"], total[lo:hi])
     # partition: every edge exactly once, owned by the rank whose node block holds its destination
