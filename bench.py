@@ -364,32 +364,16 @@ def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edge
     return out
 
 
-def run_partitioned(args):
-    """--workload wikikg2-part (BASELINE.json configs[4]): full-graph GCN-VAE training step on a synthetic
-    ogbl-wikikg2-shaped KG (2.5 M entities, 535 relations, 16 M triples = 32 M directed edges, h = 500,
-    100 blocks), destination-partitioned over the N GPUs of one box: rank p owns a block of nodes, every
-    edge into it, and its rows of the embedding table / h1 / h2 / z.  Layer inputs are NOT all-gathered:
-    the message-passing kernels gather source rows from the owners' HBM over NVLink (peer row blocks);
-    gradients wrt the sources are reduce-scattered; the decoder scores 2.2 M sampled triplets (split over
-    the ranks) against the all-gathered z.  STRONG scaling: the graph is fixed, value = 32 M edges / step
-    time (max over ranks).  N = 1 runs the same step unpartitioned."""
+def partitioned_leg(args, dev, world, rank, log, allgather, steps, warmup, scale):
+    """One measurement of the destination-partitioned wikikg2-shaped training step (see run_partitioned) on the
+    already initialised process group; returns a dict (every rank; timing = max over ranks)."""
     import torch.distributed as dist
     import gcn_vae_b200 as K
     from gcn_vae_b200 import _lib as L
     from gcn_vae_b200 import parallel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
-    clocks = ClockSampler(local)
-    scale = args.scale
     n_nodes, n_rels, n_trip = int(2_500_000 * scale), 535, int(16_000_000 * scale)
-    n_scored = int(2_200_000 * scale)
+    n_scored = n_trip * (NEG + 1)          # every train triple + NEG corruptions each, as the reference scores them
     # the same global graph on every rank (same device generator seed), then this rank's share
     gen = torch.Generator(device=dev).manual_seed(1234)
     s = torch.randint(0, n_nodes, (n_trip,), device=dev, generator=gen, dtype=torch.int32)
@@ -397,18 +381,26 @@ def run_partitioned(args):
     r = torch.randint(0, n_rels, (n_trip,), device=dev, generator=gen, dtype=torch.int32)
     src, dst, et = torch.cat([s, o]), torch.cat([o, s]), torch.cat([r, r + n_rels])     # + reverse edges
     deg = torch.bincount(dst.long(), minlength=n_nodes).clamp_(min=1).float()
-    trip = torch.stack([torch.randint(0, n_nodes, (n_scored,), device=dev, generator=gen, dtype=torch.int32),
-                        torch.randint(0, n_rels, (n_scored,), device=dev, generator=gen, dtype=torch.int32),
-                        torch.randint(0, n_nodes, (n_scored,), device=dev, generator=gen, dtype=torch.int32)], 1)
-    labels = (torch.rand(n_scored, device=dev, generator=gen) < 1.0 / (NEG + 1)).float()
     n_edges_global = int(src.numel())
+    # this rank's share of the scored triplets: positives + corruptions (subject or object replaced at random)
+    t0, t1 = parallel.block_range(n_trip, rank, world)
+    gen_t = torch.Generator(device=dev).manual_seed(99 + rank)
+    pos = torch.stack([s[t0:t1], r[t0:t1], o[t0:t1]], 1)
+    neg = pos.repeat(NEG, 1)
+    vals = torch.randint(0, n_nodes, (neg.shape[0],), device=dev, generator=gen_t, dtype=torch.int32)
+    head = torch.rand(neg.shape[0], device=dev, generator=gen_t) > 0.5
+    neg[:, 0] = torch.where(head, vals, neg[:, 0])
+    neg[:, 2] = torch.where(head, neg[:, 2], vals)
+    trip = torch.cat([pos, neg]).contiguous()
+    labels = torch.zeros(trip.shape[0], device=dev)
+    labels[:pos.shape[0]] = 1
+    del pos, neg, vals, head
     if world > 1:
         lo, hi = parallel.uniform_block_range(n_nodes, rank, world)
         keep = (dst >= lo) & (dst < hi)
         src, dst, et = src[keep].contiguous(), (dst[keep] - lo).contiguous(), et[keep].contiguous()
         norm = (1.0 / deg)[lo:hi][dst.long()].contiguous()
-        t0, t1 = parallel.block_range(n_scored, rank, world)
-        trip, labels = trip[t0:t1].contiguous(), labels[t0:t1].contiguous()
+        del keep
     else:
         lo, hi = 0, n_nodes
         norm = (1.0 / deg)[dst.long()].contiguous()
@@ -418,24 +410,24 @@ def run_partitioned(args):
     g._n = n_nodes if world > 1 else n_local
     g._dev_edges[dev] = (src, dst)
     if world > 1:
-        g.partition = parallel.Partition(lo, hi, n_nodes, peer_gather=not args.allgather)
+        g.partition = parallel.Partition(lo, hi, n_nodes, peer_gather=not allgather)
     torch.manual_seed(0)
     # the embedding table is sharded by owner: each rank holds (and updates) only its rows
     model = K.LinkPredict(K.KGVAE, max(n_local, 1), H, n_rels, num_bases=BASES, dropout=DROPOUT, use_cuda=True,
                           reg_param=REG, kl_param=KL, k=MOG_K, n_flows=0).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-    sharded = {id(model.encoder.input_layer.embedding.weight)}
-    replicated = [p for p in model.parameters() if p.requires_grad and id(p) not in sharded]
+    emb_w = model.encoder.input_layer.embedding.weight
+    buckets = model.grad_buckets(average=False, sharded=[emb_w])       # replicated parameters: SUM over the ranks
     ids = torch.arange(n_local, dtype=torch.int32, device=dev).view(-1, 1)
     norm2 = norm.view(-1, 1)
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        buckets.zero()
+        emb_w.grad = None
         embed = model(g, ids, et, norm2)
         loss, _, _, _ = model.get_loss(g, embed, trip, labels)
         loss.backward()
-        if world > 1:
-            parallel.allreduce_sum_grads(replicated)
+        buckets.finish()
         opt.step()
         return loss
 
@@ -446,15 +438,14 @@ def run_partitioned(args):
             torch.cuda.synchronize()
 
     model.train()
-    clocks.mark()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     sync_all()
     L.launches = 0
     L.profile = {}
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     b.record()
     b.synchronize()
@@ -466,26 +457,62 @@ def run_partitioned(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    op_ms = {tag: sum(x.elapsed_time(y) for x, y in evs) / steps for tag, evs in prof.items()}
+    for tag, v in sorted(op_ms.items(), key=lambda kv: -kv[1])[:10]:
+        log(f"  [wikikg2-part x{world}] {tag:44s} {v:8.3f} ms/step")
+    loss_v = float(loss)
+    if world > 1:
+        for cache in g.partition._peer_rows.values():
+            cache.close()
+    res = {"ms_per_step": ms / steps, "edges_per_s": n_edges_global * steps / (ms * 1e-3), "n_gpus": world,
+           "steps": steps, "warmup": max(warmup, 3), "loss": loss_v, "gpu_launches": launches,
+           "entities": n_nodes, "relations": n_rels, "graph_edges": n_edges_global,
+           "scored_triplets": n_scored, "scale": scale,
+           "mode": ("single GPU, unpartitioned" if world == 1 else
+                    "NCCL all-gather of layer inputs (async, overlapped with the self-loop GEMM)" if allgather else
+                    "layer inputs gathered from peer HBM by the message-passing kernels (NVLink, CUDA IPC)"),
+           "top_ops_ms": dict(sorted(op_ms.items(), key=lambda kv: -kv[1])[:8])}
+    del model, opt, buckets, g, trip, labels, src, dst, et, norm, norm2, ids
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_partitioned(args):
+    """--workload wikikg2-part (BASELINE.json configs[4]): full-graph GCN-VAE training step on a synthetic
+    ogbl-wikikg2-shaped KG (2.5 M entities, 535 relations, 16 M triples = 32 M directed edges, 176 M scored
+    triplets = every triple + 10 corruptions, h = 500, 100 blocks), destination-partitioned over the N GPUs of
+    one box: rank p owns a block of nodes, every edge into it, and its rows of the embedding table / h1 / h2 /
+    z.  Layer inputs reach the edges either by an NCCL all-gather (asynchronous, overlapped with the self-loop
+    GEMM; default) or, with --peer, straight from the owners' HBM inside the message-passing kernels; gradients
+    wrt the sources are reduce-scattered (overlapped with the weight-gradient GEMM); the decoder scores each
+    rank's share of the triplets against the all-gathered z.  STRONG scaling: the graph is fixed, value =
+    32 M edges / step time (max over ranks).  N = 1 runs the same step unpartitioned."""
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    clocks = ClockSampler(local)
+    clocks.mark()
+    r = partitioned_leg(args, dev, world, rank, log, allgather=not args.peer, steps=args.steps, warmup=args.warmup,
+                        scale=args.scale)
     clock_info = clocks.stop()
     if rank == 0:
-        op_ms = {tag: sum(x.elapsed_time(y) for x, y in evs) for tag, evs in prof.items()}
-        total_ops = sum(op_ms.values())
-        for tag, v in sorted(op_ms.items(), key=lambda kv: -kv[1])[:12]:
-            log(f"  {tag:44s} {v / args.steps:8.3f} ms/step  {100 * v / total_ops:5.1f}%")
         line = {
-            "metric": METRIC, "value": n_edges_global * args.steps / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "metric": METRIC, "value": r["edges_per_s"], "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "wikikg2-part", "entities": n_nodes, "relations": n_rels, "graph_edges": n_edges_global,
-                       "scored_triplets": n_scored, "h": H, "bases": BASES, "scale": scale,
-                       "parallelism": (f"destination-partitioned x{world}, "
-                                       + ("NCCL all-gather of layer inputs" if args.allgather else
-                                          "layer inputs gathered from peer HBM by the message-passing kernels (NVLink)")
-                                       + ", reduce-scatter of source gradients, all-gather of z for the decoder")
-                                      if world > 1 else "single GPU, unpartitioned",
+            "config": {"workload": "wikikg2-part", "entities": r["entities"], "relations": r["relations"],
+                       "graph_edges": r["graph_edges"], "scored_triplets": r["scored_triplets"], "h": H, "bases": BASES,
+                       "scale": args.scale, "parallelism": f"destination-partitioned x{world}: " + r["mode"],
                        "timed": "fwd + loss + bwd + grad all-reduce + Adam; one CUDA-event pair over all steps",
                        "l2": "inputs (5 GB feature matrices) far larger than L2"},
-            "loss": float(loss), "gpu_launches": launches, "clocks": clock_info,
+            "loss": r["loss"], "gpu_launches": r["gpu_launches"], "clocks": clock_info, "top_ops_ms": r["top_ops_ms"],
         }
         print(json.dumps(line))
     if world > 1:
@@ -674,7 +701,9 @@ def run_gpu(args):
     model = K.LinkPredict(K.KGVAE, data.num_nodes, H, data.num_rels, num_bases=BASES, dropout=DROPOUT,
                           use_cuda=True, reg_param=REG, kl_param=KL, k=MOG_K, n_flows=args.n_flows).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-    params = [p for p in model.parameters() if p.requires_grad]
+    # gradients are views of one flat buffer cut into buckets; with N > 1 a bucket is all-reduced (averaged) as soon
+    # as backward has produced it, overlapping the rest of backward; clipping runs on the flat buffer
+    buckets = model.grad_buckets()
 
     # ---- the step's inputs: the reference's own host sampler (weak scaling: one sample per rank) --
     t0 = time.perf_counter()
@@ -695,17 +724,68 @@ def run_gpu(args):
         gr._dev_edges[dev] = (t["src"], t["dst"])
         return gr
 
-    def step(t):
-        gr = make_graph(t)                                  # fresh graph: the index is rebuilt
-        opt.zero_grad(set_to_none=True)
-        embed = model(gr, t["node_id"].view(-1, 1), t["etype"], t["norm"])
-        loss, _, _, _ = model.get_loss(gr, embed, t["samples"], t["labels"])
+    def train_step(gr, node_id_t, etype_t, norm_t, samples_t, labels_t):
+        buckets.zero()
+        embed = model(gr, node_id_t, etype_t, norm_t)
+        loss, _, _, _ = model.get_loss(gr, embed, samples_t, labels_t)
         loss.backward()
-        if world > 1:                                       # replicas: average gradients over NVLink
-            K.parallel.allreduce_mean_grads(params)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        buckets.finish()                                    # replicas: bucket all-reduces launched during backward
+        buckets.clip_(1.0)
         opt.step()
         return loss
+
+    def step(t):
+        gr = make_graph(t)                                  # fresh graph: the index is rebuilt
+        return train_step(gr, t["node_id"].view(-1, 1), t["etype"], t["norm"], t["samples"], t["labels"])
+
+    def pinned_sample(seed):
+        """One fresh sample from the reference's host sampler as pinned int32 / fp32 tensors."""
+        g2, nid, et2, nn2, sm2, lb2 = sample_step(K.utils, data, batch, seed=seed)
+        return {"node_id": pin(nid, torch.int32), "src": pin(g2._src, torch.int32), "dst": pin(g2._dst, torch.int32),
+                "etype": pin(et2, torch.int32), "norm": pin(nn2[g2._dst].reshape(-1, 1), torch.float32),
+                "samples": pin(sm2, torch.int32), "labels": pin(lb2, torch.float32)}, len(nid)
+
+    def timed_with_host_sampler(n_steps, threaded):
+        """The loop of kgvae/link_predict.py:200-236 with a FRESH sample every step: host sampler (numpy, the
+        reference's random stream) + H2D copies + edge index + step + loss read-back.  `threaded`: the sampler
+        runs one step ahead in a worker thread (the bit-exact stream is kept: one thread owns np.random)."""
+        import queue
+        q = queue.Queue(maxsize=2)
+        if threaded:
+            def producer():
+                for i in range(n_steps):
+                    q.put(pinned_sample(5000 + i))
+            th = threading.Thread(target=producer, daemon=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if threaded:
+            th.start()
+        for i in range(n_steps):
+            hs, n_i = q.get() if threaded else pinned_sample(5000 + i)
+            t = {k: v.to(dev, non_blocking=True) for k, v in hs.items()}
+            gr = K.Graph()
+            gr._n = n_i
+            gr._dev_edges[dev] = (t["src"], t["dst"])
+            float(train_step(gr, t["node_id"].view(-1, 1), t["etype"], t["norm"], t["samples"], t["labels"]).detach())
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    train_dev = torch.from_numpy(np.asarray(data.train)).to(dev)
+    samp_gen = torch.Generator(device=dev).manual_seed(77 + rank)
+
+    def timed_with_device_sampler(n_steps):
+        """Same loop with utils.generate_sampled_graph_and_labels_device (--device-sampler): the uniform edge
+        sample, relabelling, negatives, graph split and edge index all on the GPU; nothing crosses PCIe but the
+        loss read-back."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_steps):
+            gr, nid, et2, en2, sm2, lb2 = K.utils.generate_sampled_graph_and_labels_device(
+                train_dev, batch, 0.5, data.num_rels, NEG, generator=samp_gen)
+            float(train_step(gr, nid, et2, en2, sm2, lb2).detach())
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b)
 
     def e2e_step():
         t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -773,6 +853,14 @@ def run_gpu(args):
     sync_all()
     ms_e2e = max_over_ranks(timed_e2e(args.steps))
     sync_all()
+    # end to end INCLUDING the sampler (fresh sample every step), three ways
+    timed_with_device_sampler(2)
+    sync_all()
+    ms_dev_sampler = max_over_ranks(timed_with_device_sampler(args.steps)) / args.steps
+    n_host = 3
+    ms_host_sampler = max_over_ranks(timed_with_host_sampler(n_host, threaded=False)) / n_host
+    ms_host_threaded = max_over_ranks(timed_with_host_sampler(n_host, threaded=True)) / n_host
+    sync_all()
 
     # ---- L2 throughput of this GPU for whole-row gathers / reductions (roofline denominator) --------
     l2_peak = None
@@ -832,6 +920,29 @@ def run_gpu(args):
     filt_ok = bool((rk_filt <= rk_raw).all())              # filtering can only improve a rank
     sync_all()
     clock_info = clocks.stop()
+
+    # ---- BASELINE.json configs[4] inside the default job: the destination-partitioned wikikg2-shaped step at
+    # this N (strong scaling; N = 1 is the unpartitioned denominator), and at N > 1 the partition parity checks
+    partitioned = None
+    if not args.no_partitioned and args.workload == "fb15k237-full":
+        model = opt = buckets = None
+        del resident
+        torch.cuda.empty_cache()
+        partitioned = {"what": "full-graph GCN-VAE train step, ogbl-wikikg2 shape (2.5 M entities, 32 M directed "
+                               "edges, 176 M scored triplets), destination-partitioned over the N GPUs; strong "
+                               "scaling: edges_per_s = 32 M / step time (max over ranks)", "modes": {}}
+        if world > 1:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import partition_selfcheck
+            partitioned["parity"] = partition_selfcheck.run_all(K, dev, rank, world)      # asserts
+            log(f"  partition parity checks passed: {partitioned['parity']}")
+        for name, ag in ((("allgather", True), ("peer", False)) if world > 1 else (("single", True),)):
+            partitioned["modes"][name] = partitioned_leg(args, dev, world, rank, log, allgather=ag, steps=3, warmup=3,
+                                                         scale=args.scale)
+            log(f"  [wikikg2-part x{world}, {name}] {partitioned['modes'][name]['ms_per_step']:.1f} ms/step")
+        best = min(partitioned["modes"].values(), key=lambda m: m["ms_per_step"])
+        partitioned.update(ms_per_step=best["ms_per_step"], edges_per_s=best["edges_per_s"], n_gpus=world)
+        sync_all()
 
     if rank != 0:
         if world > 1:
@@ -909,7 +1020,7 @@ def run_gpu(args):
 
     streaming = None
     if world == 1 and not args.no_streaming:
-        model = opt = None
+        model = opt = buckets = None
         torch.cuda.empty_cache()
         streaming = streaming_layer_bench(dev, pk, log)
 
@@ -927,6 +1038,7 @@ def run_gpu(args):
     if roof is not None:
         roof["tensor"] = eval_roof
         roof["eval"] = eval_summary
+        roof["partitioned"] = partitioned
         if streaming:
             worst = min(((k_, v) for k_, v in streaming["kernels"]["uniform"].items()), key=lambda kv: kv[1]["frac_of_hbm_peak"])
             roof["hbm"] = {"kernel": worst[0] + " @ wikikg2 shape (2.5 M nodes, 32 M edges)", "bound": "hbm",
@@ -947,7 +1059,15 @@ def run_gpu(args):
         "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                 "how": "pinned host inputs copied every step inside the timed region (double-buffered on a side "
-                       "stream: step i+1's copy overlaps step i), loss read back every step, L2 flush inside"},
+                       "stream: step i+1's copy overlaps step i), loss read back every step, L2 flush inside",
+                "with_sampler": {
+                    "what": "kgvae/link_predict.py:200-236 with a FRESH sample every step: sampler + copies + edge "
+                            "index + step + loss read-back; ms per step, max over ranks",
+                    "device_sampler_ms": ms_dev_sampler, "device_sampler_edges_per_s": E * world / (ms_dev_sampler * 1e-3),
+                    "host_sampler_ms": ms_host_sampler, "host_sampler_edges_per_s": E * world / (ms_host_sampler * 1e-3),
+                    "host_sampler_threaded_ms": ms_host_threaded,
+                    "note": "the host sampler is the reference's numpy code (bit-exact sampled indices), single "
+                            "threaded by construction; --device-sampler is the fast path"}},
         "eval": {"value": T * args.steps / (ms_eval * 1e-3), "unit": "triples/s", "test_triples": T,
                  "candidates": data.num_nodes, "ms": ms_eval / args.steps, "setting": "raw, both directions",
                  "e2e_value": T * args.steps / (ms_eval_e2e * 1e-3), "mrr_raw_random_init": mrr_raw,
@@ -958,7 +1078,7 @@ def run_gpu(args):
                  "roofline": eval_roof},
         "scored_triplets_per_s": S * world * args.steps / (ms_dev * 1e-3),
         "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
-        "rgcn_streaming": streaming,
+        "rgcn_streaming": streaming, "partitioned": partitioned,
     }
     print(json.dumps(line))
     if world > 1:
@@ -980,8 +1100,11 @@ def main():
                     help="bdd blocks per relation (default 100; 25 at wn18 shape: DGL clamps num_bases to the "
                          "36 directed relation types, which does not divide 500)")
     ap.add_argument("--scale", type=float, default=1.0, help="wikikg2-part / am-entity: shrink the graph (tests)")
-    ap.add_argument("--allgather", action="store_true",
-                    help="wikikg2-part: NCCL all-gather of layer inputs instead of the peer-memory gather")
+    ap.add_argument("--peer", action="store_true",
+                    help="wikikg2-part: the message-passing kernels gather layer inputs from peer HBM (CUDA IPC over "
+                         "NVLink) instead of the NCCL all-gather")
+    ap.add_argument("--no-partitioned", action="store_true",
+                    help="skip the wikikg2-shaped destination-partitioned leg of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streaming-only", action="store_true",
                     help="run only the wikikg2-shaped message-passing leg (profiling aid; prints its JSON object)")

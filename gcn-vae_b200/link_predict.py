@@ -30,6 +30,23 @@ class LinkPredict(nn.Module):
         self.use_cuda, self.k, self.n_flows = use_cuda, k, n_flows
         nn.init.xavier_uniform_(self.w_relation, gain=nn.init.calculate_gain("relu"))
 
+    def grad_buckets(self, group=None, average=True, sharded=()):
+        """parallel.GradBuckets over this model's parameters, cut in the order backward produces the gradients:
+        decoder / prior / flows first, then the second and the first RelGraphConv, the entity embedding last
+        (its gradient is complete only at the very end of backward).  ``sharded``: parameters that are NOT
+        replicated (destination-partitioned training shards the embedding table) and are left out."""
+        from . import parallel
+        skip = {id(p) for p in sharded}
+        enc = self.encoder
+        named = dict(self.named_parameters())
+        pick = lambda prefix: [p for n, p in named.items() if n.startswith(prefix) and p.requires_grad and id(p) not in skip]
+        head = [p for n, p in named.items() if p.requires_grad and id(p) not in skip and
+                not n.startswith(("encoder.rconv_layer_", "encoder.input_layer", "encoder.layers"))]
+        order = [head, pick("encoder.rconv_layer_2"), pick("encoder.rconv_layer_1"), pick("encoder.layers"),
+                 pick("encoder.input_layer")]
+        params = [p for p in self.parameters() if p.requires_grad and id(p) not in skip]
+        return parallel.GradBuckets(params, buckets=[b for b in order if b], group=group, average=average)
+
     def _flow_shift(self):
         if self.n_flows > 0 and isinstance(self.encoder, KGVAE):
             return self.encoder.get_flow_log_prob()
@@ -127,7 +144,10 @@ def main(args):
     val_graph, val_rel, val_norm = utils.build_test_graph(num_nodes, num_rels, valid_t)
     val_node_id, val_rel, val_norm = _graph_inputs(val_graph, val_rel, val_norm, num_nodes, device)
     adj_list, degrees = utils.get_adj_and_degrees(num_nodes, train_data)
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, fused=True)
+    # gradients live in one flat buffer: zeroing is one memset, clipping one norm + one scale
+    # (same arithmetic as optimizer.zero_grad() / clip_grad_norm_ of kgvae/link_predict.py:227,236)
+    buckets = model.grad_buckets()
     forward_time, backward_time = [], []
 
     if args.test_mode:
@@ -179,7 +199,8 @@ def main(args):
         torch.cuda.synchronize()
         t1 = time.time()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), args.grad_norm)
+        buckets.finish()
+        buckets.clip_(args.grad_norm)
         optimizer.step()
         torch.cuda.synchronize()
         t2 = time.time()
@@ -187,7 +208,7 @@ def main(args):
         backward_time.append(t2 - t1)
         print("Epoch {:04d} | Loss {:.4f} | Best MRR {:.4f} | pred_loss {:.4f} | kl {:.4f} | mmd {:.4f}".format(
             epoch, loss.item(), best_mrr, pred_loss.item(), kl.item(), mmd.item()))
-        optimizer.zero_grad()
+        buckets.zero()
 
         if epoch % args.evaluate_every == 0:
             model.eval()

@@ -82,21 +82,19 @@ class RelGraphConv(nn.Module):
         if self.regularizer == "bdd":
             if x.dtype == torch.int64 and x.dim() == 1:
                 raise TypeError("Block decomposition does not allow integer ID feature.")
-            lo, n_dst, peer = -1, -1, None
+            gather, peer = False, None
             if part is not None:      # destination-partitioned
                 peer_ok = part.use_peer_gather(gi.n_edges) and not ops.L.lib().kg_bdd_layouts_needed(
                     self.num_bases, self.submat_in, self.submat_out)
                 if peer_ok:           # fused: the kernel gathers source rows from the owners' HBM
                     peer = part.peer_rows(id(self), self.in_feat, x.device)
-                else:                 # NCCL all-gather of every node's features first
-                    from . import parallel
-                    x = parallel.AllGatherRowsFn.apply(x, part)
-                    lo, n_dst = part.lo, part.n_local
+                else:                 # NCCL all-gather of every node's features, overlapped with the self-loop GEMM
+                    gather = True
             if post is None:
                 return ops.BddConvFn.apply(x, self.weight, loop_w, h_bias, gi, self.num_bases,
-                                           act_code, mask, lo, n_dst, peer, part)
+                                           act_code, mask, gather, peer, part)
             h = ops.BddConvFn.apply(x, self.weight, loop_w, h_bias, gi, self.num_bases,
-                                    _ACT_IDENTITY, None, lo, n_dst, peer, part)
+                                    _ACT_IDENTITY, None, gather, peer, part)
             h = post(h)
             return h if mask is None else h * mask
         from . import basis   # entity-classification layers (config 4)

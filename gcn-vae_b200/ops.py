@@ -218,77 +218,86 @@ class BddConvFn(torch.autograd.Function):
     """One RelGraphConv(bdd) layer: out = dropout(act(sum_e norm_e W_{r_e} x_src + h_bias +
     x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59.
 
-    Destination-partitioned forms (edge sources are global ids, destinations local ids, the layer
-    produces the rows of the nodes this rank owns):
-    * ``dst_lo``/``n_dst``: ``x`` holds the features of ALL nodes (all-gathered by the caller), the
-      self-loop uses ``x[dst_lo:dst_lo+n_dst]``;
-    * ``peer`` (parallel.PeerRows) + ``part``: ``x`` holds only this rank's rows; they are published
-      in the rank's peer-visible block and every rank's kernel gathers the source rows it needs
-      straight from the owners' HBM over NVLink (no all-gather); the gradient wrt the sources is
-      accumulated for all nodes and reduce-scattered to the owners."""
+    Order of work: the self-loop product (+ bias) is written FIRST, straight into the buffer the messages are
+    then reduced into (so there is no zero-fill pass), and activation + dropout mask are applied in place at
+    the end.  That order is what lets the destination-partitioned forms overlap their collective with the
+    GEMM, which only needs the rows this rank owns:
+
+    * ``part`` + ``gather``: ``x`` holds this rank's rows; the NCCL all-gather of all nodes' rows is started
+      asynchronously, the self-loop GEMM runs meanwhile, message passing waits for the gather.  Backward:
+      the reduce-scatter of the source gradients runs while the weight-gradient GEMM of the self-loop does.
+    * ``peer`` (parallel.PeerRows) + ``part``: ``x`` holds only this rank's rows; they are published in the
+      rank's peer-visible block and every rank's kernel gathers the source rows it needs straight from the
+      owners' HBM over NVLink (no all-gather); the gradient wrt the sources is accumulated for all nodes and
+      reduce-scattered to the owners.
+    Edge sources are global ids, destinations local ids; the layer produces the rows of the owned nodes."""
 
     @staticmethod
-    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask, dst_lo=-1, n_dst=-1,
+    def forward(ctx, x, weight, loop_weight, h_bias, gi, num_bases, act, drop_mask, gather=False,
                 peer=None, part=None):
         x, weight = _c(x), _c(weight)
         dev = x.device
-        n, in_feat = x.shape
+        n_own, in_feat = x.shape
         R = weight.shape[0]
         si = in_feat // num_bases
         so = weight.shape[1] // (num_bases * si)
         out_feat = num_bases * so
         needs_layouts = bool(L.lib().kg_bdd_layouts_needed(num_bases, si, so))
+        pending = None
         if peer is not None:
             if needs_layouts:
                 raise RuntimeError("RelGraphConv: the peer-memory gather needs 5x5 / 5x10 blocks")
-            n_out, x_own = n, x
             peer.publish(x)
-            src_args = (None, L.ptr(peer.ptrs), peer.blk)
             n_src_rows = peer.blk * peer.world_size
-        elif dst_lo < 0:
-            if n != gi.n_nodes:
-                raise RuntimeError(f"RelGraphConv: {n} feature rows for a graph of {gi.n_nodes} nodes")
-            n_out, x_own = n, x
-            src_args, n_src_rows = (L.f32(x), None, 0), n
+        elif gather:
+            from . import parallel
+            pending = parallel.allgather_rows_start(x, part)          # NCCL, asynchronous
+            n_src_rows = part.n_global
         else:
-            if dst_lo + n_dst > n:
-                raise RuntimeError("RelGraphConv: owned node block lies outside the gathered features")
-            n_out, x_own = n_dst, x[dst_lo:dst_lo + n_dst]
-            src_args, n_src_rows = (L.f32(x), None, 0), n
+            if n_own != gi.n_nodes:
+                raise RuntimeError(f"RelGraphConv: {n_own} feature rows for a graph of {gi.n_nodes} nodes")
+            n_src_rows = n_own
         w_fwd = w_bwd = None
         if needs_layouts:
             w_fwd = torch.empty((R, si, out_feat), dtype=torch.float32, device=dev)
             w_bwd = torch.empty((R, so, in_feat), dtype=torch.float32, device=dev)
             L.call("kg_bdd_weight_layouts", L.f32(weight), R, num_bases, si, so, L.f32(w_fwd),
                    L.f32(w_bwd), L.stream())
-        agg = torch.zeros((n_out, out_feat), dtype=torch.float32, device=dev)
-        pack = _rel_order(gi, 0, n_out, 4 * out_feat)
+        bias = None if h_bias is None else _c(h_bias)
+        mask = None if drop_mask is None else _c(drop_mask)
+        out = torch.empty((n_own, out_feat), dtype=torch.float32, device=dev)
+        if loop_weight is not None:                   # out = x_own @ loop_weight + bias   (only local rows)
+            loop_weight = _c(loop_weight)
+            gemm(x, loop_weight, out, bias=bias)
+        else:
+            epilogue_only(out, bias=bias) if bias is not None else out.zero_()
+        x_src = x
+        if pending is not None:
+            x_src = pending.wait()                    # [n_global, in] on this stream from here on
+        src_args = (None, L.ptr(peer.ptrs), peer.blk) if peer is not None else (L.f32(x_src), None, 0)
+        pack = _rel_order(gi, 0, n_own, 4 * out_feat)
         hints = (HINT_STREAM_X if n_src_rows * in_feat * 4 > L2_STREAM_BYTES else 0) | \
                 (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
         L.call("kg_bdd_rel_fwd", *src_args, L.i32(pack), gi.n_edges, L.f32(weight),
-               L.f32(w_fwd), num_bases, si, so, L.f32(agg), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
-        out = torch.empty_like(agg)
-        bias = None if h_bias is None else _c(h_bias)
-        mask = None if drop_mask is None else _c(drop_mask)
-        if loop_weight is not None:
-            loop_weight = _c(loop_weight)
-            gemm(x_own, loop_weight, out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
-        else:
-            epilogue_only(out, bias=bias, addend=agg, relu=(act == 1), mask=mask)
-        ctx.save_for_backward(x, weight, loop_weight, out, mask, w_bwd)
+               L.f32(w_fwd), num_bases, si, so, L.f32(out), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
+        if act == 1 or mask is not None:              # activation + dropout mask, in place
+            epilogue_only(out, addend=out, relu=(act == 1), mask=mask)
+        ctx.save_for_backward(x_src, weight, loop_weight, out, mask, w_bwd)
         ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
         ctx.has_bias = h_bias is not None
-        ctx.dst_lo, ctx.n_out, ctx.peer, ctx.part = dst_lo, n_out, peer, part
+        ctx.gather, ctx.n_own, ctx.peer, ctx.part = bool(gather), n_own, peer, part
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight, loop_weight, out, mask, w_bwd = ctx.saved_tensors
-        gi, B, si, so, peer = ctx.gi, ctx.num_bases, ctx.si, ctx.so, ctx.peer
+        gi, B, si, so, peer, part = ctx.gi, ctx.num_bases, ctx.si, ctx.so, ctx.peer, ctx.part
         g = _c(g)
-        x_own = x if ctx.dst_lo < 0 else x[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
+        lo = part.lo if ctx.gather else 0
+        x_own = x[lo:lo + ctx.n_own] if ctx.gather else x
         gpre, dbias_fused = act_dropout_bwd(g, out, mask, ctx.act, want_colsum=ctx.has_bias)
         dx = dw = dloop = dbias = None
+        pending = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if peer is not None:       # source rows are still in the peers' blocks (published in forward)
                 n_src_rows = peer.blk * peer.world_size
@@ -305,15 +314,13 @@ class BddConvFn(torch.autograd.Function):
             L.call("kg_bdd_rel_bwd", *src_args, L.f32(gpre), L.i32(pack), gi.n_edges, L.f32(weight), L.f32(w_bwd),
                    B, si, so, L.f32(dx), L.f32(dw), hints, L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
             if dx is not None and loop_weight is not None:
-                if peer is not None:
-                    lo = peer.rank * peer.blk
-                    dx_own = dx[lo:lo + ctx.n_out]
-                else:
-                    dx_own = dx if ctx.dst_lo < 0 else dx[ctx.dst_lo:ctx.dst_lo + ctx.n_out]
-                gemm(gpre, loop_weight, dx_own, trans_b=True, accumulate=True)
-            if dx is not None and peer is not None:      # every rank holds partial sums for all nodes
+                own_lo = peer.rank * peer.blk if peer is not None else lo
+                gemm(gpre, loop_weight, dx[own_lo:own_lo + ctx.n_own], trans_b=True, accumulate=True)
+            if dx is not None and (peer is not None or ctx.gather):
+                # every rank holds partial sums for all nodes: reduce-scatter to the owners, asynchronously -
+                # the weight-gradient GEMM below does not depend on it
                 from . import parallel
-                dx = parallel.reduce_scatter_rows(dx, ctx.part)
+                pending = parallel.reduce_scatter_rows_start(dx, part)
             if not ctx.needs_input_grad[1]:
                 dw = None
         if loop_weight is not None and ctx.needs_input_grad[2]:
@@ -321,7 +328,9 @@ class BddConvFn(torch.autograd.Function):
             gemm(x_own, gpre, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = dbias_fused
-        return dx, dw, dloop, dbias, None, None, None, None, None, None, None, None
+        if pending is not None:
+            dx = pending.wait()
+        return dx, dw, dloop, dbias, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------

@@ -341,6 +341,70 @@ class PeerRows:
         self.barrier()
 
 
+class _Pending:
+    """An asynchronous collective and what turns its raw output into the result; ``wait()`` makes the current
+    stream wait for it (the host does not block) and returns the result."""
+
+    def __init__(self, work, finish):
+        self.work, self.finish = work, finish
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+        return self.finish()
+
+
+def allgather_rows_start(x_local, part):
+    """allgather_rows as an asynchronous NCCL collective (uniform or near-uniform blocks): returns a _Pending
+    whose ``wait()`` yields the [n_global, d] matrix.  Work enqueued between the call and ``wait()`` overlaps
+    the transfer."""
+    group = part.group
+    ws, n_global = part.world_size, part.n_global
+    uniform = part.blk is not None
+    rng = uniform_block_range if uniform else block_range
+    sizes = [rng(n_global, p, ws)[1] - rng(n_global, p, ws)[0] for p in range(ws)]
+    pad = max(sizes)
+    x_local = x_local.contiguous()
+    if x_local.shape[0] == pad:
+        buf = x_local
+    else:
+        buf = x_local.new_zeros((pad,) + tuple(x_local.shape[1:]))
+        buf[:x_local.shape[0]] = x_local
+    out = x_local.new_empty((ws * pad,) + tuple(x_local.shape[1:]))
+    if dist.get_backend(group) == "gloo":
+        lst = [torch.empty_like(buf) for _ in range(ws)]
+        work = dist.all_gather(lst, buf, group=group, async_op=True)
+
+        def finish():
+            return torch.cat([lst[p][:n] for p, n in enumerate(sizes)], dim=0)
+    else:
+        work = dist.all_gather_into_tensor(out, buf, group=group, async_op=True)
+
+        def finish():
+            if all(n == pad for n in sizes):
+                return out
+            if uniform:               # only the last blocks are short: the first n_global rows are the matrix
+                return out[:n_global]
+            parts = out.view((ws, pad) + tuple(x_local.shape[1:]))
+            return torch.cat([parts[p][:n] for p, n in enumerate(sizes)], dim=0)
+    return _Pending(work, finish)
+
+
+def reduce_scatter_rows_start(g_full, part):
+    """reduce_scatter_rows as an asynchronous collective: ``wait()`` yields this rank's rows of the sum."""
+    if part.blk is not None and hasattr(dist, "reduce_scatter_tensor") and dist.get_backend(part.group) != "gloo":
+        rows = part.blk * part.world_size
+        if g_full.shape[0] < rows:
+            pad = g_full.new_zeros((rows,) + tuple(g_full.shape[1:]))
+            pad[:g_full.shape[0]] = g_full
+            g_full = pad
+        out = g_full.new_empty((part.blk,) + tuple(g_full.shape[1:]))
+        work = dist.reduce_scatter_tensor(out, g_full[:rows], op=dist.ReduceOp.SUM, group=part.group, async_op=True)
+        return _Pending(work, lambda: out[:part.n_local])
+    work = dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=part.group, async_op=True)
+    return _Pending(work, lambda: g_full[part.lo:part.hi].clone())
+
+
 class AllGatherRowsFn(torch.autograd.Function):
     """x_local [n_local, d] -> x_full [n_global, d]; backward: reduce-scatter(sum) of the gradient -
     every rank's loss depends on every row it gathered."""

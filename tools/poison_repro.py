@@ -81,7 +81,7 @@ def step(model, host):
 
 def main():
     bad_total = 0
-    for n_flows, sample_edges in ((0, 2000), (1, 2000), (0, 20000)):
+    for n_flows, sample_edges in ((0, 2000), (1, 2000), (0, 8000)):
         model, host = build(n_flows, sample_edges)
         first = step(model, host)          # un-poisoned reference run
         for rep in range(REPS):
