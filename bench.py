@@ -285,6 +285,46 @@ def measure_l2_peak(dev, rows, row_floats, n_ops=3_000_000, reps=5):
     return out
 
 
+def gemm_vs_library(dev, log, iters=10):
+    """kg_gemm_f32 (tcgen05, fp32-accurate two-term fp16 split, operand conversion included) next to the library
+    kernel it replaces on the same box: torch.matmul in fp32 with TF32 off (cuBLAS SGEMM - what DGL / F.linear
+    run in the reference, kgvae/model.py:55,58, kgvae/flow_network.py:15), at the benchmarked shapes."""
+    from gcn_vae_b200 import ops
+    gen = torch.Generator(device=dev).manual_seed(3)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {}
+    try:
+        for (M, N, Kd, ta, tb) in [(14541, 500, 500, False, False), (14541, 1000, 500, False, False),
+                                   (14541, 500, 1000, False, True), (500, 1000, 14541, True, False),
+                                   (40914, 500, 500, False, True), (500, 500, 40914, True, False)]:
+            a = torch.randn((Kd, M) if ta else (M, Kd), device=dev, generator=gen)
+            b = torch.randn((N, Kd) if tb else (Kd, N), device=dev, generator=gen)
+            c = torch.empty(M, N, device=dev)
+            am, bm = (a.t() if ta else a), (b.t() if tb else b)
+
+            def t_of(fn):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                e1.synchronize()
+                return e0.elapsed_time(e1) / iters
+            ours = t_of(lambda: ops.gemm(a, b, c, trans_a=ta, trans_b=tb))
+            lib = t_of(lambda: torch.matmul(am, bm, out=c))
+            err = float((c - ops.gemm(a, b, torch.empty_like(c), trans_a=ta, trans_b=tb)).abs().max() / c.abs().max())
+            tag = f"{M}x{N}x{Kd},{'T' if ta else 'N'}{'T' if tb else 'N'}"
+            out[tag] = {"kg_gemm_f32_ms": ours, "torch_matmul_fp32_ms": lib, "speedup": lib / ours,
+                        "tflops_algorithmic": 2.0 * M * N * Kd / (ours * 1e-3) / 1e12, "max_rel_diff": err}
+            log(f"  [gemm {tag}] kg_gemm_f32 {ours:.3f} ms, torch.matmul fp32 {lib:.3f} ms ({lib / ours:.2f}x), diff {err:.1e}")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
 def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edges=32_000_000, iters=5):
     """RGCN(bdd) message passing at the ogbl-wikikg2 shape (BASELINE.json configs[4]: 2.5 M entities,
     2 x 535 relation types, 2 x 16 M directed edges, h = 500, 100 blocks) on ONE GPU: the regime the
@@ -868,6 +908,7 @@ def run_gpu(args):
         l2_peak = measure_l2_peak(dev, N, H)
         log(f"  [l2 probe] read {l2_peak['read_gbs']:.0f} GB/s, reduce {l2_peak['reduce_gbs']:.0f} GB/s, "
             f"read+reduce {l2_peak['mixed_gbs']:.0f} GB/s")
+    gemm_cmp = gemm_vs_library(dev, log) if (rank == 0 and world == 1) else None
 
     # ---- evaluation: encoder on the test graph + all-entity ranks -----------------------------
     model.eval()
@@ -1039,6 +1080,7 @@ def run_gpu(args):
         roof["tensor"] = eval_roof
         roof["eval"] = eval_summary
         roof["partitioned"] = partitioned
+        roof["gemm_vs_library"] = gemm_cmp
         if streaming:
             worst = min(((k_, v) for k_, v in streaming["kernels"]["uniform"].items()), key=lambda kv: kv[1]["frac_of_hbm_peak"])
             roof["hbm"] = {"kernel": worst[0] + " @ wikikg2 shape (2.5 M nodes, 32 M edges)", "bound": "hbm",

@@ -115,7 +115,7 @@ struct GemmArgs {
   int relu, accumulate;
   float* partial;        // split-K: [splits][M][N] raw products (scales applied), else null
   TileMap tmap;
-  int Kp;
+  int Kp, n_terms;
 };
 
 __device__ __forceinline__ float finish(float v, const GemmArgs& g, int n, size_t off) {
@@ -137,9 +137,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int total = g.tmap.total();
 
   if (warp == 0) {
-    pipe_producer_wide(P, &tm_a, &tm_b, g.tmap, g.Kp);
+    pipe_producer_wide(P, &tm_a, &tm_b, g.tmap, g.Kp, g.n_terms);
   } else if (warp == 1) {
-    pipe_mma_wide(P, g.tmap);
+    pipe_mma_wide(P, g.tmap, g.n_terms);
   } else {
     // TMEM lanes are reachable by warp id % 4: warps 2..5 take columns [0, 128) of their quadrant, 6..9 [128, 256)
     const int quad = warp & 3, etid = threadIdx.x - 64, half = (warp - 2) >> 2;
@@ -369,6 +369,7 @@ int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb
   g.partial = partial;
   g.tmap = TileMap{L.m_tiles, L.n_tiles, L.splits, L.Kp / BK, L.k_per_split};
   g.Kp = L.Kp;
+  g.n_terms = tc05::tc_terms();
   const int total = g.tmap.total();
   const int grid = total < kg_sm_count() ? total : kg_sm_count();
   gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, g);

@@ -76,7 +76,7 @@ entity_prep(const float* __restrict__ emb, int cand_begin, int n_cand, int n_col
 __global__ void __launch_bounds__(256)
 query_prep(const float* __restrict__ emb, const float* __restrict__ w, const int* __restrict__ a,
            const int* __restrict__ r, const int* __restrict__ b, int M, int h, int Kp,
-           const float* __restrict__ shift_p, float* __restrict__ q32, __half* __restrict__ acat,
+           const float* __restrict__ shift_p, float mu, float* __restrict__ q32, __half* __restrict__ acat,
            float4* __restrict__ rowp, float* __restrict__ sqv) {
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -105,7 +105,7 @@ query_prep(const float* __restrict__ emb, const float* __restrict__ w, const int
   }
   if (lane == 0) {
     const float t = acc + shift;                         // utils.py:206-207
-    rowp[m] = make_float4(s * (t - shift), s * kMu * sqrtf(ss) * 1.000002f,
+    rowp[m] = make_float4(s * (t - shift), s * mu * sqrtf(ss) * 1.000002f,
                           s * (kEps * (fabsf(shift) + fabsf(t)) + 1e-37f), t);
     sqv[m] = s;
   }
@@ -121,7 +121,7 @@ struct RankArgs {
   int* ranks;
   const float* sqv;      // per-query scale (only read when dump != nullptr)
   float* dump;           // test hook: tensor-core scores [M, n_cand] (nullptr in production)
-  int M, h, Kp, cand_begin, n_cand, m_tiles, n_tiles;
+  int M, h, Kp, cand_begin, n_cand, m_tiles, n_tiles, n_terms;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -135,9 +135,9 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int total = tmap.total();
 
   if (warp == 0) {
-    pipe_producer(P, &tm_a, &tm_b, tmap, p.Kp);
+    pipe_producer(P, &tm_a, &tm_b, tmap, p.Kp, p.n_terms);
   } else if (warp == 1) {
-    pipe_mma(P, tmap);
+    pipe_mma(P, tmap, p.n_terms);
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..5)
     const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad + 32)
@@ -321,7 +321,10 @@ extern "C" int kg_distmult_rank(const float* emb, const float* w, const int32_t*
   float2* colp = reinterpret_cast<float2*>(ws + L.colp);
   float* sqv = reinterpret_cast<float*>(ws + L.sqv);
 
-  query_prep<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(emb, w, a, r, b, M, h, L.Kp, shift, q32, acat, rowp, sqv);
+  // single-product mode: the tensor-core score IS the decision (no band; only exact ties are re-scored)
+  const int n_terms = tc05::tc_terms();
+  query_prep<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(emb, w, a, r, b, M, h, L.Kp, shift,
+                                                               n_terms == 3 ? kMu : 0.f, q32, acat, rowp, sqv);
   KG_LAUNCH_OK();
   if (n_cand == 0) return KG_OK;
   const int n_cols = L.n_tiles * BN;
@@ -341,7 +344,7 @@ extern "C" int kg_distmult_rank(const float* emb, const float* w, const int32_t*
   args.q32 = q32; args.emb = emb; args.rowp = rowp; args.colp = colp; args.tgt = b; args.shift = shift;
   args.ranks = ranks; args.sqv = sqv; args.dump = tc_scores;
   args.M = M; args.h = h; args.Kp = L.Kp; args.cand_begin = cand_begin; args.n_cand = n_cand;
-  args.m_tiles = L.m_tiles; args.n_tiles = L.n_tiles;
+  args.m_tiles = L.m_tiles; args.n_tiles = L.n_tiles; args.n_terms = n_terms;
   const int total = L.m_tiles * L.n_tiles;
   const int grid = total < kg_sm_count() ? total : kg_sm_count();
   rank_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, args);

@@ -87,8 +87,10 @@ __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap*
 }
 
 // warp 0
+// n_terms = 3: the fp32-accurate product lo*hi + hi*lo + hi*hi;  n_terms = 1: hi*hi only (single-product
+// mode: operands rounded to 11 bits, a third of the MMAs - reported separately, never the default)
 __device__ __forceinline__ void pipe_producer(const Pipe& P, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
-                                              const TileMap& tmap, int Kp) {
+                                              const TileMap& tmap, int Kp, int n_terms = 3) {
   if (!elect_one()) return;
   int stage = 0;
   uint32_t phase = 0;
@@ -96,7 +98,7 @@ __device__ __forceinline__ void pipe_producer(const Pipe& P, const CUtensorMap* 
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     int m0, n0, split, ks0, nks;
     tmap.decode(tile, m0, n0, split, ks0, nks);
-    for (int term = 0; term < 3; ++term) {
+    for (int term = 3 - n_terms; term < 3; ++term) {
       // small terms first: lo*hi, hi*lo, then hi*hi   (hi at column 0, lo at column Kp)
       const int a_off = term == 0 ? Kp : 0, b_off = term == 1 ? Kp : 0;
       for (int ks = ks0; ks < ks0 + nks; ++ks) {
@@ -112,7 +114,7 @@ __device__ __forceinline__ void pipe_producer(const Pipe& P, const CUtensorMap* 
 }
 
 // warp 1
-__device__ __forceinline__ void pipe_mma(const Pipe& P, const TileMap& tmap) {
+__device__ __forceinline__ void pipe_mma(const Pipe& P, const TileMap& tmap, int n_terms = 3) {
   if (!elect_one()) return;
   constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
   int stage = 0;
@@ -126,7 +128,7 @@ __device__ __forceinline__ void pipe_mma(const Pipe& P, const TileMap& tmap) {
     mbar_wait(P.tempty + buf, ((it >> 1) & 1) ^ 1);
     fence_after_thread_sync();
     const uint32_t tacc = P.tmem_base + buf * BN;
-    for (int ks = 0; ks < 3 * nks; ++ks) {
+    for (int ks = 0; ks < n_terms * nks; ++ks) {
       mbar_wait(P.full + stage, phase);
       fence_after_thread_sync();
       const uint32_t sa = smem_u32(P.smem + stage * STAGE_BYTES);
@@ -155,7 +157,7 @@ static_assert(WIDE_STAGES * WIDE_STAGE_BYTES <= STAGES * STAGE_BYTES, "wide stag
 
 // warp 0
 __device__ __forceinline__ void pipe_producer_wide(const Pipe& P, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
-                                                   const TileMap& tmap, int Kp) {
+                                                   const TileMap& tmap, int Kp, int n_terms = 3) {
   if (!elect_one()) return;
   int stage = 0;
   uint32_t phase = 0;
@@ -166,18 +168,20 @@ __device__ __forceinline__ void pipe_producer_wide(const Pipe& P, const CUtensor
     for (int ks = ks0; ks < ks0 + nks; ++ks) {
       mbar_wait(P.empty + stage, phase ^ 1);
       uint8_t* st = P.smem + stage * WIDE_STAGE_BYTES;
-      mbar_arrive_expect_tx(P.full + stage, WIDE_STAGE_BYTES);
+      mbar_arrive_expect_tx(P.full + stage, n_terms == 3 ? WIDE_STAGE_BYTES : STAGE_BYTES);
       tma_load_2d(st, tm_a, P.full + stage, ks * BK, m0);                              // A_hi
-      tma_load_2d(st + A_BYTES, tm_a, P.full + stage, Kp + ks * BK, m0);               // A_lo
       tma_load_2d(st + 2 * A_BYTES, tm_b, P.full + stage, ks * BK, n0);                // B_hi
-      tma_load_2d(st + 2 * A_BYTES + B_BYTES, tm_b, P.full + stage, Kp + ks * BK, n0); // B_lo
+      if (n_terms == 3) {
+        tma_load_2d(st + A_BYTES, tm_a, P.full + stage, Kp + ks * BK, m0);               // A_lo
+        tma_load_2d(st + 2 * A_BYTES + B_BYTES, tm_b, P.full + stage, Kp + ks * BK, n0); // B_lo
+      }
       if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
     }
   }
 }
 
 // warp 1
-__device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap) {
+__device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap, int n_terms = 3) {
   if (!elect_one()) return;
   constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
   int stage = 0;
@@ -197,12 +201,17 @@ __device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap
       const uint32_t sa = smem_u32(P.smem + stage * WIDE_STAGE_BYTES);
       const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + A_BYTES);
       const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * A_BYTES), b_lo = smem_desc_k_sw128(sa + 2 * A_BYTES + B_BYTES);
+      if (n_terms == 3) {
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);   // small terms first
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);   // small terms first
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
+      } else {
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);
+      }
       mma_commit(P.empty + stage);        // frees the stage once these MMAs have read it
       if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
     }

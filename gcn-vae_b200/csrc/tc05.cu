@@ -37,4 +37,17 @@ int make_tensor_map_2d_b16(CUtensorMap* map, const void* base, uint64_t rows, ui
   return KG_OK;
 }
 
+static int g_tc_terms = 3;
+int tc_terms() { return g_tc_terms; }
+
 }  // namespace tc05
+
+// 3 (default): every tensor-core product of the library is the fp32-accurate three-term fp16 split.
+// 1: single-product mode - operands rounded to 11 significant bits (per-row scaled fp16), one MMA per k-step
+// instead of three; the "reduced-precision GEMM variant, reported separately" of north_star.  Affects
+// kg_gemm_f32 (tensor-core path) and kg_distmult_rank; returns the previous setting.
+extern "C" int kg_set_tc_terms(int terms) {
+  const int old = tc05::g_tc_terms;
+  if (terms == 1 || terms == 3) tc05::g_tc_terms = terms;
+  return old;
+}

@@ -168,5 +168,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------
 int make_tensor_map_2d_b16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                            uint64_t row_stride_bytes, uint32_t box_rows);
+// number of split terms the tensor-core products use: 3 (fp32-accurate, default) or 1 (kg_set_tc_terms)
+int tc_terms();
 
 }  // namespace tc05

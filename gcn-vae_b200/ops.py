@@ -15,6 +15,23 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+class tensor_core_terms:
+    """Context manager: run the tensor-core products (kg_gemm_f32, kg_distmult_rank) with ``terms`` split
+    terms - 3 is the fp32-accurate default, 1 the single-product mode that north_star asks to be reported
+    separately (operands rounded to 11 significant bits)."""
+
+    def __init__(self, terms):
+        self.terms = int(terms)
+
+    def __enter__(self):
+        self.old = L.lib().kg_set_tc_terms(self.terms)
+        return self
+
+    def __exit__(self, *exc):
+        L.lib().kg_set_tc_terms(self.old)
+        return False
+
+
 def as_i32(t, device=None):
     """int32 contiguous view/copy of an index tensor (reference tensors are int64)."""
     if not isinstance(t, torch.Tensor):

@@ -323,6 +323,13 @@ int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const i
                      void* workspace, size_t workspace_bytes, int32_t* ranks, float* tc_scores,
                      void* stream);
 
+/* Precision of the tensor-core products behind kg_gemm_f32 and kg_distmult_rank (new; the reference runs
+ * fp32 library kernels, kgvae/utils.py:200-205, kgvae/flow_network.py:15).  3 (default): the fp32-accurate
+ * three-term fp16 split every parity claim is made on.  1: single-product mode - operands rounded to 11
+ * significant bits, a third of the MMAs; ranks / outputs then carry that rounding (bench.py reports the mode
+ * separately with its measured deviation).  Returns the previous setting. */
+int kg_set_tc_terms(int terms);
+
 /* ------------------------------------------------------------------------------------
  * measurement aid (new; no reference counterpart): sustained L2 throughput of this GPU for
  * the access pattern of kg_distmult_bce_fwd - whole fp32 rows of an L2-resident matrix read

@@ -254,13 +254,19 @@ def iaf_forward(z, params, n_flows):
 # ---------------------------------------------------------------------------
 # a2 + a3 + a5 + a6  encoder        reference kgvae/model.py:107-124
 # ---------------------------------------------------------------------------
-def kgvae_encode(params, graph, node_id, eps, num_bases, n_flows=0, drop_masks=(None, None)):
+def kgvae_encode(params, graph, node_id, eps, num_bases, n_flows=0, drop_masks=(None, None), relu_pattern=None):
+    """``relu_pattern`` (bool [N, h], optional): which units of layer 1 count as active.  ReLU has no derivative
+    at 0, and a pre-activation within rounding error of 0 can land on either side depending on the summation
+    order; a gradient comparison at millions of units (the benchmark-size parity test) hands the other
+    implementation's pattern in here so that both sides differentiate the same piecewise-linear function.
+    The forward value changes by at most the magnitude of those pre-activations (~1e-6)."""
     p = params
     h0 = p["encoder.input_layer.embedding.weight"][torch.as_tensor(node_id).view(-1)]
+    act1 = torch.relu if relu_pattern is None else (lambda t: t * relu_pattern.to(t.dtype))
     h1 = rgcn_bdd_layer(h0, graph, p["encoder.rconv_layer_1.weight"],
                         p["encoder.rconv_layer_1.h_bias"],
                         p["encoder.rconv_layer_1.loop_weight"], num_bases,
-                        torch.relu, drop_masks[0])
+                        act1, drop_masks[0])
     h2 = rgcn_bdd_layer(h1, graph, p["encoder.rconv_layer_2.weight"],
                         p["encoder.rconv_layer_2.h_bias"],
                         p["encoder.rconv_layer_2.loop_weight"], num_bases,

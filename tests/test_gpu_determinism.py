@@ -158,7 +158,10 @@ def test_bench_configuration_step_against_oracle():
     enc.preset_eps, enc.rconv_layer_1.dropout_mask, enc.rconv_layer_2.dropout_mask = eps.to(DEV), m1.to(DEV), m2.to(DEV)
     edge_norm = K.node_norm_to_edge_norm(g, torch.from_numpy(node_norm).view(-1, 1)).to(DEV)
     model.train()
+    taps = {}
+    hook = enc.rconv_layer_1.register_forward_hook(lambda m, i, o: taps.__setitem__("h1", o.detach().cpu()))
     embed = model(g, torch.from_numpy(node_id).view(-1, 1).to(DEV), torch.from_numpy(edge_type).to(DEV), edge_norm)
+    hook.remove()
     loss, pred, kl, _ = model.get_loss(g, embed, torch.from_numpy(samples).to(DEV), torch.from_numpy(labels).to(DEV))
     loss.backward()
 
@@ -166,10 +169,19 @@ def test_bench_configuration_step_against_oracle():
               for key, val in model.state_dict().items() if not key.endswith(("mask", "pi"))}
     graph = {"num_nodes": n, "src": g._src, "dst": g._dst, "etype": edge_type, "norm": node_norm,
              "edge_norm": node_norm[g._dst].reshape(-1, 1).astype(np.float32)}
-    torch.set_num_threads(max(1, torch.get_num_threads()))
-    ref_enc = O.kgvae_encode(params, graph, node_id, eps, bases, 0, (m1, m2))
+    # 7.3 M hidden units: a handful of layer-1 pre-activations lie within rounding error of 0 and land on different
+    # sides in the two implementations; ReLU has no derivative there, so the oracle differentiates with the pattern
+    # the GPU run used (the test bounds how many units that concerns and how far from 0 they are)
+    pattern = (taps["h1"] > 0) | (m1 == 0)
+    with torch.no_grad():
+        plain = O.kgvae_encode(params, graph, node_id, eps, bases, 0, (m1, m2))
+    flipped = ((plain["h1"] > 0) != (taps["h1"] > 0)) & (m1 > 0)
+    assert int(flipped.sum()) <= 64, f"{int(flipped.sum())} ReLU units differ in sign"
+    assert float((plain["h1"] - taps["h1"]).abs()[flipped].max() if flipped.any() else 0.0) < 1e-4
+    ref_enc = O.kgvae_encode(params, graph, node_id, eps, bases, 0, (m1, m2), relu_pattern=pattern)
     ref = O.kgvae_loss(params, ref_enc, samples, labels, 0.01, 1e-5, 0)
     ref["loss"].backward()
+    assert_close(taps["h1"], plain["h1"], RTOL, "h1")
     assert_close(embed, ref_enc["z"], RTOL, "z")
     assert_close(loss, ref["loss"], RTOL, "loss")
     assert_close(pred, ref["pred"] if "pred" in ref else ref["predict_loss"], RTOL, "predict loss")
