@@ -69,6 +69,8 @@ _SIGNATURES = {
     "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _Z, _P, _P, _P]),
     "kg_probe_l2": (_I, [_P, _P, _I, _I, _L, _I, _P, _P]),
     "kg_set_tc_terms": (_I, [_I]),
+    "kg_distmult_topk_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "kg_distmult_topk": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _Z, _P, _P, _P]),
 }
 
 _lib = None

@@ -268,6 +268,163 @@ filter_correction(const float* __restrict__ q32, const float* __restrict__ emb, 
   if (lane == 0 && cnt) atomicSub(ranks + m, cnt);
 }
 
+// ------------------------------------------------------------------------------------------
+// top-k tails: the same score tiles with a top-k epilogue (reference kgvae/utils.py:245-288, `generate`:
+// argmax tail per query; k = 1 there).  Each epilogue thread owns one query row of the tile and keeps the
+// KK = k + 1 best tensor-core scores of the tile's 256 candidates in registers; they go to a
+// [M, n_tiles, KK] candidate list.  A finish kernel re-scores every listed candidate with the canonical
+// fp32 dot product and keeps the k best by (score desc, entity id asc); a tile whose (k+1)-th listed score
+// could still reach the k-th exact score (within the filter's error band) is re-scanned completely, so
+// the result does not depend on the tensor-core rounding.
+// ------------------------------------------------------------------------------------------
+struct TopkArgs {
+  const float2* colp;
+  const float* sqv;
+  float* cand_v;
+  int* cand_i;
+  int M, Kp, n_cand, m_tiles, n_tiles, n_terms;
+};
+
+template <int KK>
+__device__ __forceinline__ void topk_insert(float (&bv)[KK], int (&bi)[KK], float v, int n) {
+  if (!(v > bv[KK - 1])) return;
+  bv[KK - 1] = v;
+  bi[KK - 1] = n;
+#pragma unroll
+  for (int i = KK - 1; i > 0; --i) {
+    if (bv[i] > bv[i - 1]) {
+      const float tv = bv[i]; bv[i] = bv[i - 1]; bv[i - 1] = tv;
+      const int ti = bi[i]; bi[i] = bi[i - 1]; bi[i - 1] = ti;
+    }
+  }
+}
+
+template <int KK>
+__global__ void __launch_bounds__(THREADS, 1)
+topk_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TopkArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b);
+  float2* colp_s = reinterpret_cast<float2*>(P.scratch);                       // [2][BN]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TileMap tmap{p.m_tiles, p.n_tiles, 1, p.Kp / BK, p.Kp / BK};
+  const int total = tmap.total();
+  if (warp == 0) {
+    pipe_producer(P, &tm_a, &tm_b, tmap, p.Kp, p.n_terms);
+  } else if (warp == 1) {
+    pipe_mma(P, tmap, p.n_terms);
+  } else {
+    const int quad = warp & 3, etid = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * BM, n0 = n_tile * BN;
+      const int m = m0 + quad * 32 + lane;
+      float4* cs4 = reinterpret_cast<float4*>(colp_s + buf * BN);
+      cs4[etid] = __ldg(reinterpret_cast<const float4*>(p.colp + n0) + etid);
+      const float inv_sq = m < p.M ? 1.f / __ldg(p.sqv + m) : 0.f;
+      epi_barrier();
+      const uint32_t taddr = epi_acquire(P, it);
+      float bv[KK];
+      int bi[KK];
+#pragma unroll
+      for (int i = 0; i < KK; ++i) { bv[i] = -INFINITY; bi[i] = -1; }
+      const float2* cs = colp_s + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 cp = cs[c * 32 + j];                                    // {1 / s_e, |e|}: broadcast
+          const int n = n0 + c * 32 + j;
+          const float val = n < p.n_cand ? __uint_as_float(v[j]) * cp.x * inv_sq : -INFINITY;
+          topk_insert<KK>(bv, bi, val, n);
+        }
+      }
+      epi_release(P, it);
+      if (m < p.M) {
+        float* ov = p.cand_v + ((size_t)m * p.n_tiles + n_tile) * KK;
+        int* oi = p.cand_i + ((size_t)m * p.n_tiles + n_tile) * KK;
+#pragma unroll
+        for (int i = 0; i < KK; ++i) { ov[i] = bv[i]; oi[i] = bi[i]; }
+      }
+    }
+  }
+  pipe_teardown(P);
+}
+
+// max_j |e_j| over the candidate records (one block)
+__global__ void __launch_bounds__(256)
+colp_max_kernel(const float2* __restrict__ colp, int n_cand, float* __restrict__ out) {
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n_cand; i += 256) m = fmaxf(m, __ldg(&colp[i].y));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    out[0] = m;
+  }
+}
+
+constexpr int kTopkMax = 10;
+
+// one warp per query; every lane keeps the same sorted list (scores are warp-uniform after the butterfly sum)
+__global__ void __launch_bounds__(256)
+topk_finish_kernel(const float* __restrict__ q32, const float* __restrict__ emb, const float4* __restrict__ rowp,
+                   const float* __restrict__ sqv, const float* __restrict__ cand_v, const int* __restrict__ cand_i,
+                   const float* __restrict__ emax_p, int M, int h, int n_cand, int n_tiles, int KK, int k,
+                   const float* __restrict__ shift_p, int* __restrict__ out_idx, float* __restrict__ out_score) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float shift = shift_p ? __ldg(shift_p) : 0.f;
+  const float* q = q32 + (size_t)m * h;
+  float ts[kTopkMax];
+  int ti[kTopkMax];
+#pragma unroll
+  for (int i = 0; i < kTopkMax; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
+  auto offer = [&](float sc, int n) {           // order: score descending, entity id ascending; no duplicates
+#pragma unroll
+    for (int i = 0; i < kTopkMax; ++i)
+      if (ti[i] == n) return;
+    if (!(sc > ts[kTopkMax - 1] || (sc == ts[kTopkMax - 1] && n < ti[kTopkMax - 1]))) return;
+    ts[kTopkMax - 1] = sc;
+    ti[kTopkMax - 1] = n;
+#pragma unroll
+    for (int i = kTopkMax - 1; i > 0; --i) {
+      if (ts[i] > ts[i - 1] || (ts[i] == ts[i - 1] && ti[i] < ti[i - 1])) {
+        const float tv = ts[i]; ts[i] = ts[i - 1]; ts[i - 1] = tv;
+        const int tn = ti[i]; ti[i] = ti[i - 1]; ti[i - 1] = tn;
+      }
+    }
+  };
+  const float* cv = cand_v + (size_t)m * n_tiles * KK;
+  const int* ci = cand_i + (size_t)m * n_tiles * KK;
+  for (int t = 0; t < n_tiles; ++t)
+    for (int i = 0; i < KK; ++i) {
+      const int n = __ldg(ci + t * KK + i);
+      if (n < 0) continue;
+      offer(warp_dot(q, emb + (size_t)n * h, h, lane) + shift, n);
+    }
+  // error band of a tensor-core score in real units: mu |q| |e| (+ eps terms), |q| recovered from the row record
+  const float4 rp = __ldg(rowp + m);
+  const float s = __ldg(sqv + m);
+  const float band = (rp.y / s) * __ldg(emax_p) * 1.01f + 4.f * kEps * (fabsf(shift) + fabsf(ts[0] - shift)) + 1e-30f;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float v_last = __ldg(cv + t * KK + KK - 1);        // the best score NOT kept is <= this one
+    if (!(v_last + shift + band >= ts[k - 1])) continue;
+    const int n_end = min(n_cand, (t + 1) * BN);
+    for (int n = t * BN; n < n_end; ++n) offer(warp_dot(q, emb + (size_t)n * h, h, lane) + shift, n);
+  }
+  if (lane == 0)
+    for (int i = 0; i < k; ++i) {
+      out_idx[(size_t)m * k + i] = ti[i] == 0x7fffffff ? -1 : ti[i];
+      out_score[(size_t)m * k + i] = ts[i];
+    }
+}
+
 struct Layout {
   size_t q32, acat, bcat, rowp, colp, sqv, total;
   int Kp, n_tiles, m_tiles;
@@ -354,5 +511,82 @@ extern "C" int kg_distmult_rank(const float* emb, const float* w, const int32_t*
         q32, emb, rowp, b, filt_ptr, filt_idx, M, h, shift, cand_begin, cand_end, ranks);
     KG_LAUNCH_OK();
   }
+  return KG_OK;
+}
+
+static int topk_kk(int k) { return k <= 1 ? 2 : (k <= 3 ? 4 : kTopkMax + 1); }
+
+extern "C" size_t kg_distmult_topk_workspace_bytes(int n_queries, int n_entities, int h, int k) {
+  if (n_queries <= 0 || h <= 0 || n_entities <= 0) return 1024;
+  const Layout L = layout(n_queries, n_entities, h);
+  const size_t cand = (size_t)n_queries * L.n_tiles * topk_kk(k);
+  return L.total + kg_align_up(cand * sizeof(float), 1024) + kg_align_up(cand * sizeof(int), 1024) + 2048;
+}
+
+// out_idx [n_queries, k] int32 (entity ids, best first; -1 when fewer than k entities), out_score [n_queries, k]
+// fp32 canonical scores (+ shift): the k highest-scored tails of each query (a_i, r_i) among ALL entities.
+extern "C" int kg_distmult_topk(const float* emb, const float* w, const int32_t* a, const int32_t* r,
+                                int n_queries, int n_entities, int h, const float* shift, int k,
+                                void* workspace, size_t workspace_bytes, int32_t* out_idx, float* out_score,
+                                void* stream) {
+  KG_REQUIRE(n_queries >= 0 && n_entities > 0 && h > 0, "topk: bad sizes");
+  KG_REQUIRE(k >= 1 && k <= kTopkMax, "topk: k must be in 1..10");
+  cudaStream_t st = kg_stream(stream);
+  const int M = n_queries, n_cand = n_entities;
+  if (M == 0) return KG_OK;
+  const Layout L = layout(M, n_cand, h);
+  const int KK = topk_kk(k);
+  const size_t cand = (size_t)M * L.n_tiles * KK;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023;
+  const size_t need = L.total + kg_align_up(cand * sizeof(float), 1024) + kg_align_up(cand * sizeof(int), 1024) + 1024;
+  if (!workspace || base + need > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes)
+    return kg_fail(KG_ERR_WORKSPACE, "topk: workspace too small (%zu needed)", need + 1024);
+  char* ws = reinterpret_cast<char*>(base);
+  float* q32 = reinterpret_cast<float*>(ws + L.q32);
+  __half* acat = reinterpret_cast<__half*>(ws + L.acat);
+  __half* bcat = reinterpret_cast<__half*>(ws + L.bcat);
+  float4* rowp = reinterpret_cast<float4*>(ws + L.rowp);
+  float2* colp = reinterpret_cast<float2*>(ws + L.colp);
+  float* sqv = reinterpret_cast<float*>(ws + L.sqv);
+  float* cand_v = reinterpret_cast<float*>(ws + L.total);
+  int* cand_i = reinterpret_cast<int*>(ws + L.total + kg_align_up(cand * sizeof(float), 1024));
+  float* emax = reinterpret_cast<float*>(ws + L.total + kg_align_up(cand * sizeof(float), 1024) +
+                                         kg_align_up(cand * sizeof(int), 1024));
+
+  const int n_terms = tc05::tc_terms();
+  // the target slot of the row record is unused here: hand the subject in as a dummy target
+  query_prep<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(emb, w, a, r, a, M, h, L.Kp, shift, kMu, q32, acat, rowp, sqv);
+  KG_LAUNCH_OK();
+  const int n_cols = L.n_tiles * BN;
+  entity_prep<<<kg_div_up((long long)n_cols * 32, 256), 256, 0, st>>>(emb, 0, n_cand, n_cols, h, L.Kp, bcat, colp);
+  KG_LAUNCH_OK();
+  colp_max_kernel<<<1, 256, 0, st>>>(colp, n_cand, emax);
+  KG_LAUNCH_OK();
+  CUtensorMap tm_a, tm_b;
+  const uint64_t row_bytes = (uint64_t)2 * L.Kp * sizeof(__half);
+  int rc = make_tensor_map_2d_b16(&tm_a, acat, M, 2 * L.Kp, row_bytes, BM);
+  if (rc != KG_OK) return rc;
+  rc = make_tensor_map_2d_b16(&tm_b, bcat, n_cand, 2 * L.Kp, row_bytes, BN);
+  if (rc != KG_OK) return rc;
+  TopkArgs args;
+  args.colp = colp; args.sqv = sqv; args.cand_v = cand_v; args.cand_i = cand_i;
+  args.M = M; args.Kp = L.Kp; args.n_cand = n_cand; args.m_tiles = L.m_tiles; args.n_tiles = L.n_tiles;
+  args.n_terms = n_terms;
+  const int total = L.m_tiles * L.n_tiles;
+  const int grid = total < kg_sm_count() ? total : kg_sm_count();
+#define KG_TOPK_LAUNCH(KK_, SLOT_)                                                                              \
+  do {                                                                                                          \
+    if (kg_attr_needed(SLOT_))                                                                                  \
+      KG_CUDA(cudaFuncSetAttribute(topk_tc_kernel<KK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+    topk_tc_kernel<KK_><<<grid, THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, args);                                   \
+  } while (0)
+  if (KK == 2) KG_TOPK_LAUNCH(2, 2);
+  else if (KK == 4) KG_TOPK_LAUNCH(4, 3);
+  else KG_TOPK_LAUNCH(kTopkMax + 1, 4);
+#undef KG_TOPK_LAUNCH
+  KG_LAUNCH_OK();
+  topk_finish_kernel<<<kg_div_up((long long)M * 32, 256), 256, 0, st>>>(
+      q32, emb, rowp, sqv, cand_v, cand_i, emax, M, h, n_cand, L.n_tiles, KK, k, shift, out_idx, out_score);
+  KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -161,6 +161,11 @@ def main(args):
         print("Using best epoch: {}".format(checkpoint["epoch"]))
         with torch.no_grad():
             embed = model(test_graph, test_node_id, test_rel, test_norm)
+        if args.generate:             # kgvae/link_predict.py:181-184: generation instead of ranking
+            tails, scores = utils.generate(embed, model.w_relation, test_t, flow_log_prob=model._flow_shift(),
+                                           out_path="result.txt")
+            print(f"generated tails for {len(tails)} test queries -> result.txt")
+            return tails
         return utils.calc_mrr(embed, model.w_relation, test_t, hits=[1, 3, 10],
                               eval_bz=args.eval_batch_size, all_batches=True,
                               flow_log_prob=model._flow_shift())

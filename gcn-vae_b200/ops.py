@@ -639,3 +639,19 @@ def distmult_rank(emb, w, a, r, b, shift=None, cand_range=None, filt_ptr=None, f
            int(lo), int(hi), L.i32(filt_ptr), L.i32(filt_idx), L.ptr(ws), ws.numel(), L.i32(ranks),
            L.f32(tc_scores), L.stream())
     return ranks[:M]
+
+
+def distmult_topk(emb, w, a, r, k=1, shift=None):
+    """The ``k`` highest-scored tails of each query (a_i, r_i) among all entities, best first (ties by ascending
+    entity id): utils.generate's ``score.argmax`` (kgvae/utils.py:245-288) generalised to top-k, without the
+    score matrix.  Returns (idx int32 [M, k], score fp32 [M, k])."""
+    emb, w = _c(emb.detach()), _c(w.detach())
+    M, (V, h) = a.numel(), emb.shape
+    dev = emb.device
+    idx = torch.empty((max(M, 1), k), dtype=torch.int32, device=dev)
+    score = torch.empty((max(M, 1), k), dtype=torch.float32, device=dev)
+    ws = L.workspace(L.lib().kg_distmult_topk_workspace_bytes(M, V, h, k), dev)
+    sh = None if shift is None else _c(torch.as_tensor(shift, dtype=torch.float32, device=dev).reshape(1))
+    L.call("kg_distmult_topk", L.f32(emb), L.f32(w), L.i32(a), L.i32(r), M, V, h, L.f32(sh), int(k),
+           L.ptr(ws), ws.numel(), L.i32(idx), L.f32(score), L.stream())
+    return idx[:M], score[:M]

@@ -228,6 +228,36 @@ def calc_mrr(embedding, w, test_triplets, hits=[], eval_bz=100, all_batches=True
     return (mrr.item(), ranks) if return_ranks else mrr.item()
 
 
+def generate(embedding, w, test_triplets, eval_bz=200, topk=1, flow_log_prob=None, entity_names=None,
+             relation_names=None, out_path=None, max_lines=None):
+    """Tail generation (kgvae/utils.py:245-288): for every test triple (a, r, b) the highest-scored tail(s) among
+    all entities.  The reference scores 200 queries at a time through the D x E x V tensor, takes
+    ``score.argmax`` and prints the triples around one hard-coded entity using name files from the author's home
+    directory; here all queries go through one tcgen05 score pass with a top-k epilogue (``eval_bz`` is accepted
+    and ignored), and the triples are written as ids - or names, when ``entity_names`` / ``relation_names``
+    (sequences or dicts indexed by id) are given - to ``out_path`` (default: nothing is written).
+
+    Returns (tails int64 [T, topk], scores fp32 [T, topk]) on the embedding's device; ``tails[:, 0]`` is the
+    reference's ``highest_scored``."""
+    with torch.no_grad():
+        dev = embedding.device
+        t = torch.as_tensor(test_triplets)
+        a, r = ops.as_i32(t[:, 0], dev), ops.as_i32(t[:, 1], dev)
+        idx, score = ops.distmult_topk(embedding, w, a, r, k=topk, shift=flow_log_prob)
+        tails = idx.long()
+    if out_path is not None:
+        ent = (lambda i: str(entity_names[i])) if entity_names is not None else (lambda i: f"e{i}")
+        rel = (lambda i: str(relation_names[i])) if relation_names is not None else (lambda i: f"r{i}")
+        a_h, r_h, b_h, c_h = (x.cpu().tolist() for x in (t[:, 0], t[:, 1], t[:, 2], tails))
+        with open(out_path, "w") as f:
+            for i in range(len(a_h) if max_lines is None else min(len(a_h), max_lines)):
+                f.write(" - ".join([ent(a_h[i]), rel(r_h[i]), ent(b_h[i])]) + "\n")      # the known triple
+                for c in c_h[i]:
+                    if c != b_h[i]:
+                        f.write(" = ".join([ent(a_h[i]), rel(r_h[i]), ent(c)]) + "\n")   # a generated one
+    return tails, score
+
+
 def build_filter(all_triplets, queries_a, queries_r, num_rels, direction, device):
     """CSR of known-true candidates per query for filtered ranking (extension; the reference is
     raw-only).  direction "object": candidates c with (a, r, c) known; "subject": (c, r, a)."""

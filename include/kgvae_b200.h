@@ -323,6 +323,21 @@ int kg_distmult_rank(const float* emb, const float* w, const int32_t* a, const i
                      void* workspace, size_t workspace_bytes, int32_t* ranks, float* tc_scores,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * top-k tail generation
+ * replaces: utils.generate kgvae/utils.py:245-288 (the reference scores every entity through the same
+ * D x E x V tensor as the evaluation and takes the argmax tail per query; k = 1 there)
+ * The k (1..10) highest-scored entities of each query (a_i, r_i) among all n_entities, best first, ties by
+ * ascending entity id; scores are the canonical fp32 values of kg_distmult_rank (+ shift).  Same tcgen05
+ * score tiles with a top-k epilogue; a finish pass re-scores the listed candidates in fp32 and re-scans any
+ * tile the tensor-core rounding could not decide, so the result is exact.
+ * ---------------------------------------------------------------------------------- */
+size_t kg_distmult_topk_workspace_bytes(int n_queries, int n_entities, int h, int k);
+int kg_distmult_topk(const float* emb, const float* w, const int32_t* a, const int32_t* r,
+                     int n_queries, int n_entities, int h, const float* shift /* device scalar or NULL */,
+                     int k, void* workspace, size_t workspace_bytes, int32_t* out_idx, float* out_score,
+                     void* stream);
+
 /* Precision of the tensor-core products behind kg_gemm_f32 and kg_distmult_rank (new; the reference runs
  * fp32 library kernels, kgvae/utils.py:200-205, kgvae/flow_network.py:15).  3 (default): the fp32-accurate
  * three-term fp16 split every parity claim is made on.  1: single-product mode - operands rounded to 11

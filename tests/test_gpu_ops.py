@@ -712,3 +712,74 @@ def test_device_sampler_structure_and_train_step():
     loss, _, _, _ = model.get_loss(g, embed, samples, labels)
     loss.backward()
     assert torch.isfinite(loss) and torch.isfinite(model.w_relation.grad).all()
+
+
+# ------------------------------------------------------------------------------ top-k tails (N3)
+@pytest.mark.parametrize("V,h,M,k", [(96, 16, 80, 1), (1000, 100, 300, 3), (14541, 500, 200, 10), (130, 20, 1, 5),
+                                     (300, 64, 50, 1)])
+def test_topk_dyadic_inputs_bit_exact(V, h, M, k):
+    """utils.generate's argmax generalised to top-k (kgvae/utils.py:245-288): on dyadic inputs every partial sum
+    is exact, so the k best tails (ties by ascending id) and their scores must equal the oracle's exactly -
+    massive ties included (few distinct score values)."""
+    rng = np.random.default_rng(V * 3 + k)
+    emb = torch.from_numpy(rng.integers(-4, 5, size=(V, h)).astype(np.float32) / 4)
+    w = torch.from_numpy(rng.integers(-4, 5, size=(7, h)).astype(np.float32) / 4)
+    a, r = rng.integers(0, V, M), rng.integers(0, 7, M)
+    shift = -0.25
+    want_idx, want_sc = O.topk_tails(emb, w, torch.as_tensor(a), torch.as_tensor(r), k, shift)
+    dv = lambda x: torch.from_numpy(x.astype(np.int32)).to(DEV)
+    idx, sc = ops.distmult_topk(emb.to(DEV), w.to(DEV), dv(a), dv(r), k=k, shift=shift)
+    assert torch.equal(idx.cpu().long(), want_idx)
+    assert torch.equal(sc.cpu(), want_sc)
+
+
+def test_topk_random_floats_and_generate(tmp_path):
+    rng = np.random.default_rng(21)
+    V, h, M, k = 3000, 500, 150, 5
+    emb = torch.from_numpy(rng.standard_normal((V, h)).astype(np.float32))
+    w = torch.from_numpy(rng.standard_normal((11, h)).astype(np.float32))
+    trip = np.stack([rng.integers(0, V, M), rng.integers(0, 11, M), rng.integers(0, V, M)], 1)
+    score = O.eval_scores(emb.double(), w.double(), torch.as_tensor(trip[:, 0]), torch.as_tensor(trip[:, 1]))
+    want_sc, want_idx = torch.topk(score, k, dim=1)
+    out = tmp_path / "result.txt"
+    tails, sc = K.utils.generate(emb.to(DEV), w.to(DEV), torch.from_numpy(trip).to(DEV), topk=k, out_path=str(out))
+    # scores agree to fp32 accuracy; indices agree wherever the fp64 gap to the next candidate exceeds that accuracy
+    assert float((sc.cpu().double() - want_sc).abs().max()) <= 1e-4 * float(score.abs().max())
+    kth_gap = (want_sc[:, :-1] - want_sc[:, 1:]).min(1)[0]
+    clear = kth_gap > 1e-4 * score.abs().max()
+    assert torch.equal(tails.cpu()[clear], want_idx[clear])
+    lines = out.read_text().splitlines()
+    assert len(lines) >= M and lines[0].count(" - ") == 2
+
+
+# ------------------------------------------------------------------------------ single-product mode
+def test_single_product_mode_is_reported_separately():
+    """kg_set_tc_terms(1): one fp16 product instead of the three-term split (north_star: reduced-precision GEMM
+    variants, reported separately with their tolerance).  Default mode restored afterwards; the default result
+    stays fp32-accurate, the single-product one is within 2^-9 of |a||b| per entry."""
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    M, N, Kd = 4096, 512, 500
+    a = torch.randn(M, Kd, device=DEV, generator=gen)
+    b = torch.randn(Kd, N, device=DEV, generator=gen)
+    want = a.double() @ b.double()
+    bound = (a.double().norm(dim=1).view(-1, 1) * b.double().norm(dim=0).view(1, -1))
+    full = ops.gemm(a, b, torch.empty(M, N, device=DEV))
+    with ops.tensor_core_terms(1):
+        single = ops.gemm(a, b, torch.empty(M, N, device=DEV))
+    again = ops.gemm(a, b, torch.empty(M, N, device=DEV))
+    assert torch.equal(full, again)                                   # mode restored
+    e_full = float(((full.double() - want).abs() / bound).max())
+    e_single = float(((single.double() - want).abs() / bound).max())
+    assert e_full < 4e-6 and 1e-6 < e_single < 2.0 ** -9, (e_full, e_single)
+    # ranks: identical wherever the exact decision margin is wider than the single product's rounding
+    V, h, Mq = 4000, 500, 512
+    emb = torch.randn(V, h, device=DEV, generator=gen)
+    w = torch.randn(9, h, device=DEV, generator=gen)
+    qa = torch.randint(0, V, (Mq,), device=DEV, generator=gen, dtype=torch.int32)
+    qr = torch.randint(0, 9, (Mq,), device=DEV, generator=gen, dtype=torch.int32)
+    qb = torch.randint(0, V, (Mq,), device=DEV, generator=gen, dtype=torch.int32)
+    exact = ops.distmult_rank(emb, w, qa, qr, qb)
+    with ops.tensor_core_terms(1):
+        approx = ops.distmult_rank(emb, w, qa, qr, qb)
+    diff = (exact.long() - approx.long()).abs()
+    assert float((diff > 0).float().mean()) < 0.5 and int(diff.max()) <= 8

@@ -149,3 +149,28 @@ def test_neighbor_sampler_matches_reference_golden(golden):
     assert np.array_equal(node_id, gv["node_id"]) and np.array_equal(edge_type, gv["edge_type"])
     assert np.array_equal(data, gv["samples"])
     assert np.array_equal(g._src, gv["g_src"]) and np.array_equal(g._dst, gv["g_dst"])
+
+
+def test_entity_classify_directory_loader(tmp_path):
+    """N4: the on-disk typed-graph loader that stands in for dgl.contrib.data.load_data (kgvae/entity_classify.py:47):
+    inverse relation types, self-loops, (dst, src, type) order, per-(dst, type) norms, bfs pruning, relabelling."""
+    from gcn_vae_b200 import entity_classify as EC
+    (tmp_path / "edges.tsv").write_text("a\tknows\tb\nb\tknows\tc\nc\tlikes\ta\nd\tlikes\te\nx\tknows\ty\n")
+    (tmp_path / "trainingSet.tsv").write_text("a\tperson\nc\trobot\n")
+    (tmp_path / "testSet.tsv").write_text("b\tperson\n")
+    full = EC.load_data(str(tmp_path), bfs_level=0)
+    n, E = full.num_nodes, len(full.edge_src)
+    assert (n, full.num_rels, full.num_classes) == (7, 5, 2) and E == 2 * 5 + 7
+    order = np.lexsort((full.edge_type, full.edge_src, full.edge_dst))
+    assert np.array_equal(order, np.arange(E))                       # sorted by (dst, src, type)
+    assert np.all(full.edge_type[full.edge_src == full.edge_dst] == 4)   # self-loop relation = 2 P
+    for d, t_, w_ in zip(full.edge_dst, full.edge_type, full.edge_norm):
+        assert abs(w_ - 1.0 / np.sum((full.edge_dst == d) & (full.edge_type == t_))) < 1e-7
+    assert list(full.labels[full.train_idx]) == [0, 1] and list(full.labels[full.test_idx]) == [0]
+    # one round from the labelled nodes {a, b, c}: only edges INTO them survive; d, e, x, y are never reached
+    pruned = EC.load_data(str(tmp_path), bfs_level=1)
+    assert set(pruned.edge_dst.tolist()) <= {0, 1, 2} and len(pruned.edge_src) == 3 + 6
+    small = EC.load_data(str(tmp_path), bfs_level=2, relabel=True)
+    assert small.num_nodes == 3 and small.edge_src.max() < 3 and small.edge_dst.max() < 3
+    toy = EC.load_data("toy:3")
+    assert toy.num_nodes == 300 and len(toy.edge_src) == 2500
