@@ -567,7 +567,10 @@ def run_entity(args):
     training epoch as in entity_classify.py:106-113: forward over every edge (input layer = basis lookup
     sum_b coef[r,b] V[b, src, :] without materialising the [R, N, h] table, output layer = dense basis
     conv + softmax), cross-entropy on the training nodes, backward, Adam(weight_decay).  value = directed
-    edges per second; N > 1 runs independent replicas (weak scaling, gradients all-reduced)."""
+    edges per second.  N > 1: ONE graph over the N GPUs (strong scaling) - the 2.67 GB basis table and its Adam
+    state are sharded by source-node owner, the partial hidden states (67 MB) are all-reduced, the output layer
+    is destination-partitioned (entity_classify.PartitionedEntityClassify); --replicas runs the old weak-scaling
+    form (one full graph per rank, gradients all-reduced)."""
     import torch.distributed as dist
     import torch.nn.functional as F
     import gcn_vae_b200 as K
@@ -585,7 +588,8 @@ def run_entity(args):
     clocks = ClockSampler(local)
     n_hidden, n_bases, l2norm = 10, 40, 5e-4
     t0 = time.perf_counter()
-    data = EC.synthetic_graph("am", seed=rank, scale=args.scale)
+    partitioned = world > 1 and not args.replicas
+    data = EC.synthetic_graph("am", seed=0 if partitioned else rank, scale=args.scale)
     log(f"synthetic AM-shaped graph: {time.perf_counter() - t0:.1f}s; nodes={data.num_nodes} edges={len(data.edge_src)}")
     E, N = len(data.edge_src), data.num_nodes
     pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory()
@@ -595,11 +599,16 @@ def run_entity(args):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
     torch.manual_seed(0)
-    model = EC.EntityClassify(N, n_hidden, data.num_classes, data.num_rels, num_bases=n_bases, num_hidden_layers=0,
+    n_table = N
+    if partitioned:
+        lo_p, hi_p = K.parallel.block_range(N, rank, world)
+        n_table = hi_p - lo_p
+    model = EC.EntityClassify(n_table, n_hidden, data.num_classes, data.num_rels, num_bases=n_bases, num_hidden_layers=0,
                               dropout=0.0, use_self_loop=False, use_cuda=True).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=l2norm, fused=True)
     params = [p for p in model.parameters() if p.requires_grad]
     feats = model.create_features()
+    pe = EC.PartitionedEntityClassify(model, data, rank, world, dev) if partitioned else None
 
     graphs = {}
 
@@ -616,7 +625,17 @@ def run_entity(args):
             graphs[key] = gr
         return graphs[key]
 
+    def step_partitioned():
+        opt.zero_grad(set_to_none=True)
+        loss = pe.loss(pe.logits())
+        loss.backward()
+        pe.reduce_grads()
+        opt.step()
+        return loss
+
     def step(t):
+        if partitioned:
+            return step_partitioned()
         gr = graph_of(t)
         opt.zero_grad(set_to_none=True)
         logits = model(gr, feats, t["etype"], t["norm"])
@@ -628,6 +647,8 @@ def run_entity(args):
         return loss
 
     def e2e_step():
+        if partitioned:                      # the graph shards stay resident (built once, as in the reference)
+            return float(step_partitioned())
         return float(step({k: v.to(dev, non_blocking=True) for k, v in host.items()}))
 
     def timed(fn, n_steps):
@@ -684,10 +705,11 @@ def run_entity(args):
     pk = peaks()
     # algorithmic bytes of the input-layer lookup: per edge the n_bases rows
     # V[b, src, :] (4*h bytes each) + the 16-byte record + the coefficient row; per node the h-wide output
-    table = 4 * n_bases * N * n_hidden                # the basis table V [n_bases, N, h]: 2.67 GB
-    ab = {"kg_basis_id_src_fwd": table + E * (16 + 4 * n_hidden) + 4 * N * n_hidden,   # V once, record + out row per edge
+    table = 4 * n_bases * n_table * n_hidden          # this rank's rows of the basis table V [n_bases, N, h] (2.67 GB in all)
+    e_rank = E // world if partitioned else E         # edges one launch walks
+    ab = {"kg_basis_id_src_fwd": table + e_rank * (16 + 4 * n_hidden) + 4 * N * n_hidden,   # V once, record + out row per edge
           # backward: V read once, dV written once, record + upstream gradient row per edge
-          "kg_basis_id_src_bwd": 2 * table + E * (16 + 4 * n_hidden)}
+          "kg_basis_id_src_bwd": 2 * table + e_rank * (16 + 4 * n_hidden)}
     roof = None
     for tag, ms in top:
         if tag in ab:
@@ -698,19 +720,23 @@ def run_entity(args):
                     "algorithmic_bytes": ab[tag], "share_of_step": ms / total_ops,
                     "regime": "streaming: the basis table V is 2.67 GB, its gradient another 2.67 GB"}
             break
-    total_edges = E * world * args.steps
+    total_edges = E * (1 if partitioned else world) * args.steps
     line = {
         "metric": METRIC, "value": total_edges / (ms_dev * 1e-3), "unit": "edges/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {"workload": "am-entity", "nodes": N, "relations": data.num_rels, "graph_edges": E,
                    "classes": data.num_classes, "n_hidden": n_hidden, "n_bases": n_bases, "l2norm": l2norm,
                    "train_nodes": len(data.train_idx), "scale": args.scale,
-                   "parallelism": f"replicas x{world} (grad all-reduce)",
+                   "parallelism": (f"one graph over {world} GPUs: basis table sharded by source owner, hidden state "
+                                   f"all-reduced, output layer destination-partitioned") if partitioned else
+                                  f"replicas x{world} (grad all-reduce)",
                    "timed": "fwd + cross-entropy + bwd + Adam (graph built once before the epochs, as in the reference); "
                             "per-step CUDA events",
                    "l2": "inputs (2.67 GB basis table) far larger than L2"},
-        "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_bytes,
+        "e2e": {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s",
+                "h2d_bytes_per_step": 0 if partitioned else h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clock_info, "roofline": roof, "cpu_baseline": None,
     }
@@ -957,6 +983,22 @@ def run_gpu(args):
         emb_once = model(tg, t_ids, t_rel, t_norm)          # one sample of z for the raw / filtered comparison
     rk_raw = eval_ranks(test_dev, emb=emb_once).float() + 1
     rk_filt = eval_ranks(test_dev, filtered=True, emb=emb_once).float() + 1
+    # single-product tensor-core mode (north_star: reduced-precision GEMM variant, reported separately): one fp16
+    # product per k-step instead of the fp32-accurate three-term split; ranks then carry the 11-bit operand rounding
+    with K.ops.tensor_core_terms(1):
+        eval_ranks(test_dev)
+        L.profile = {}
+        ms_eval_1p = max_over_ranks(timed(lambda: eval_ranks(test_dev), args.steps))
+        prof_1p, L.profile = L.profile, None
+        rk_1p = eval_ranks(test_dev, emb=emb_once).float() + 1
+    d1p = (rk_1p - rk_raw).abs()
+    single_product = {"value": len(data.test) * args.steps / (ms_eval_1p * 1e-3), "unit": "triples/s",
+                      "ms": ms_eval_1p / args.steps,
+                      "rank_launch_ms": (lambda e: sum(a.elapsed_time(b) for a, b in e) / len(e))(prof_1p["kg_distmult_rank"]),
+                      "ranks_identical_frac": float((d1p == 0).float().mean()), "max_rank_diff": float(d1p.max()),
+                      "mrr_exact": float((1.0 / rk_raw).mean()), "mrr_single_product": float((1.0 / rk_1p).mean()),
+                      "what": "kg_set_tc_terms(1): operands rounded to 11 significant bits (per-row scaled fp16), no "
+                              "fp32 re-scoring band; NOT the default - every parity claim is on the three-term mode"}
     mrr_raw, mrr_filt = float((1.0 / rk_raw).mean()), float((1.0 / rk_filt).mean())
     filt_ok = bool((rk_filt <= rk_raw).all())              # filtering can only improve a rank
     sync_all()
@@ -1078,6 +1120,11 @@ def run_gpu(args):
                     "setting": f"{T} test triples x 2 directions x {data.num_nodes} candidates, encoder included"}
     if roof is not None:
         roof["tensor"] = eval_roof
+        if eval_roof is not None:
+            flops_1p = 2.0 * len(data.test) * (hi - lo) * H
+            single_product["algorithmic_tflops"] = flops_1p / (single_product["rank_launch_ms"] * 1e-3) / 1e12
+            single_product["frac_of_bf16_sustained"] = single_product["algorithmic_tflops"] / pk["bf16_tflops"]
+            eval_roof["single_product"] = single_product
         roof["eval"] = eval_summary
         roof["partitioned"] = partitioned
         roof["gemm_vs_library"] = gemm_cmp
@@ -1145,6 +1192,8 @@ def main():
     ap.add_argument("--peer", action="store_true",
                     help="wikikg2-part: the message-passing kernels gather layer inputs from peer HBM (CUDA IPC over "
                          "NVLink) instead of the NCCL all-gather")
+    ap.add_argument("--replicas", action="store_true",
+                    help="am-entity with N > 1: independent replicas (weak scaling) instead of one graph over the N GPUs")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="skip the wikikg2-shaped destination-partitioned leg of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")

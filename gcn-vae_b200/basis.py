@@ -125,6 +125,39 @@ class BasisIdConvFn(torch.autograd.Function):
         return None, dV, dcoef, dloop, dbias, None, None, None
 
 
+class BasisIdSrcPartialFn(torch.autograd.Function):
+    """Source-sharded form of the integer-id input layer (multi-GPU entity classification): this rank holds the
+    rows V[:, lo:hi, :] of the basis table and every edge whose SOURCE it owns (local source ids, global
+    destination ids); the result is this rank's PARTIAL sum of messages for all ``n_global`` destinations - the
+    caller sums the partials over the ranks (parallel.AllReduceSumFn, whose backward all-reduces the gradient).
+    dV needs no communication at all: every row of the table is written by its owner."""
+
+    @staticmethod
+    def forward(ctx, V, coef, gi, n_global):
+        V, cf = _c(V), _c(coef)
+        NB, n_local, out_f = V.shape
+        if not L.lib().kg_basis_id_src_eligible(cf.shape[0], NB, out_f):
+            raise RuntimeError("source-sharded basis layer: shape not covered (num_bases <= 64, out_feat <= 16)")
+        gi.ensure_node_major()
+        agg = torch.zeros((n_global, out_f), dtype=torch.float32, device=V.device)
+        L.call("kg_basis_id_src_fwd", L.f32(V), L.f32(cf), L.i32(gi.col_ptr), L.i32(gi.bwd_pack), n_local,
+               cf.shape[0], NB, out_f, L.f32(agg), L.stream())
+        ctx.save_for_backward(V, cf)
+        ctx.gi = gi
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        V, cf = ctx.saved_tensors
+        gi = ctx.gi
+        NB, n_local, out_f = V.shape
+        dV = torch.empty_like(V)
+        dcoef = torch.zeros_like(cf)
+        L.call("kg_basis_id_src_bwd", L.f32(V), L.f32(cf), L.f32(_c(g)), L.i32(gi.col_ptr), L.i32(gi.bwd_pack),
+               n_local, cf.shape[0], NB, out_f, L.f32(dV), L.f32(dcoef), L.stream())
+        return dV, dcoef, None, None
+
+
 class BasisDenseConvFn(torch.autograd.Function):
     """Dense features with composed per-relation weights W [R, in, out]."""
 

@@ -61,6 +61,78 @@ def synthetic_graph(name="am", seed=0, scale=1.0):
 
 
 # --------------------------------------------------------------------------------------------
+# multi-GPU form (new; the reference is single-process, kgvae/entity_classify.py:66-72)
+# --------------------------------------------------------------------------------------------
+class PartitionedEntityClassify:
+    """Entity classification over the GPUs of one box (BASELINE.json configs[3]: "1/2/4/8 B200").
+
+    The integer-id input layer is an embedding-style lookup into the basis table V [B, N, h] (2.67 GB at the AM
+    shape) - so it is sharded by SOURCE-row ownership: rank p holds V[:, lo_p:hi_p, :] (and its
+    Adam state) and every edge whose source it owns, computes that share of the messages for all destinations
+    (h = 10: a 67 MB matrix) and the partial sums are all-reduced; its backward all-reduces the gradient of that
+    matrix once, after which every row of dV is produced by its owner without any communication.  The output
+    layer (dense basis conv h -> classes, softmax) is destination-partitioned on the all-reduced hidden state.
+    Replicated parameters (coefficients, output-layer basis, biases) receive partial gradients: SUM over ranks.
+
+    ``model``: an EntityClassify built with ``num_nodes = hi - lo`` (the table shard), two layers."""
+
+    def __init__(self, model, data, rank, world, device, group=None):
+        from . import parallel
+        from .graph import Graph
+        if len(model.layers) != 2:
+            raise RuntimeError("partitioned entity classification covers the two-layer model (the reference's AM flags)")
+        self.model, self.rank, self.world, self.group = model, rank, world, group
+        self.n_global = int(data.num_nodes)
+        self.lo, self.hi = parallel.block_range(self.n_global, rank, world)
+        src, dst = np.asarray(data.edge_src), np.asarray(data.edge_dst)
+        et, nm = np.asarray(data.edge_type), np.asarray(data.edge_norm, dtype=np.float32)
+        own_src = (src >= self.lo) & (src < self.hi)
+        own_dst = (dst >= self.lo) & (dst < self.hi)
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(device)
+        self.g_src = Graph()                 # edges by source owner: local source ids, global destinations
+        self.g_src._n = self.n_global
+        self.g_src._dev_edges[torch.device(device)] = (to(src[own_src] - self.lo, torch.int32), to(dst[own_src], torch.int32))
+        self.et_src, self.nm_src = to(et[own_src], torch.int32), to(nm[own_src].reshape(-1, 1), torch.float32)
+        self.g_dst = Graph()                 # edges by destination owner: global ids on both ends
+        self.g_dst._n = self.n_global
+        self.g_dst._dev_edges[torch.device(device)] = (to(src[own_dst], torch.int32), to(dst[own_dst], torch.int32))
+        self.et_dst, self.nm_dst = to(et[own_dst], torch.int32), to(nm[own_dst].reshape(-1, 1), torch.float32)
+        tr = np.asarray(data.train_idx)
+        self.n_train = len(tr)
+        self.train_own = to(tr[(tr >= self.lo) & (tr < self.hi)], torch.int64)
+        self.labels = to(np.asarray(data.labels), torch.int64)
+        self.sharded = [model.layers[0].weight]
+        self.replicated = [p for p in model.parameters() if p.requires_grad and p is not model.layers[0].weight]
+
+    def logits(self):
+        from . import basis, parallel
+        l1, l2 = self.model.layers[0], self.model.layers[1]
+        if l1.self_loop:
+            raise RuntimeError("partitioned entity classification: use_self_loop is not supported")
+        gi = self.g_src.index_for(self.et_src, self.nm_src, l1.num_rels, node_major=True)
+        part = basis.BasisIdSrcPartialFn.apply(l1.weight, l1.w_comp, gi, self.n_global)
+        agg = parallel.AllReduceSumFn.apply(part, self.group)
+        if l1.bias:                          # every rank computes the same bias gradient: count it once in the SUM
+            b = l1.h_bias
+            agg = agg + (b.detach() + (b - b.detach()) / self.world)
+        h1 = F.relu(agg)
+        return l2(self.g_dst, h1, self.et_dst, self.nm_dst)
+
+    def loss(self, logits):
+        """This rank's share of F.cross_entropy(logits[train_idx], labels[train_idx]) (entity_classify.py:110):
+        the sum over its own training nodes divided by the GLOBAL count - the shares add up to the reference's loss."""
+        idx = self.train_own
+        if idx.numel() == 0:
+            return logits.sum() * 0.0
+        return F.cross_entropy(logits[idx], self.labels[idx], reduction="sum") / self.n_train
+
+    def reduce_grads(self):
+        from . import parallel
+        if self.world > 1:
+            parallel.allreduce_sum_grads(self.replicated, group=self.group)
+
+
+# --------------------------------------------------------------------------------------------
 # on-disk typed graphs (stands in for dgl.contrib.data.load_data, kgvae/entity_classify.py:47)
 # --------------------------------------------------------------------------------------------
 def _bfs_keep_edges(src, dst, seeds, num_nodes, levels):

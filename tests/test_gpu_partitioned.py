@@ -49,3 +49,31 @@ def test_partitioned_step_matches_single_gpu(n_flows, mode, mmd):
         res = [out[r] for r in range(WORLD)]
     for r in range(WORLD):
         assert res[r]["loss"] <= 1e-4 and res[r]["z"] <= 1e-4 and max(res[r]["grads"].values()) <= (2e-4 if mmd == 0 else 1e-3)
+
+
+def _entity_worker(rank, port, out):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gcn_vae_b200 as K
+    import partition_selfcheck
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=dev)
+    try:
+        out[rank] = partition_selfcheck.run_entity(K, dev, rank, WORLD)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_entity_classification_matches_single_gpu():
+    """configs[3] over 2 GPUs: basis table sharded by source owner, output layer destination-partitioned."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs 2 GPUs")
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_entity_worker, args=(port, out), nprocs=WORLD, join=True)
+        res = [out[r] for r in range(WORLD)]
+    for r in range(WORLD):
+        assert res[r]["loss"] <= 1e-4 and res[r]["logits"] <= 1e-4 and max(res[r]["grads"].values()) <= 2e-4
