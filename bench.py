@@ -325,7 +325,7 @@ def gemm_vs_library(dev, log, iters=10):
     return out
 
 
-def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edges=32_000_000, iters=5):
+def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edges=32_000_000, iters=5, l2_peak=None):
     """RGCN(bdd) message passing at the ogbl-wikikg2 shape (BASELINE.json configs[4]: 2.5 M entities,
     2 x 535 relation types, 2 x 16 M directed edges, h = 500, 100 blocks) on ONE GPU: the regime the
     HBM-roofline target of north_star is about - every feature matrix (5 / 10 GB) is far larger than
@@ -394,6 +394,18 @@ def streaming_layer_bench(dev, pk, log, n_nodes=2_500_000, n_etypes=1070, n_edge
                 ab = algorithmic_bytes(name, {"N": n_nodes, "E": n_edges, "S": 0, "R2": n_etypes, "R": n_etypes // 2})
                 res[name] = {"ms": t, "algorithmic_bytes": ab, "achieved_gbs": ab / t / 1e6,
                              "frac_of_hbm_peak": ab / t / 1e6 / pk["hbm_gbs"], "edges_per_s": n_edges / t * 1e3}
+                # the second bound of these launches: every edge's message (forward: `out` floats) or source gradient
+                # (backward: `in` floats) is REDUCED into an L2-resident tile; the probe gives what L2 sustains for
+                # whole-row reductions.  The 5x10 forward reduces 4 KB per edge for 2 KB gathered: reduce-bound.
+                red_bytes = n_edges * 4 * (out_f if name.startswith("kg_bdd_rel_fwd") else in_f)
+                res[name]["reduce_bytes"] = red_bytes
+                if l2_peak:
+                    floor_ms = max(ab / pk["hbm_gbs"] / 1e6, red_bytes / l2_peak["reduce_gbs"] / 1e6)
+                    res[name]["l2_reduce_gbs"] = red_bytes / t / 1e6
+                    res[name]["frac_of_l2_reduce_probe"] = red_bytes / t / 1e6 / l2_peak["reduce_gbs"]
+                    res[name]["floor_ms"] = floor_ms
+                    res[name]["frac_of_floor"] = floor_ms / t
+                    res[name]["bound"] = "l2 reductions" if red_bytes / l2_peak["reduce_gbs"] > ab / pk["hbm_gbs"] else "hbm"
                 log(f"  [streaming/{graph_kind}] {name:26s} {t:8.2f} ms  {ab / t / 1e6:8.0f} GB/s  "
                     f"{100 * ab / t / 1e6 / pk['hbm_gbs']:5.1f}% of measured HBM peak")
             del agg, dx, dw, weight, w_fwd, w_bwd
@@ -1105,7 +1117,7 @@ def run_gpu(args):
     if world == 1 and not args.no_streaming:
         model = opt = buckets = None
         torch.cuda.empty_cache()
-        streaming = streaming_layer_bench(dev, pk, log)
+        streaming = streaming_layer_bench(dev, pk, log, l2_peak=l2_peak)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
