@@ -182,10 +182,15 @@ __global__ void __launch_bounds__(128)
 kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
                   const float* __restrict__ zv, const float* __restrict__ z_pre,
                   const float* __restrict__ ws, const float* __restrict__ resp, float scale, int n,
-                  int h, int k, float* __restrict__ dz, float* __restrict__ dmean,
+                  int h, int k, const float* __restrict__ coefs, const float* __restrict__ add,
+                  float* __restrict__ dz, float* __restrict__ dmean,
                   float* __restrict__ dvar, float* __restrict__ dz_pre) {
   const int d = blockIdx.y * blockDim.x + threadIdx.x;
   if (d >= h) return;
+  // fused form (kg_kl_mog_bwd_fused): the whole gradient of the loss head wrt z in one pass -
+  //   dz = coefs[0] * dKL/dz + coefs[1] * add + coefs[2] * z     (add: dz of the DistMult term; z: the regulariser)
+  const float c_add = coefs ? __ldg(coefs + 1) : 0.f, c_z = coefs ? __ldg(coefs + 2) : 0.f;
+  if (coefs) scale *= __ldg(coefs);
   const int r0 = blockIdx.x * kKlRows, r1 = min(n, r0 + kKlRows);
   float pm[kMaxMix], ipv[kMaxMix], gpm[kMaxMix], gpv[kMaxMix];
 #pragma unroll
@@ -214,7 +219,9 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
         gpm[i] -= q;
         gpv[i] -= ri * (0.5f * u * u * ipv[i] * ipv[i] - 0.5f * ipv[i]);
       }
-    dz[off] = scale * gz;
+    float out = scale * gz;
+    if (coefs) out += c_z * zc + (add ? c_add * add[off] : 0.f);
+    dz[off] = out;
   }
 #pragma unroll
   for (int i = 0; i < kMaxMix; ++i)
@@ -259,7 +266,25 @@ extern "C" int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z
   if (n == 0) return KG_OK;
   dim3 grid(kg_div_up(n, kKlRows), kg_div_up(h, 128));
   kl_mog_bwd_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, z_mean, z_var, z_pre, prior_ws, resp, scale, n,
-                                                         h, k, dz, dmean, dvar, dz_pre);
+                                                         h, k, nullptr, nullptr, dz, dmean, dvar, dz_pre);
+  KG_LAUNCH_OK();
+  return KG_OK;
+}
+
+// The same pass producing the COMBINED gradient of the loss head (kgvae/link_predict.py:74-91) wrt z:
+//   dz = coefs[0] * scale * dKL/dz + coefs[1] * add + coefs[2] * z;   dmean, dvar, dz_pre scaled by coefs[0] * scale
+// coefs: device [3] (upstream gradient times kl_param; times 1 for the DistMult term `add` [n, h], may be NULL;
+// times 2 reg_param / (n h) for the regulariser mean(z^2)).
+extern "C" int kg_kl_mog_bwd_fused(const float* z, const float* z_mean, const float* z_var,
+                                   const float* z_pre, const float* prior_ws, const float* resp, float scale,
+                                   int n, int h, int k, const float* coefs, const float* add, float* dz,
+                                   float* dmean, float* dvar, float* dz_pre, void* stream) {
+  KG_REQUIRE(n >= 0 && h > 0 && k > 0 && k <= kMaxMix, "kl bwd: need 0 < k <= 16");
+  KG_REQUIRE(coefs != nullptr, "kl bwd fused: coefs is required");
+  if (n == 0) return KG_OK;
+  dim3 grid(kg_div_up(n, kKlRows), kg_div_up(h, 128));
+  kl_mog_bwd_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, z_mean, z_var, z_pre, prior_ws, resp, scale, n,
+                                                         h, k, coefs, add, dz, dmean, dvar, dz_pre);
   KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -69,9 +69,25 @@ class LinkPredict(nn.Module):
             return self._get_loss_partitioned(g.partition, embed, triplets, labels)
         trip = ops.as_i32(triplets, embed.device)
         lab = torch.as_tensor(labels, dtype=torch.float32, device=embed.device)
+        zero = lambda: torch.zeros(1, device=embed.device)
+        enc = self.encoder
+        if isinstance(enc, KGVAE) and embed.requires_grad:
+            # pred + reg + KL in one autograd node: their gradients wrt z are combined in a single pass
+            flp = enc.flow_log_prob if enc.n_flows > 0 else None
+            head, predict_loss, reg_loss, kl_core = ops.LossHeadFn.apply(
+                embed, enc.z_mean, enc.z_sigma, enc.z_pre, self.w_relation, trip, lab, self._flow_shift(),
+                self.reg_param, self.kl_param)
+            # the reference adds None here when n_flows == 0 and crashes; None -> 0
+            kl = (kl_core if flp is None else kl_core + flp) if self.kl_param > 0 else zero()
+            mmd = enc.get_mmd(embed) if self.mmd_param > 0 else zero()
+            loss = head
+            if self.kl_param > 0 and flp is not None:
+                loss = loss + self.kl_param * flp
+            if self.mmd_param > 0:
+                loss = loss + self.mmd_param * mmd
+            return loss, predict_loss, kl, mmd
         predict_loss = ops.DistMultBceFn.apply(embed, self.w_relation, trip, lab, self._flow_shift())
         reg_loss = self.regularization_loss(embed)
-        zero = lambda: torch.zeros(1, device=embed.device)
         kl = self.encoder.get_kl(embed) if self.kl_param > 0 else zero()
         mmd = self.encoder.get_mmd(embed) if self.mmd_param > 0 else zero()
         loss = predict_loss + self.reg_param * reg_loss + self.kl_param * kl + self.mmd_param * mmd

@@ -585,6 +585,88 @@ class DistMultBceFn(torch.autograd.Function):
         return dzo, dwo, None, None, dshift
 
 
+class LossHeadFn(torch.autograd.Function):
+    """The loss head of LinkPredict.get_loss in one autograd node (kgvae/link_predict.py:74-91):
+
+        pred = mean BCE-with-logits(DistMult(z, w, triplets) + shift, labels)      (kg_distmult_bce_fwd)
+        reg  = mean(z^2) + mean(w^2)                                               (kg_sum_squares)
+        kl   = mean_n[log N(z; m, v) - log MoG(z)]                                 (kg_kl_mog_fwd)
+        loss = pred + reg_param * reg + kl_param * kl
+
+    Returns (loss, pred, reg, kl).  As separate Functions these three terms each produced their own [n, h]
+    gradient wrt z, scaled it by the upstream scalar with an elementwise multiply, and autograd added the three
+    up: ten elementwise passes over 29 MB matrices.  Here backward forms the total in the KL backward pass
+    (kg_kl_mog_bwd_fused): dz = c_kl dKL/dz + c_pred dz_pred + c_reg (2 / n h) z, coefficients on the device.
+    The scalar flow terms (flow_log_prob in the scores' shift and in the KL) stay with the caller."""
+
+    @staticmethod
+    def forward(ctx, z, z_mean, z_var, z_pre, w, triplets, labels, shift, reg_param, kl_param):
+        z, w, labels = _c(z), _c(w), _c(labels)
+        S, (n, h) = triplets.shape[0], z.shape
+        dev = z.device
+        idx = TripletIndex(triplets, n, w.shape[0], entity_index=False)
+        g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
+        dw = torch.zeros_like(w)
+        dz_pred = torch.zeros_like(z)
+        out = torch.empty(2, dtype=torch.float32, device=dev)         # pred loss, sum of g
+        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
+        ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
+        L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
+               None, L.f32(g), L.f32(dw), L.f32(dz_pred), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
+               L.stream())
+        pred = out[0].clone()
+        reg = _reduce("kg_sum_squares", z) / z.numel() + _reduce("kg_sum_squares", w) / w.numel()
+        use_kl = kl_param > 0 and z_mean is not None
+        if use_kl:
+            z_mean, z_var = _c(z_mean), _c(z_var)
+            zp = _c(z_pre.reshape(-1, z_pre.shape[-1]))
+            k = zp.shape[0] // 2
+            pws = torch.empty((3, k, h), dtype=torch.float32, device=dev)
+            rows = torch.empty(n, dtype=torch.float32, device=dev)
+            resp = torch.empty((n, k), dtype=torch.float32, device=dev)
+            L.call("kg_kl_mog_fwd", L.f32(z), L.f32(z_mean), L.f32(z_var), L.f32(zp), n, h, k, L.f32(pws),
+                   L.f32(rows), L.f32(resp), L.stream())
+            kl = _reduce("kg_sum", rows) / n
+            ctx.save_for_backward(z, w, dz_pred, dw, out, z_mean, z_var, zp, pws, resp)
+            loss = pred + reg_param * reg + kl_param * kl
+        else:
+            kl = torch.zeros((), dtype=torch.float32, device=dev)
+            ctx.save_for_backward(z, w, dz_pred, dw, out)
+            loss = pred + reg_param * reg
+        ctx.use_kl, ctx.reg_param, ctx.kl_param = use_kl, float(reg_param), float(kl_param)
+        ctx.shift_shape = None if shift is None else shift.shape
+        ctx.pre_shape = None if z_pre is None else z_pre.shape
+        return loss, pred, reg, kl
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pred, g_reg, g_kl):
+        saved = ctx.saved_tensors
+        z, w, dz_pred, dw, out = saved[:5]
+        n, h = z.shape
+        zero = torch.zeros((), dtype=torch.float32, device=z.device)
+        g_loss, g_pred, g_reg, g_kl = ((zero if t is None else t.reshape(()).to(torch.float32))
+                                       for t in (g_loss, g_pred, g_reg, g_kl))
+        c_pred = g_loss + g_pred
+        c_reg = g_loss * ctx.reg_param + g_reg
+        c_kl = g_loss * ctx.kl_param + g_kl
+        dm = dv = dzp = None
+        if ctx.use_kl:
+            z_mean, z_var, zp, pws, resp = saved[5:]
+            k = zp.shape[0] // 2
+            coefs = torch.stack([c_kl, c_pred, c_reg * (2.0 / z.numel())]).contiguous()
+            dz, dm, dv = (torch.empty_like(z) for _ in range(3))
+            dzp = torch.zeros_like(zp)
+            L.call("kg_kl_mog_bwd_fused", L.f32(z), L.f32(z_mean), L.f32(z_var), L.f32(zp), L.f32(pws), L.f32(resp),
+                   1.0 / n, n, h, k, L.f32(coefs), L.f32(dz_pred), L.f32(dz), L.f32(dm), L.f32(dv), L.f32(dzp),
+                   L.stream(), tag="kg_kl_mog_bwd")
+            dzp = dzp.view(ctx.pre_shape)
+        else:
+            dz = torch.addcmul(dz_pred * c_pred, z, c_reg * (2.0 / z.numel()))
+        dwo = torch.addcmul(dw * c_pred, w, c_reg * (2.0 / w.numel()))
+        dshift = (out[1] * c_pred).reshape(ctx.shift_shape) if ctx.shift_shape is not None else None
+        return dz, dm, dv, dzp, dwo, None, None, dshift, None, None
+
+
 class BceLogitsFn(torch.autograd.Function):
     """F.binary_cross_entropy_with_logits(score, labels), mean reduction (kgvae/link_predict.py:77)."""
 

@@ -228,6 +228,14 @@ int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z_var, const
 int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z_var, const float* z_pre,
                   const float* prior_ws, const float* resp, float scale, int n, int h, int k,
                   float* dz, float* dmean, float* dvar, float* dz_pre, void* stream);
+/* kg_kl_mog_bwd with the rest of the loss head folded in (link_predict.py:74-91): one pass writes the TOTAL
+ * gradient wrt z:  dz = coefs[0] scale dKL/dz + coefs[1] add + coefs[2] z  (add = dz of the DistMult + BCE
+ * term, may be NULL; z = the regulariser's 2 z / (n h), the factor folded into coefs[2]); dmean, dvar, dz_pre
+ * carry coefs[0] scale.  coefs: DEVICE [3], so the upstream gradient never visits the host. */
+int kg_kl_mog_bwd_fused(const float* z, const float* z_mean, const float* z_var, const float* z_pre,
+                        const float* prior_ws, const float* resp, float scale, int n, int h, int k,
+                        const float* coefs, const float* add, float* dz, float* dmean, float* dvar,
+                        float* dz_pre, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a6  IAF: element update of one MADE pass
