@@ -112,9 +112,8 @@ class PartitionedEntityClassify:
         gi = self.g_src.index_for(self.et_src, self.nm_src, l1.num_rels, node_major=True)
         part = basis.BasisIdSrcPartialFn.apply(l1.weight, l1.w_comp, gi, self.n_global)
         agg = parallel.AllReduceSumFn.apply(part, self.group)
-        if l1.bias:                          # every rank computes the same bias gradient: count it once in the SUM
-            b = l1.h_bias
-            agg = agg + (b.detach() + (b - b.detach()) / self.world)
+        if l1.bias:          # added after the sum: the gradient reaching it is each rank's PARTIAL one, so SUM is right
+            agg = agg + l1.h_bias
         h1 = F.relu(agg)
         return l2(self.g_dst, h1, self.et_dst, self.nm_dst)
 

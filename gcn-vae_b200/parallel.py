@@ -25,6 +25,29 @@ def world():
     return 0, 1
 
 
+class _exposed:
+    """Context manager: when bench.py has switched per-op profiling on (_lib.profile is a dict), record CUDA
+    events on the CURRENT stream around a collective (or around the wait for an asynchronous one).  The
+    compute stream idles while it waits for NCCL's stream, so the elapsed time is the communication time that
+    was NOT hidden behind compute - what bench.py reports as comm_ms."""
+
+    def __init__(self, tag):
+        self.tag = "nccl_exposed[" + tag + "]"
+
+    def __enter__(self):
+        if L.profile is not None:
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if L.profile is not None and hasattr(self, "ev0"):
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            L.profile.setdefault(self.tag, []).append((self.ev0, ev1))
+        return False
+
+
 def agree_scalar(value, op, group=None):
     """All-reduce of one integer over the group (on the backend's device type): the ranks leave with the
     same number, so decisions derived from it are taken identically everywhere."""
@@ -142,10 +165,11 @@ class GradBuckets:
             for b, n in enumerate(self._pending):
                 if n > 0:                     # unused parameters: zeros on this rank, still part of the layout
                     self._launch(b)
-            for h, b, op in self._handles:
-                h.wait()
-                if self.average and op == dist.ReduceOp.SUM:
-                    self.slices[b].div_(self.world_size)
+            with _exposed("gradient buckets"):
+                for h, b, op in self._handles:
+                    h.wait()
+                    if self.average and op == dist.ReduceOp.SUM:
+                        self.slices[b].div_(self.world_size)
         self._reset()
 
 
@@ -331,7 +355,8 @@ class PeerRows:
         self._own_ptr, self._peer_ptrs, self.views, self.local = None, [], [], None
 
     def barrier(self):
-        dist.all_reduce(self._sync, group=self.group)       # stream-ordered on every rank
+        with _exposed("peer barrier"):
+            dist.all_reduce(self._sync, group=self.group)       # stream-ordered on every rank
 
     def publish(self, x):
         if x.shape[0] > self.blk or x.shape[1] != self.width:
@@ -345,12 +370,13 @@ class _Pending:
     """An asynchronous collective and what turns its raw output into the result; ``wait()`` makes the current
     stream wait for it (the host does not block) and returns the result."""
 
-    def __init__(self, work, finish):
-        self.work, self.finish = work, finish
+    def __init__(self, work, finish, tag="collective"):
+        self.work, self.finish, self.tag = work, finish, tag
 
     def wait(self):
         if self.work is not None:
-            self.work.wait()
+            with _exposed(self.tag):
+                self.work.wait()
         return self.finish()
 
 
@@ -387,7 +413,7 @@ def allgather_rows_start(x_local, part):
                 return out[:n_global]
             parts = out.view((ws, pad) + tuple(x_local.shape[1:]))
             return torch.cat([parts[p][:n] for p, n in enumerate(sizes)], dim=0)
-    return _Pending(work, finish)
+    return _Pending(work, finish, "all-gather rows")
 
 
 def reduce_scatter_rows_start(g_full, part):
@@ -400,9 +426,9 @@ def reduce_scatter_rows_start(g_full, part):
             g_full = pad
         out = g_full.new_empty((part.blk,) + tuple(g_full.shape[1:]))
         work = dist.reduce_scatter_tensor(out, g_full[:rows], op=dist.ReduceOp.SUM, group=part.group, async_op=True)
-        return _Pending(work, lambda: out[:part.n_local])
+        return _Pending(work, lambda: out[:part.n_local], "reduce-scatter rows")
     work = dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=part.group, async_op=True)
-    return _Pending(work, lambda: g_full[part.lo:part.hi].clone())
+    return _Pending(work, lambda: g_full[part.lo:part.hi].clone(), "reduce-scatter rows")
 
 
 class AllGatherRowsFn(torch.autograd.Function):
@@ -412,12 +438,14 @@ class AllGatherRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, part):
         ctx.part = part
-        return allgather_rows(x_local.contiguous(), part.n_global, part.group, uniform=part.blk is not None)
+        with _exposed("all-gather rows"):
+            return allgather_rows(x_local.contiguous(), part.n_global, part.group, uniform=part.blk is not None)
 
     @staticmethod
     def backward(ctx, g_full):
         part = ctx.part
-        return reduce_scatter_rows(g_full.contiguous(), part), None
+        with _exposed("reduce-scatter rows"):
+            return reduce_scatter_rows(g_full.contiguous(), part), None
 
 
 def reduce_scatter_rows(g_full, part):
