@@ -460,7 +460,16 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(weight) && aligned16(agg)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
-    if (so == 5) return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    static const int exp = [] { const char* v = getenv("KG_EXP"); return v ? atoi(v) : 0; }();     // TEMPORARY: variant sweep
+    if (so == 5) {
+      if (exp % 10 == 1) return bddwarp::launch_fwd<5, 5, 4, 1, 4, 3>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+      if (exp % 10 == 2) return bddwarp::launch_fwd<5, 5, 4, 1, 6, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+      return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    }
+    if (exp / 10 % 10 == 1) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    if (exp / 10 % 10 == 2) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 4, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    if (exp / 10 % 10 == 3) return bddwarp::launch_fwd<5, 10, 2, 2, 6, 3>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    if (exp / 10 % 10 == 4) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 6>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
     return bddwarp::launch_fwd<5, 10, 2, 2, 8>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel fwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
@@ -501,8 +510,12 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
     // 2 KB weight-gradient role wait for the 4 KB input-gradient role on every edge)
     if ((hints & kHintStreamD) && so == 5)
       return bddwarp::launch_bwd_paired<5, 5, 4, 1, 6>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    static const int exp = [] { const char* v = getenv("KG_EXP"); return v ? atoi(v) : 0; }();     // TEMPORARY: variant sweep
     if (so == 5)
       return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    if (exp / 100 % 10 == 1) return bddwarp::launch_bwd<5, 10, 2, 2, 4, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    if (exp / 100 % 10 == 2) return bddwarp::launch_bwd<5, 10, 2, 2, 6, 3>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
+    if (exp / 100 % 10 == 3) return bddwarp::launch_bwd_paired<5, 10, 2, 2, 8>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
     return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel bwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");

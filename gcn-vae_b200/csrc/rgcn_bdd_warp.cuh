@@ -60,14 +60,18 @@ struct FwdLayout {
     lpw = lanes_per_warp(B / TB, WPS, CN);
     stage_f = round4(lpw * XN) + 4;
   }
-  __host__ __device__ int per_warp(int depth) const { return depth * stage_f + 2 * 32 * CN; }
-  __host__ size_t smem(int depth) const {
-    return sizeof(float) * ((size_t)4 * kChunk + (size_t)kWarps * per_warp(depth)) + sizeof(uint64_t) * kWarps * depth;
+  __host__ __device__ int per_warp(int depth, int nt) const { return depth * stage_f + nt * 32 * CN; }
+  __host__ size_t smem(int depth, int nt) const {
+    return sizeof(float) * ((size_t)4 * kChunk + (size_t)kWarps * per_warp(depth, nt)) + sizeof(uint64_t) * kWarps * depth;
   }
 };
 
-template <int FI, int FO, int TB, int WPS, int DEPTH>
-__global__ void __launch_bounds__(kCta)
+// NT = parked-output buffers per warp = bulk reductions a warp keeps in flight.  ncu on the 5x10 layer showed the
+// L1 -> XBAR path 80 % busy at 5.3 TB/s with two buffers: with 12 warps per SM that is 48 KB of reductions in
+// flight, i.e. the launch was bound by the LATENCY of a bulk reduction, not by the path; four buffers (and a
+// shallower gather ring to stay at three CTAs per SM) double the bytes in flight.
+template <int FI, int FO, int TB, int WPS, int DEPTH, int NT, int MINB>
+__global__ void __launch_bounds__(kCta, MINB)
 fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __restrict__ weight, int B, int hints,
            float* __restrict__ out) {
   constexpr int XN = TB * FI, CN = TB * FO, WN = TB * FI * FO, SLOTS = kWarps / WPS;
@@ -77,9 +81,9 @@ fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / WPS, wsl = warp % WPS;
   int4* P_s = reinterpret_cast<int4*>(sm);                     // [kChunk] {src, dst, etype, norm}
-  float* ring = sm + 4 * kChunk + warp * L.per_warp(DEPTH);    // [DEPTH][stage_f] this warp's slices
-  float* tbuf = ring + DEPTH * L.stage_f;                      // [2][32 * CN] parked outputs
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + 4 * kChunk + kWarps * L.per_warp(DEPTH)) + warp * DEPTH;
+  float* ring = sm + 4 * kChunk + warp * L.per_warp(DEPTH, NT);   // [DEPTH][stage_f] this warp's slices
+  float* tbuf = ring + DEPTH * L.stage_f;                         // [NT][32 * CN] parked outputs
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + 4 * kChunk + kWarps * L.per_warp(DEPTH, NT)) + warp * DEPTH;
   const int e0 = blockIdx.x * kChunk, n = min(E - e0, kChunk);
   for (int i = threadIdx.x; i < n; i += kCta) P_s[i] = __ldg(pack + e0 + i);
   if (lane == 0) {
@@ -137,8 +141,8 @@ fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __
         for (int i = 0; i < FI; ++i) a = fmaf(xv[tb * FI + i], w[(tb * FI + i) * FO + o], a);
         m[tb * FO + o] = a;
       }
-    float* tb_cur = tbuf + (k & 1) * 32 * CN;
-    bulk_wait_read<1>();                      // (lane 0 owns the groups) the reduction of edge k-2 has read this buffer
+    float* tb_cur = tbuf + (k % NT) * 32 * CN;
+    bulk_wait_read<NT - 1>();                 // (lane 0 owns the groups) the reduction of edge k-NT has read this buffer
     __syncwarp();
     park_raw<CN>(tb_cur + lane * CN, m);
     fence_async_smem();
@@ -168,15 +172,15 @@ struct BwdLayout {
     xoff_w = round4(lpw_w * DN) + 4;                           // dagg slice, then x slice
     stage_w = xoff_w + round4(lpw_w * XN) + 4;
   }
-  __host__ __device__ int x_warp(int depth) const { return depth * stage_x + 2 * 32 * XN; }
+  __host__ __device__ int x_warp(int depth, int nt) const { return depth * stage_x + nt * 32 * XN; }
   __host__ __device__ int w_warp(int depth) const { return depth * stage_w; }
-  __host__ __device__ int total_f(int depth) const { return SLOTS * WPR * (x_warp(depth) + w_warp(depth)); }
-  __host__ size_t smem(int depth) const {
-    return sizeof(float) * ((size_t)4 * kChunk + (size_t)total_f(depth)) + sizeof(uint64_t) * kWarps * depth;
+  __host__ __device__ int total_f(int depth, int nt) const { return SLOTS * WPR * (x_warp(depth, nt) + w_warp(depth)); }
+  __host__ size_t smem(int depth, int nt) const {
+    return sizeof(float) * ((size_t)4 * kChunk + (size_t)total_f(depth, nt)) + sizeof(uint64_t) * kWarps * depth;
   }
 };
 
-template <int SI, int SO, int TB, int WPR, int DEPTH>
+template <int SI, int SO, int TB, int WPR, int DEPTH, int NT>
 __global__ void __launch_bounds__(kCta)
 bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
            const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
@@ -190,10 +194,10 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
   const int wr_i = xrole ? wsl : wsl - WPR;   // warp index inside its role
   const int nx = slot * WPR + (xrole ? wsl : WPR), nw = slot * WPR + (xrole ? 0 : wsl - WPR);   // warps of each role before me
   int4* P_s = reinterpret_cast<int4*>(sm);
-  float* ring = sm + 4 * kChunk + nx * L.x_warp(DEPTH) + nw * L.w_warp(DEPTH);
+  float* ring = sm + 4 * kChunk + nx * L.x_warp(DEPTH, NT) + nw * L.w_warp(DEPTH);
   const int stage_f = xrole ? L.stage_x : L.stage_w;
-  float* tbuf = ring + DEPTH * stage_f;       // input-gradient warps only: [2][32 * XN]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + 4 * kChunk + L.total_f(DEPTH)) + warp * DEPTH;
+  float* tbuf = ring + DEPTH * stage_f;       // input-gradient warps only: [NT][32 * XN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + 4 * kChunk + L.total_f(DEPTH, NT)) + warp * DEPTH;
   const int e0 = blockIdx.x * kChunk, n = min(E - e0, kChunk);
   for (int i = threadIdx.x; i < n; i += kCta) P_s[i] = __ldg(pack + e0 + i);
   if (lane == 0) {
@@ -271,8 +275,8 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
           for (int o = 0; o < SO; ++o) a = fmaf(dv[tb * SO + o], r[(tb * SI + i) * SO + o], a);
           m[tb * SI + i] = nv * a;
         }
-      float* tb_cur = tbuf + (k & 1) * 32 * XN;
-      bulk_wait_read<1>();
+      float* tb_cur = tbuf + (k % NT) * 32 * XN;
+      bulk_wait_read<NT - 1>();
       __syncwarp();
       park_raw<XN>(tb_cur + lane * XN, m);
       fence_async_smem();
@@ -491,22 +495,22 @@ bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __res
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int FI, int FO, int TB, int WPS, int DEPTH>
+template <int FI, int FO, int TB, int WPS, int DEPTH, int NT = 2, int MINB = 1>
 int launch_fwd(RowSource feat, const void* pack, int E, const float* weight, int B, int hints, float* out,
                cudaStream_t st) {
-  const size_t smem = FwdLayout<FI, FO, TB, WPS>(B).smem(DEPTH);
-  auto kern = fwd_kernel<FI, FO, TB, WPS, DEPTH>;
+  const size_t smem = FwdLayout<FI, FO, TB, WPS>(B).smem(DEPTH, NT);
+  auto kern = fwd_kernel<FI, FO, TB, WPS, DEPTH, NT, MINB>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(feat, reinterpret_cast<const int4*>(pack), E, weight, B, hints, out);
   KG_LAUNCH_OK();
   return KG_OK;
 }
 
-template <int SI, int SO, int TB, int WPR, int DEPTH>
+template <int SI, int SO, int TB, int WPR, int DEPTH, int NT = 2>
 int launch_bwd(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
                float* dx, float* dW, cudaStream_t st) {
-  const size_t smem = BwdLayout<SI, SO, TB, WPR>(B).smem(DEPTH);
-  auto kern = bwd_kernel<SI, SO, TB, WPR, DEPTH>;
+  const size_t smem = BwdLayout<SI, SO, TB, WPR>(B).smem(DEPTH, NT);
+  auto kern = bwd_kernel<SI, SO, TB, WPR, DEPTH, NT>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
                                                  dx, dW);
