@@ -99,9 +99,16 @@ L2_STREAM_BYTES = 64 << 20          # a gathered matrix larger than this is read
 HINT_STREAM_X, HINT_STREAM_D, HINT_TILE_RESIDENT = 1, 2, 4
 
 
+TILE_MIN_EDGES_PER_ROW = 4           # below this, a tile's rows are touched too rarely for L2 residency to pay
+
+
 def _rel_order(gi, by_src, n_rows, row_bytes):
-    """the relation-major record list to walk for a reduction into ``n_rows`` rows of ``row_bytes``"""
-    if n_rows * row_bytes <= max(L2_TILE_BYTES, L2_RESIDENT_BYTES) or gi.n_edges == 0:
+    """the relation-major record list to walk for a reduction into ``n_rows`` rows of ``row_bytes``.  Node tiling
+    trades relation-run length (block weights reloaded, weight gradients flushed once per (tile, relation) group)
+    for L2 residency of the reduced rows; with few edges per reduced row - the backward pass of a destination-
+    partitioned rank spreads its 1/P of the edges over ALL source rows (1.6 edges per row at P = 8) - there is
+    nothing to keep resident and the groups shrink to a dozen edges, so the plain relation-major list is walked."""
+    if n_rows * row_bytes <= max(L2_TILE_BYTES, L2_RESIDENT_BYTES) or gi.n_edges < TILE_MIN_EDGES_PER_ROW * n_rows:
         return gi.rel_pack
     return gi.tiled_rel_pack(by_src, max(L2_TILE_BYTES // row_bytes, 256))
 
