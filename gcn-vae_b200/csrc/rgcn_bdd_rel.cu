@@ -21,7 +21,6 @@
 // so there is no CTA-wide barrier in the loop.  dX and dW share one kernel (both need the gathered
 // dagg row).  Summation order across CTAs is not fixed: results are reproducible to fp32 rounding.
 #include "common.cuh"
-#include <stdlib.h>
 
 #include "rgcn_bdd_own.cuh"
 #include "rgcn_bdd_tile.cuh"
@@ -460,16 +459,10 @@ extern "C" int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows
   cudaStream_t st = kg_stream(stream);
   if (weight && bddown::eligible(num_bases, si, so) && aligned16(x) && aligned16(weight) && aligned16(agg)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
-    static const int exp = [] { const char* v = getenv("KG_EXP"); return v ? atoi(v) : 0; }();     // TEMPORARY: variant sweep
-    if (so == 5) {
-      if (exp % 10 == 1) return bddwarp::launch_fwd<5, 5, 4, 1, 4, 3>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-      if (exp % 10 == 2) return bddwarp::launch_fwd<5, 5, 4, 1, 6, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-      return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    }
-    if (exp / 10 % 10 == 1) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    if (exp / 10 % 10 == 2) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 4, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    if (exp / 10 % 10 == 3) return bddwarp::launch_fwd<5, 10, 2, 2, 6, 3>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
-    if (exp / 10 % 10 == 4) return bddwarp::launch_fwd<5, 10, 2, 2, 4, 6>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
+    // (gather ring depth, reductions in flight per warp) = (4, 2) / (8, 2): a sweep at the wikikg2 shape
+    // (profiles/r02g_reduction_depth_sweep.txt) found 3-6 reductions in flight no faster - the 5x10 launch sits at
+    // 84 % of what L2 sustains for whole-row reductions (kg_probe_l2), not on the latency of a bulk reduction
+    if (so == 5) return bddwarp::launch_fwd<5, 5, 4, 1, 4>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
     return bddwarp::launch_fwd<5, 10, 2, 2, 8>(src, rel_pack, n_edges, weight, num_bases, hints, agg, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel fwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
@@ -505,17 +498,13 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
       aligned16(dx) && aligned16(dweight)) {
     const bddown::RowSource src{x, reinterpret_cast<const float* const*>(x_parts), part_rows};
     // dagg streams from HBM (wikikg2 shape): with 5x5 blocks the partner warps of the paired variant share one
-    // gather of dagg[dst] (103 GB of DRAM traffic instead of 148 GB, 25.0 vs 25.3 ms); with 5x10 blocks the
-    // independent warps win although they fetch the row twice (ncu: 40.1 vs 46.1 ms - the paired ring makes the
-    // 2 KB weight-gradient role wait for the 4 KB input-gradient role on every edge)
+    // gather of dagg[dst] (103 GB of DRAM traffic instead of 148 GB, 25.0 vs 25.3 ms); with 5x10 blocks the two
+    // variants time the same in the bench loop (48.7 vs 49.6 ms; under ncu 40.1 vs 46.1 ms), so the independent
+    // warps - no cross-warp handshake - serve every regime
     if ((hints & kHintStreamD) && so == 5)
       return bddwarp::launch_bwd_paired<5, 5, 4, 1, 6>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    static const int exp = [] { const char* v = getenv("KG_EXP"); return v ? atoi(v) : 0; }();     // TEMPORARY: variant sweep
     if (so == 5)
       return bddwarp::launch_bwd<5, 5, 4, 1, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    if (exp / 100 % 10 == 1) return bddwarp::launch_bwd<5, 10, 2, 2, 4, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    if (exp / 100 % 10 == 2) return bddwarp::launch_bwd<5, 10, 2, 2, 6, 3>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
-    if (exp / 100 % 10 == 3) return bddwarp::launch_bwd_paired<5, 10, 2, 2, 8>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
     return bddwarp::launch_bwd<5, 10, 2, 2, 4>(src, dagg, rel_pack, n_edges, weight, num_bases, hints, dx, dweight, st);
   }
   KG_REQUIRE(x_parts == nullptr, "bdd rel bwd: peer row blocks need the 5x5 / 5x10 block-owner kernels");
