@@ -105,9 +105,9 @@ class LinkPredict(nn.Module):
         lab = torch.as_tensor(labels, dtype=torch.float32, device=dev)
         counts = torch.tensor([float(trip.shape[0])], device=dev)
         torch.distributed.all_reduce(counts, group=part.group)
-        z_full = parallel.AllGatherRowsFn.apply(embed, part)
-        predict_loss = ops.DistMultBceFn.apply(z_full, self.w_relation, trip, lab, self._flow_shift())
-        predict_loss = predict_loss * (float(trip.shape[0]) / counts).reshape(())      # device scalar: no host sync
+        # the all-gather of z runs while the local terms (regulariser, KL) are computed; the reduce-scatter of dz is
+        # started inside the decoder's forward pass (the fused kernel has the gradient then) and waited for in backward
+        pending_z = parallel.allgather_rows_start(embed.detach(), part)
         frac = part.n_local / part.n_global
         reg_loss = ops.MeanSquareFn.apply(embed) * frac + ops.MeanSquareFn.apply(self.w_relation) / part.world_size
         zero = lambda: torch.zeros(1, device=dev)
@@ -117,6 +117,9 @@ class LinkPredict(nn.Module):
                 kl = kl + self.encoder.flow_log_prob / part.world_size
         else:
             kl = zero()
+        predict_loss = ops.PartitionedDistMultBceFn.apply(embed, self.w_relation, trip, lab, self._flow_shift(),
+                                                          part, pending_z)
+        predict_loss = predict_loss * (float(trip.shape[0]) / counts).reshape(())      # device scalar: no host sync
         if self.mmd_param > 0:            # every rank evaluates the same term on the same 200 + 200 rows
             mmd = self.encoder.get_mmd_partitioned(embed, part) / part.world_size
         else:

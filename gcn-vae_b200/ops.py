@@ -592,6 +592,50 @@ class DistMultBceFn(torch.autograd.Function):
         return dzo, dwo, None, None, dshift
 
 
+class PartitionedDistMultBceFn(torch.autograd.Function):
+    """DistMultBceFn for destination-partitioned training: this rank's rows of z go in, its share of the triplets
+    (global entity ids) is scored against the all-gathered z.  Both collectives are taken off the critical path:
+    ``pending_z`` is the asynchronous all-gather the caller started before its local loss terms (KL, regulariser),
+    and the reduce-scatter of dz - which the fused kernel already produced in the FORWARD pass - is started right
+    after the kernel and only waited for when backward needs the rows (the upstream scalar is applied afterwards:
+    the reduction is linear)."""
+
+    @staticmethod
+    def forward(ctx, z_local, w, triplets, labels, shift, part, pending_z):
+        from . import parallel
+        z = pending_z.wait()                                  # [n_global, h]
+        w, labels = _c(w), _c(labels)
+        S, h = triplets.shape[0], z.shape[1]
+        dev = z.device
+        idx = TripletIndex(triplets, z.shape[0], w.shape[0], entity_index=False)
+        g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
+        dw = torch.zeros_like(w)
+        dz = torch.zeros_like(z)
+        out = torch.empty(2, dtype=torch.float32, device=dev)         # loss, sum of g
+        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
+        ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
+        L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
+               None, L.f32(g), L.f32(dw), L.f32(dz), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
+               L.stream())
+        ctx.pending_dz = parallel.reduce_scatter_rows_start(dz, part) if ctx.needs_input_grad[0] else None
+        ctx.save_for_backward(dw, out)
+        ctx.shift_shape = None if shift is None else shift.shape
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, go):
+        dw, out = ctx.saved_tensors
+        dzo = dwo = dshift = None
+        if ctx.pending_dz is not None:
+            dzo = ctx.pending_dz.wait() * go
+            ctx.pending_dz = None
+        if ctx.needs_input_grad[1]:
+            dwo = dw * go
+        if ctx.shift_shape is not None and ctx.needs_input_grad[4]:
+            dshift = (out[1] * go).reshape(ctx.shift_shape)
+        return dzo, dwo, None, None, dshift, None, None
+
+
 class LossHeadFn(torch.autograd.Function):
     """The loss head of LinkPredict.get_loss in one autograd node (kgvae/link_predict.py:74-91):
 

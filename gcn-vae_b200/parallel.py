@@ -119,7 +119,7 @@ class GradBuckets:
         total = sum(p.numel() for g in self.groups for p in g)
         dev = self.groups[0][0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.slices, self._bucket_of, self._pending, self._handles = [], {}, [], []
+        self.slices, self._bucket_of, self._pending, self._handles, self._hooks = [], {}, [], [], []
         off = 0
         for b, g in enumerate(self.groups):
             start = off
@@ -127,10 +127,20 @@ class GradBuckets:
                 n = p.numel()
                 p.grad = self.flat[off:off + n].view_as(p)
                 self._bucket_of[id(p)] = b
-                p.register_post_accumulate_grad_hook(self._hook)
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
                 off += n
             self.slices.append(self.flat[start:off])
         self._reset()
+
+    def close(self):
+        """Detach from the parameters: remove the hooks and give every parameter a gradient tensor of its own."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for g in self.groups:
+            for p in g:
+                if p.grad is not None:
+                    p.grad = p.grad.clone()
 
     def _reset(self):
         self._pending = [len(g) for g in self.groups]
