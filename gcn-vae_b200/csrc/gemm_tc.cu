@@ -15,7 +15,6 @@ using namespace splitpipe;
 
 namespace {
 
-constexpr int kCluster = 4;                                     // CTAs sharing one B tile (multicast form)
 constexpr int EPI_WARPS = 8;                                    // two per 32-row quadrant: columns [0,128) and [128,256)
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_PITCH = 20;                                   // padded row of a 32 x 16 transpose block (16-byte aligned)
@@ -128,171 +127,137 @@ __device__ __forceinline__ float finish(float v, const GemmArgs& g, int n, size_
   return v;
 }
 
-// epilogue of ONE tile (the 8 epilogue warps; `it` = this CTA's tile counter): scales, bias / addend / ReLU / mask /
-// accumulate, straight from tensor memory
-__device__ __forceinline__ void gemm_epilogue_tile(const Pipe& P, const GemmArgs& g, float* sb_s, float* epi_t, int it,
-                                                   int m0, int n0, int split) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // TMEM lanes are reachable by warp id % 4: warps 2..5 take columns [0, 128) of their quadrant, 6..9 [128, 256)
-  const int quad = warp & 3, etid = threadIdx.x - 64, half = (warp - 2) >> 2;
-  const int buf = it & 1;
-  float* sb = sb_s + buf * BN;
-  sb[etid] = __ldg(g.inv_sb + n0 + etid);
-  const int m = m0 + quad * 32 + lane;
-  const float sa = m < g.M ? __ldg(g.inv_sa + m) : 0.f;
-  asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps: column scales staged
-  // while the accumulator is still being produced: pull this warp's lines of addend / mask / C towards L2
-  if (!g.partial && m < g.M && (g.addend || g.mask || g.accumulate)) {
-    const size_t off0 = (size_t)m * g.ldc + n0 + half * (BN / 2);
-#pragma unroll
-    for (int q = 0; q < BN / 2; q += 32) {
-      if (n0 + half * (BN / 2) + q < g.N) {
-        if (g.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.addend + off0 + q));
-        if (g.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.mask + off0 + q));
-        if (g.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.C + off0 + q));
-      }
-    }
-  }
-  const uint32_t taddr = epi_acquire(P, it);
-  float* out = g.partial ? g.partial + ((size_t)split * g.M + m) * g.N : g.C + (size_t)m * g.ldc;
-  const int ld_out = g.partial ? g.N : g.ldc;
-  const bool vec = (ld_out & 3) == 0 && (g.N & 3) == 0 &&
-                   (reinterpret_cast<uintptr_t>(g.partial ? g.partial : g.C) & 15) == 0 &&
-                   (!g.addend || (reinterpret_cast<uintptr_t>(g.addend) & 15) == 0) &&
-                   (!g.mask || (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0) &&
-                   (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
-  float* T = epi_t + (warp - 2) * EPI_T;
-#pragma unroll 1
-  for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr + c * 32, v);
-    tmem_ld_wait();
-    const int nb = n0 + c * 32;
-    if (vec && nb < g.N) {
-      // The accumulator arrives one ROW per lane.  Written out that way a warp store is 32 strided
-      // 16-byte pieces; instead the warp parks 32 x 16 blocks in shared memory and walks them with
-      // 4 lanes per row (4 columns each): C / addend / mask are touched in whole 64-byte runs.
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + 16 * hh + j);
-          *reinterpret_cast<float4*>(T + lane * EPI_PITCH + j) = make_float4(
-              __uint_as_float(v[16 * hh + j]) * sa * s4.x, __uint_as_float(v[16 * hh + j + 1]) * sa * s4.y,
-              __uint_as_float(v[16 * hh + j + 2]) * sa * s4.z, __uint_as_float(v[16 * hh + j + 3]) * sa * s4.w);
-        }
-        __syncwarp();
-        const int n = nb + 16 * hh + 4 * (lane & 3);
-        if (n < g.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.bias && !g.partial) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = 8 * i + (lane >> 2), mm = m0 + quad * 32 + rl;
-            if (mm < g.M) {
-              float4 r = *reinterpret_cast<const float4*>(T + rl * EPI_PITCH + 4 * (lane & 3));
-              if (g.partial) {
-                *reinterpret_cast<float4*>(g.partial + ((size_t)split * g.M + mm) * g.N + n) = r;
-              } else {
-                const size_t off = (size_t)mm * g.ldc + n;
-                r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
-                if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
-                if (g.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r.x *= k.x; r.y *= k.y; r.z *= k.z; r.w *= k.w; }
-                if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-                *reinterpret_cast<float4*>(g.C + off) = r;
-              }
-            }
-          }
-        }
-        __syncwarp();                                   // the block is consumed before the next one is parked
-      }
-    } else if (m < g.M && nb < g.N) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = nb + j;
-        const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
-        float r0 = __uint_as_float(v[j]) * sa * s4.x, r1 = __uint_as_float(v[j + 1]) * sa * s4.y;
-        float r2 = __uint_as_float(v[j + 2]) * sa * s4.z, r3 = __uint_as_float(v[j + 3]) * sa * s4.w;
-        if (g.partial) {
-          if (vec && n + 3 < g.N) {
-            *reinterpret_cast<float4*>(out + n) = make_float4(r0, r1, r2, r3);
-          } else {
-            if (n < g.N) out[n] = r0;
-            if (n + 1 < g.N) out[n + 1] = r1;
-            if (n + 2 < g.N) out[n + 2] = r2;
-            if (n + 3 < g.N) out[n + 3] = r3;
-          }
-        } else {
-          const size_t off = (size_t)m * g.ldc + n;
-          if (vec && n + 3 < g.N) {
-            if (g.bias) { r0 += __ldg(g.bias + n); r1 += __ldg(g.bias + n + 1); r2 += __ldg(g.bias + n + 2); r3 += __ldg(g.bias + n + 3); }
-            if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r0 += a.x; r1 += a.y; r2 += a.z; r3 += a.w; }
-            if (g.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
-            if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r0 *= k.x; r1 *= k.y; r2 *= k.z; r3 *= k.w; }
-            if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r0 += o.x; r1 += o.y; r2 += o.z; r3 += o.w; }
-            *reinterpret_cast<float4*>(g.C + off) = make_float4(r0, r1, r2, r3);
-          } else {
-            if (n < g.N) g.C[off] = finish(r0, g, n, off);
-            if (n + 1 < g.N) g.C[off + 1] = finish(r1, g, n + 1, off + 1);
-            if (n + 2 < g.N) g.C[off + 2] = finish(r2, g, n + 2, off + 2);
-            if (n + 3 < g.N) g.C[off + 3] = finish(r3, g, n + 3, off + 3);
-          }
-        }
-      }
-    }
-  }
-  epi_release(P, it);
-}
-
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b, EPI_WARPS);
   float* sb_s = reinterpret_cast<float*>(P.scratch);      // [2][BN] column scales
   float* epi_t = sb_s + 2 * 2 * BN;                       // [8][32 x 20] epilogue transpose blocks
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = g.tmap.total();
+
   if (warp == 0) {
     pipe_producer_wide(P, &tm_a, &tm_b, g.tmap, g.Kp, g.n_terms);
   } else if (warp == 1) {
     pipe_mma_wide(P, g.tmap, g.n_terms);
   } else {
+    // TMEM lanes are reachable by warp id % 4: warps 2..5 take columns [0, 128) of their quadrant, 6..9 [128, 256)
+    const int quad = warp & 3, etid = threadIdx.x - 64, half = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       int m0, n0, split, ks0, nks;
       g.tmap.decode(tile, m0, n0, split, ks0, nks);
-      gemm_epilogue_tile(P, g, sb_s, epi_t, it, m0, n0, split);
+      const int buf = it & 1;
+      float* sb = sb_s + buf * BN;
+      sb[etid] = __ldg(g.inv_sb + n0 + etid);
+      const int m = m0 + quad * 32 + lane;
+      const float sa = m < g.M ? __ldg(g.inv_sa + m) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps: column scales staged
+      // while the accumulator is still being produced: pull this warp's lines of addend / mask / C towards L2
+      if (!g.partial && m < g.M && (g.addend || g.mask || g.accumulate)) {
+        const size_t off0 = (size_t)m * g.ldc + n0 + half * (BN / 2);
+#pragma unroll
+        for (int q = 0; q < BN / 2; q += 32) {
+          if (n0 + half * (BN / 2) + q < g.N) {
+            if (g.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.addend + off0 + q));
+            if (g.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.mask + off0 + q));
+            if (g.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.C + off0 + q));
+          }
+        }
+      }
+      const uint32_t taddr = epi_acquire(P, it);
+      float* out = g.partial ? g.partial + ((size_t)split * g.M + m) * g.N : g.C + (size_t)m * g.ldc;
+      const int ld_out = g.partial ? g.N : g.ldc;
+      const bool vec = (ld_out & 3) == 0 && (g.N & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(g.partial ? g.partial : g.C) & 15) == 0 &&
+                       (!g.addend || (reinterpret_cast<uintptr_t>(g.addend) & 15) == 0) &&
+                       (!g.mask || (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0) &&
+                       (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+      float* T = epi_t + (warp - 2) * EPI_T;
+#pragma unroll 1
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (vec && nb < g.N) {
+          // The accumulator arrives one ROW per lane.  Written out that way a warp store is 32 strided
+          // 16-byte pieces; instead the warp parks 32 x 16 blocks in shared memory and walks them with
+          // 4 lanes per row (4 columns each): C / addend / mask are touched in whole 64-byte runs.
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + 16 * hh + j);
+              *reinterpret_cast<float4*>(T + lane * EPI_PITCH + j) = make_float4(
+                  __uint_as_float(v[16 * hh + j]) * sa * s4.x, __uint_as_float(v[16 * hh + j + 1]) * sa * s4.y,
+                  __uint_as_float(v[16 * hh + j + 2]) * sa * s4.z, __uint_as_float(v[16 * hh + j + 3]) * sa * s4.w);
+            }
+            __syncwarp();
+            const int n = nb + 16 * hh + 4 * (lane & 3);
+            if (n < g.N) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g.bias && !g.partial) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rl = 8 * i + (lane >> 2), mm = m0 + quad * 32 + rl;
+                if (mm < g.M) {
+                  float4 r = *reinterpret_cast<const float4*>(T + rl * EPI_PITCH + 4 * (lane & 3));
+                  if (g.partial) {
+                    *reinterpret_cast<float4*>(g.partial + ((size_t)split * g.M + mm) * g.N + n) = r;
+                  } else {
+                    const size_t off = (size_t)mm * g.ldc + n;
+                    r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+                    if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
+                    if (g.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                    if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r.x *= k.x; r.y *= k.y; r.z *= k.z; r.w *= k.w; }
+                    if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                    *reinterpret_cast<float4*>(g.C + off) = r;
+                  }
+                }
+              }
+            }
+            __syncwarp();                                   // the block is consumed before the next one is parked
+          }
+        } else if (m < g.M && nb < g.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nb + j;
+            const float4 s4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+            float r0 = __uint_as_float(v[j]) * sa * s4.x, r1 = __uint_as_float(v[j + 1]) * sa * s4.y;
+            float r2 = __uint_as_float(v[j + 2]) * sa * s4.z, r3 = __uint_as_float(v[j + 3]) * sa * s4.w;
+            if (g.partial) {
+              if (vec && n + 3 < g.N) {
+                *reinterpret_cast<float4*>(out + n) = make_float4(r0, r1, r2, r3);
+              } else {
+                if (n < g.N) out[n] = r0;
+                if (n + 1 < g.N) out[n + 1] = r1;
+                if (n + 2 < g.N) out[n + 2] = r2;
+                if (n + 3 < g.N) out[n + 3] = r3;
+              }
+            } else {
+              const size_t off = (size_t)m * g.ldc + n;
+              if (vec && n + 3 < g.N) {
+                if (g.bias) { r0 += __ldg(g.bias + n); r1 += __ldg(g.bias + n + 1); r2 += __ldg(g.bias + n + 2); r3 += __ldg(g.bias + n + 3); }
+                if (g.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(g.addend + off)); r0 += a.x; r1 += a.y; r2 += a.z; r3 += a.w; }
+                if (g.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+                if (g.mask) { const float4 k = __ldg(reinterpret_cast<const float4*>(g.mask + off)); r0 *= k.x; r1 *= k.y; r2 *= k.z; r3 *= k.w; }
+                if (g.accumulate) { const float4 o = *reinterpret_cast<const float4*>(g.C + off); r0 += o.x; r1 += o.y; r2 += o.z; r3 += o.w; }
+                *reinterpret_cast<float4*>(g.C + off) = make_float4(r0, r1, r2, r3);
+              } else {
+                if (n < g.N) g.C[off] = finish(r0, g, n, off);
+                if (n + 1 < g.N) g.C[off + 1] = finish(r1, g, n + 1, off + 1);
+                if (n + 2 < g.N) g.C[off + 2] = finish(r2, g, n + 2, off + 2);
+                if (n + 3 < g.N) g.C[off + 3] = finish(r3, g, n + 3, off + 3);
+              }
+            }
+          }
+        }
+      }
+      epi_release(P, it);
     }
   }
   pipe_teardown(P);
-}
-
-// Cluster-multicast form (split_pipe.cuh): C CTAs of a cluster take C consecutive row tiles of one column tile and
-// share the loads of the B operand.  No split-K.  tm_b: box rows = BN / C.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmArgs g,
-                  ClusterTileMap cmap) {
-  extern __shared__ uint8_t smem_raw[];
-  const Pipe P = pipe_setup(smem_raw, &tm_a, &tm_b, EPI_WARPS, cmap.C);
-  float* sb_s = reinterpret_cast<float*>(P.scratch);
-  float* epi_t = sb_s + 2 * 2 * BN;
-  const int warp = threadIdx.x >> 5;
-  const int rank = (int)cluster_ctarank(), cluster_id = blockIdx.x / cmap.C, n_clusters = gridDim.x / cmap.C;
-  const int total = cmap.total();
-  if (warp == 0) {
-    pipe_producer_wide_mc(P, &tm_a, &tm_b, cmap, g.Kp, g.n_terms, cluster_id, n_clusters, rank);
-  } else if (warp == 1) {
-    pipe_mma_wide_mc(P, cmap, g.n_terms, cluster_id, n_clusters);
-  } else {
-    int it = 0;
-    for (int st = cluster_id; st < total; st += n_clusters, ++it) {
-      int m0, n0;
-      cmap.decode(st, rank, m0, n0);
-      gemm_epilogue_tile(P, g, sb_s, epi_t, it, m0, n0, 0);
-    }
-  }
-  pipe_teardown(P, cmap.C);
 }
 
 // split-K: C = epilogue(sum_s partial[s]) in a fixed order
@@ -393,6 +358,11 @@ int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb
   const uint64_t row_bytes = (uint64_t)2 * L.Kp * sizeof(__half);
   rc = make_tensor_map_2d_b16(&tm_a, acat, M, 2 * L.Kp, row_bytes, BM);
   if (rc != KG_OK) return rc;
+  rc = make_tensor_map_2d_b16(&tm_b, bcat, N, 2 * L.Kp, row_bytes, BN);
+  if (rc != KG_OK) return rc;
+
+  if (kg_attr_needed(0))
+    KG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   GemmArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.inv_sa = inv_sa; g.inv_sb = inv_sb;
   g.bias = bias; g.addend = addend; g.mask = mask; g.relu = relu; g.accumulate = accumulate;
@@ -400,43 +370,6 @@ int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb
   g.tmap = TileMap{L.m_tiles, L.n_tiles, L.splits, L.Kp / BK, L.k_per_split};
   g.Kp = L.Kp;
   g.n_terms = tc05::tc_terms();
-
-  // Many row tiles, no split-K: clusters of kCluster CTAs share the loads of the B operand (TMA multicast)
-  if (L.splits == 1 && L.m_tiles >= 2 * kCluster) {
-    rc = make_tensor_map_2d_b16(&tm_b, bcat, N, 2 * L.Kp, row_bytes, BN / kCluster);
-    if (rc != KG_OK) return rc;
-    if (kg_attr_needed(5)) {
-      KG_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      KG_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
-    const ClusterTileMap cmap{L.m_tiles, L.n_tiles, L.Kp / BK, kCluster};
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cfg.gridDim = dim3(kCluster);
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_mc_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
-      (void)cudaGetLastError();
-      max_clusters = kg_sm_count() / kCluster;
-    }
-    const int n_clusters = cmap.total() < max_clusters ? cmap.total() : max_clusters;
-    cfg.gridDim = dim3(n_clusters * kCluster);
-    KG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_mc_kernel, tm_a, tm_b, g, cmap));
-    return KG_OK;
-  }
-
-  rc = make_tensor_map_2d_b16(&tm_b, bcat, N, 2 * L.Kp, row_bytes, BN);
-  if (rc != KG_OK) return rc;
-  if (kg_attr_needed(0))
-    KG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int total = g.tmap.total();
   const int grid = total < kg_sm_count() ? total : kg_sm_count();
   gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(tm_a, tm_b, g);

@@ -52,7 +52,7 @@ struct Pipe {
 
 // all 192 threads; returns after TMEM is allocated and barriers are initialised
 __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
-                                           int epi_warps = 4, int cluster = 1) {
+                                           int epi_warps = 4) {
   Pipe P;
   P.smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(P.smem + STAGES * STAGE_BYTES);
@@ -70,7 +70,7 @@ __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap*
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(P.full + s, 1);
-      mbar_init(P.empty + s, cluster);        // multicast pipeline: one release per CTA of the cluster
+      mbar_init(P.empty + s, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(P.tfull + i, 1);
@@ -81,7 +81,6 @@ __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem_raw, const CUtensorMap*
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   fence_before_thread_sync();
   __syncthreads();
-  if (cluster > 1) cluster_sync_all();        // no CTA multicasts into a peer whose barriers are not initialised yet
   fence_after_thread_sync();
   P.tmem_base = *tmem_slot;
   return P;
@@ -220,93 +219,6 @@ __device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Cluster-multicast variant of the wide pair.  A cluster of C CTAs works on C consecutive row tiles of the SAME
-// column tile at the same time: every CTA loads its own A tile, but only 1/C of the B tile (BN / C rows), which
-// TMA delivers to all C CTAs.  At K = 500 the B (weight) operand was two thirds of the L2 -> SM traffic that
-// bounds the kernel (every 128-row tile streamed all of it); with C = 4 that part drops to a quarter.
-// Protocol: full[s] of a CTA collects its own A bytes and the C slices of B; a stage may be overwritten - by ANY
-// CTA's multicast - only after every CTA's MMAs have read it, so each MMA warp releases the stage with a commit
-// that arrives on empty[s] of all C CTAs (count C).  All CTAs of a cluster walk the same tile list in lockstep.
-// ------------------------------------------------------------------------------------------
-struct ClusterTileMap {
-  int m_tiles, n_tiles, k_steps, C;          // super-tile = C consecutive row tiles x one column tile
-  __host__ __device__ int super_rows() const { return (m_tiles + C - 1) / C; }
-  __host__ __device__ int total() const { return super_rows() * n_tiles; }
-  __device__ __forceinline__ void decode(int st, int rank, int& m0, int& n0) const {
-    n0 = (st % n_tiles) * BN;
-    m0 = ((st / n_tiles) * C + rank) * BM;   // may lie beyond M (ghost tile): loads zero-fill, stores are masked
-  }
-};
-
-// warp 0.  tm_b_slice: tensor map of B with box rows = BN / C
-__device__ __forceinline__ void pipe_producer_wide_mc(const Pipe& P, const CUtensorMap* tm_a, const CUtensorMap* tm_b_slice,
-                                                      const ClusterTileMap& tmap, int Kp, int n_terms, int cluster_id,
-                                                      int n_clusters, int rank) {
-  if (!elect_one()) return;
-  int stage = 0;
-  uint32_t phase = 0;
-  const int total = tmap.total(), slice_rows = BN / tmap.C, slice_bytes = slice_rows * BK * 2;
-  const uint16_t mask = (uint16_t)((1u << tmap.C) - 1);
-  for (int st_i = cluster_id; st_i < total; st_i += n_clusters) {
-    int m0, n0;
-    tmap.decode(st_i, rank, m0, n0);
-    for (int ks = 0; ks < tmap.k_steps; ++ks) {
-      mbar_wait(P.empty + stage, phase ^ 1);
-      uint8_t* st = P.smem + stage * WIDE_STAGE_BYTES;
-      mbar_arrive_expect_tx(P.full + stage, n_terms == 3 ? WIDE_STAGE_BYTES : STAGE_BYTES);
-      tma_load_2d(st, tm_a, P.full + stage, ks * BK, m0);                                              // A_hi (own)
-      tma_load_2d_mc(st + 2 * A_BYTES + rank * slice_bytes, tm_b_slice, P.full + stage, ks * BK,
-                     n0 + rank * slice_rows, mask);                                                    // my slice of B_hi -> all
-      if (n_terms == 3) {
-        tma_load_2d(st + A_BYTES, tm_a, P.full + stage, Kp + ks * BK, m0);                             // A_lo (own)
-        tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + rank * slice_bytes, tm_b_slice, P.full + stage, Kp + ks * BK,
-                       n0 + rank * slice_rows, mask);                                                  // my slice of B_lo -> all
-      }
-      if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
-    }
-  }
-}
-
-// warp 1
-__device__ __forceinline__ void pipe_mma_wide_mc(const Pipe& P, const ClusterTileMap& tmap, int n_terms, int cluster_id,
-                                                 int n_clusters) {
-  if (!elect_one()) return;
-  constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
-  int stage = 0;
-  uint32_t phase = 0;
-  int it = 0;
-  const int total = tmap.total();
-  const uint16_t mask = (uint16_t)((1u << tmap.C) - 1);
-  for (int st_i = cluster_id; st_i < total; st_i += n_clusters, ++it) {
-    const int buf = it & 1;
-    mbar_wait(P.tempty + buf, ((it >> 1) & 1) ^ 1);
-    fence_after_thread_sync();
-    const uint32_t tacc = P.tmem_base + buf * BN;
-    for (int ks = 0; ks < tmap.k_steps; ++ks) {
-      mbar_wait(P.full + stage, phase);
-      fence_after_thread_sync();
-      const uint32_t sa = smem_u32(P.smem + stage * WIDE_STAGE_BYTES);
-      const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + A_BYTES);
-      const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * A_BYTES), b_lo = smem_desc_k_sw128(sa + 2 * A_BYTES + B_BYTES);
-      if (n_terms == 3) {
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
-      } else {
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);
-      }
-      mma_commit_mc(P.empty + stage, mask);   // the stage is free once EVERY CTA of the cluster has read it
-      if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
-    }
-    mma_commit(P.tfull + buf);                // accumulator complete (local)
-  }
-}
-
 // epilogue warps: wait for the accumulator of iteration `it`; returns this warp's TMEM address
 __device__ __forceinline__ uint32_t epi_acquire(const Pipe& P, int it) {
   const int buf = it & 1, quad = (threadIdx.x >> 5) & 3;
@@ -324,11 +236,10 @@ __device__ __forceinline__ void epi_release(const Pipe& P, int it) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// all threads, at the end (cluster > 1: peers may still signal this CTA's barriers until they are done too)
-__device__ __forceinline__ void pipe_teardown(const Pipe& P, int cluster = 1) {
+// all threads, at the end
+__device__ __forceinline__ void pipe_teardown(const Pipe& P) {
   fence_before_thread_sync();
   __syncthreads();
-  if (cluster > 1) cluster_sync_all();
   if ((threadIdx.x >> 5) == 2) {
     fence_after_thread_sync();
     tmem_dealloc<512>(P.tmem_base);
