@@ -526,7 +526,9 @@ def partitioned_leg(args, dev, world, rank, log, allgather, steps, warmup, scale
            "mode": ("single GPU, unpartitioned" if world == 1 else
                     "NCCL all-gather of layer inputs (async, overlapped with the self-loop GEMM)" if allgather else
                     "layer inputs gathered from peer HBM by the message-passing kernels (NVLink, CUDA IPC)"),
-           "top_ops_ms": dict(sorted(op_ms.items(), key=lambda kv: -kv[1])[:8])}
+           "top_ops_ms": dict(sorted(op_ms.items(), key=lambda kv: -kv[1])[:8]),
+           "all_ops_ms": {k_: round(v, 3) for k_, v in sorted(op_ms.items(), key=lambda kv: -kv[1])},
+           "ops_total_ms": sum(op_ms.values())}
     del model, opt, buckets, g, trip, labels, src, dst, et, norm, norm2, ids
     torch.cuda.empty_cache()
     return res
