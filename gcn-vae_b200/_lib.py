@@ -31,6 +31,8 @@ _SIGNATURES = {
     "kg_bdd_weight_layouts": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "kg_bdd_rel_fwd": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
     "kg_bdd_rel_bwd": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "kg_bdd_rel_fwd_cols": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "kg_bdd_rel_bwd_cols": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "kg_bdd_layouts_needed": (_I, [_I, _I, _I]),
     "kg_graph_rel_tiled_workspace_bytes": (_Z, [_I]),
     "kg_graph_rel_tiled": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

@@ -533,3 +533,54 @@ extern "C" int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows
   KG_LAUNCH_OK();
   return KG_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Column chunks of a layer (destination-partitioned training pipelines message passing against
+// column chunks of the layer-input all-gather and of the source-gradient reduce-scatter).
+// The weight of a relation is block-diagonal, so blocks [block0, block0 + num_bases) of
+// num_bases_total only touch columns [block0 * si, ...) of x and [block0 * so, ...) of agg:
+//   x_chunk   [n_src, num_bases * si]   compact matrix holding just those columns (all nodes)
+//   weight    the FULL weight [R, num_bases_total * si * so];  agg / dagg the FULL matrices
+//   dx_chunk  [n_src, num_bases * si]   compact, zero-filled;  dweight the FULL gradient (zero-filled once)
+// 5x5 / 5x10 blocks only (the warp-autonomous kernels).  A chunk is run with TWO blocks per lane and ONE warp per
+// edge (the full layer uses 4 blocks per lane for 5x5 and two warps per edge for 5x10): num_bases even, <= 64, so
+// that a chunk of about half the layer still fills 25 of a warp's 32 lanes.
+// ------------------------------------------------------------------------------------------
+extern "C" int kg_bdd_rel_fwd_cols(const float* x_chunk, const void* rel_pack, int n_edges, const float* weight,
+                                   int block0, int num_bases, int num_bases_total, int si, int so, float* agg,
+                                   int hints, void* stream) {
+  KG_REQUIRE(n_edges >= 0 && num_bases > 0 && block0 >= 0 && block0 + num_bases <= num_bases_total, "bdd fwd cols: bad block range");
+  KG_REQUIRE(si == 5 && (so == 5 || so == 10) && num_bases % 2 == 0 && num_bases <= 64 && aligned16(x_chunk) &&
+             aligned16(weight) && aligned16(agg) && (block0 * si * so) % 4 == 0 && (block0 * so) % 4 == 0 &&
+             (num_bases * si) % 4 == 0,
+             "bdd fwd cols: needs 5x5 / 5x10 blocks, an even chunk of <= 64 blocks and 16-byte aligned chunk offsets");
+  if (n_edges == 0) return KG_OK;
+  cudaStream_t st = kg_stream(stream);
+  const bddown::RowSource src{x_chunk, nullptr, 0};
+  const float* w = weight + (size_t)block0 * si * so;
+  float* out = agg + (size_t)block0 * so;
+  const int ldw = num_bases_total * si * so, ldo = num_bases_total * so;
+  if (so == 5) return bddwarp::launch_fwd<5, 5, 2, 1, 4>(src, rel_pack, n_edges, w, num_bases, hints, out, st, ldw, ldo);
+  return bddwarp::launch_fwd<5, 10, 2, 1, 4>(src, rel_pack, n_edges, w, num_bases, hints, out, st, ldw, ldo);
+}
+
+extern "C" int kg_bdd_rel_bwd_cols(const float* x_chunk, const float* dagg, const void* rel_pack, int n_edges,
+                                   const float* weight, int block0, int num_bases, int num_bases_total, int si,
+                                   int so, float* dx_chunk, float* dweight, int hints, void* stream) {
+  KG_REQUIRE(n_edges >= 0 && num_bases > 0 && block0 >= 0 && block0 + num_bases <= num_bases_total, "bdd bwd cols: bad block range");
+  KG_REQUIRE(si == 5 && (so == 5 || so == 10) && num_bases % 2 == 0 && num_bases <= 64 && aligned16(x_chunk) &&
+             aligned16(dagg) && aligned16(weight) && aligned16(dx_chunk) && aligned16(dweight) &&
+             (block0 * si * so) % 4 == 0 && (block0 * so) % 4 == 0 && (num_bases * si) % 4 == 0,
+             "bdd bwd cols: needs 5x5 / 5x10 blocks, an even chunk of <= 64 blocks and 16-byte aligned chunk offsets");
+  if (n_edges == 0) return KG_OK;
+  cudaStream_t st = kg_stream(stream);
+  const bddown::RowSource src{x_chunk, nullptr, 0};
+  const float* w = weight + (size_t)block0 * si * so;
+  float* dw = dweight + (size_t)block0 * si * so;
+  const float* dg = dagg + (size_t)block0 * so;
+  const int ldw = num_bases_total * si * so, ldd = num_bases_total * so;
+  if (so == 5)
+    return bddwarp::launch_bwd<5, 5, 2, 1, 4>(src, dg, rel_pack, n_edges, w, num_bases, hints, dx_chunk, dw, st, ldw, ldd);
+  return bddwarp::launch_bwd<5, 10, 2, 1, 4>(src, dg, rel_pack, n_edges, w, num_bases, hints, dx_chunk, dw, st, ldw, ldd);
+}

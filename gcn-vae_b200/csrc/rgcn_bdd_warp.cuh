@@ -72,12 +72,15 @@ struct FwdLayout {
 // shallower gather ring to stay at three CTAs per SM) double the bytes in flight.
 template <int FI, int FO, int TB, int WPS, int DEPTH, int NT, int MINB>
 __global__ void __launch_bounds__(kCta, MINB)
-fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __restrict__ weight, int B, int hints,
-           float* __restrict__ out) {
+fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __restrict__ weight, int B, int ldw,
+           int ldo, int hints, float* __restrict__ out) {
+  // B = blocks handled by this launch; ldw / ldo = row strides (floats) of weight / out.  A launch over a COLUMN
+  // CHUNK of the layer (blocks [b0, b0 + B) of B_total) gets weight + b0 * FI * FO, out + b0 * FO, the chunk's own
+  // compact x matrix, ldw = B_total * FI * FO and ldo = B_total * FO: block-diagonal weights make chunks independent.
   constexpr int XN = TB * FI, CN = TB * FO, WN = TB * FI * FO, SLOTS = kWarps / WPS;
   extern __shared__ __align__(16) float sm[];
   const FwdLayout<FI, FO, TB, WPS> L(B);
-  const int width = B * FO, in_w = B * FI, per = B / TB;
+  const int width = ldo, in_w = B * FI, per = B / TB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / WPS, wsl = warp % WPS;
   int4* P_s = reinterpret_cast<int4*>(sm);                     // [kChunk] {src, dst, etype, norm}
@@ -120,7 +123,7 @@ fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __
     const int4 p = rec[k];
     if (p.z != cur) {                                          // relation run starts (warp-uniform)
       cur = p.z;
-      const float4* wr = reinterpret_cast<const float4*>(row_at(w_g, cur, B * FI * FO));
+      const float4* wr = reinterpret_cast<const float4*>(row_at(w_g, cur, ldw));
 #pragma unroll
       for (int i = 0; i < WN / 4; ++i) {
         const float4 t = __ldg(wr + i);
@@ -183,11 +186,12 @@ struct BwdLayout {
 template <int SI, int SO, int TB, int WPR, int DEPTH, int NT>
 __global__ void __launch_bounds__(kCta)
 bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
-           const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
+           const float* __restrict__ weight, int B, int ldw, int ldd, int hints, float* __restrict__ dx,
+           float* __restrict__ dW) {
   constexpr int XN = TB * SI, DN = TB * SO, WN = TB * SI * SO, WPS = 2 * WPR, SLOTS = kWarps / WPS;
   extern __shared__ __align__(16) float sm[];
   const BwdLayout<SI, SO, TB, WPR> L(B);
-  const int in_w = B * SI, out_w = B * SO, per = B / TB;
+  const int in_w = B * SI, out_w = ldd, per = B / TB;          // out_w: row stride of dagg (see fwd_kernel on column chunks)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / WPS, wsl = warp % WPS;
   const bool xrole = wsl < WPR;               // warp-uniform: input-gradient warps come first
@@ -230,7 +234,7 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
   const bool owner = lane < cnt;
   const float* dg = ring + ds.skip + gl * DN;
   const float* xg = ring + L.xoff_w + xsp.skip + gl * XN;
-  const size_t KW = (size_t)B * SI * SO;
+  const size_t KW = (size_t)ldw;
   const float* w_g = weight + (size_t)(g_lo + gl) * WN;
   float* dW_g = dW + (size_t)(g_lo + gl) * WN;
   float* dx_w = dx + g_lo * XN;
@@ -347,11 +351,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int SI, int SO, int TB, int WPR, int DEPTH>
 __global__ void __launch_bounds__(kCta)
 bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__ pack, int E,
-           const float* __restrict__ weight, int B, int hints, float* __restrict__ dx, float* __restrict__ dW) {
+           const float* __restrict__ weight, int B, int ldw, int ldd, int hints, float* __restrict__ dx,
+           float* __restrict__ dW) {
   constexpr int XN = TB * SI, DN = TB * SO, WN = TB * SI * SO, WPS = 2 * WPR, SLOTS = kWarps / WPS, PAIRS = kWarps / 2;
   extern __shared__ __align__(16) float sm[];
   const PairedLayout<SI, SO, TB, WPR> L(B);
-  const int in_w = B * SI, out_w = B * SO, per = B / TB;
+  const int in_w = B * SI, out_w = ldd, per = B / TB;          // out_w: row stride of dagg (see fwd_kernel on column chunks)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / WPS, wsl = warp % WPS;
   const bool xrole = wsl < WPR;               // warp-uniform: input-gradient warps come first
@@ -406,7 +411,7 @@ bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __res
   const bool owner = lane < cnt;
   const float* dg = ring + ds.skip + gl * DN;
   const float* xg = ring + L.xoff + xsp.skip + gl * XN;
-  const size_t KW = (size_t)B * SI * SO;
+  const size_t KW = (size_t)ldw;
   const float* w_g = weight + (size_t)(g_lo + gl) * WN;
   float* dW_g = dW + (size_t)(g_lo + gl) * WN;
   float* dx_w = dx + g_lo * XN;
@@ -497,35 +502,41 @@ bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __res
 // ------------------------------------------------------------------------------------------
 template <int FI, int FO, int TB, int WPS, int DEPTH, int NT = 2, int MINB = 1>
 int launch_fwd(RowSource feat, const void* pack, int E, const float* weight, int B, int hints, float* out,
-               cudaStream_t st) {
+               cudaStream_t st, int ldw = 0, int ldo = 0) {
+  if (ldw == 0) ldw = B * FI * FO;
+  if (ldo == 0) ldo = B * FO;
   const size_t smem = FwdLayout<FI, FO, TB, WPS>(B).smem(DEPTH, NT);
   auto kern = fwd_kernel<FI, FO, TB, WPS, DEPTH, NT, MINB>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(feat, reinterpret_cast<const int4*>(pack), E, weight, B, hints, out);
+  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(feat, reinterpret_cast<const int4*>(pack), E, weight, B, ldw, ldo, hints, out);
   KG_LAUNCH_OK();
   return KG_OK;
 }
 
 template <int SI, int SO, int TB, int WPR, int DEPTH, int NT = 2>
 int launch_bwd(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
-               float* dx, float* dW, cudaStream_t st) {
+               float* dx, float* dW, cudaStream_t st, int ldw = 0, int ldd = 0) {
+  if (ldw == 0) ldw = B * SI * SO;
+  if (ldd == 0) ldd = B * SO;
   const size_t smem = BwdLayout<SI, SO, TB, WPR>(B).smem(DEPTH, NT);
   auto kern = bwd_kernel<SI, SO, TB, WPR, DEPTH, NT>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
-                                                 dx, dW);
+  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, ldw, ldd,
+                                                 hints, dx, dW);
   KG_LAUNCH_OK();
   return KG_OK;
 }
 
 template <int SI, int SO, int TB, int WPR, int DEPTH>
 int launch_bwd_paired(RowSource x, const float* dagg, const void* pack, int E, const float* weight, int B, int hints,
-                      float* dx, float* dW, cudaStream_t st) {
+                      float* dx, float* dW, cudaStream_t st, int ldw = 0, int ldd = 0) {
+  if (ldw == 0) ldw = B * SI * SO;
+  if (ldd == 0) ldd = B * SO;
   const size_t smem = PairedLayout<SI, SO, TB, WPR>(B).smem(DEPTH);
   auto kern = bwd_paired_kernel<SI, SO, TB, WPR, DEPTH>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, hints,
-                                                 dx, dW);
+  kern<<<kg_div_up(E, kChunk), kCta, smem, st>>>(x, dagg, reinterpret_cast<const int4*>(pack), E, weight, B, ldw, ldd,
+                                                 hints, dx, dW);
   KG_LAUNCH_OK();
   return KG_OK;
 }

@@ -238,6 +238,20 @@ class EmbeddingFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # a3  RelGraphConv("bdd") layer
 # ---------------------------------------------------------------------------------------------
+def _block_chunks(num_bases, si, so, n_chunks):
+    """Split the diagonal blocks of a bdd layer into ``n_chunks`` contiguous ranges the column-chunk kernels accept
+    (5x5 / 5x10 blocks, an even number of blocks per chunk, at most 64, chunk offsets 16-byte aligned); [] when the
+    shape has no chunked kernels."""
+    if n_chunks <= 1 or L.lib().kg_bdd_layouts_needed(num_bases, si, so) or num_bases % 4:
+        return []
+    units = num_bases // 4                  # cut at multiples of 4 blocks: 20 / 40 floats of x / agg -> 16-byte aligned
+    if units < n_chunks:
+        return []
+    cuts = [0] + [4 * ((units * (c + 1)) // n_chunks) for c in range(n_chunks)]
+    out = [(cuts[c], cuts[c + 1]) for c in range(n_chunks) if cuts[c + 1] > cuts[c]]
+    return out if all(b1 - b0 <= 64 for b0, b1 in out) else []
+
+
 class BddConvFn(torch.autograd.Function):
     """One RelGraphConv(bdd) layer: out = dropout(act(sum_e norm_e W_{r_e} x_src + h_bias +
     x @ loop_weight)) - DGL RelGraphConv.forward as constructed at kgvae/model.py:54-59.
@@ -275,7 +289,11 @@ class BddConvFn(torch.autograd.Function):
             n_src_rows = peer.blk * peer.world_size
         elif gather:
             from . import parallel
-            pending = parallel.allgather_rows_start(x, part)          # NCCL, asynchronous
+            chunks = _block_chunks(num_bases, si, so, getattr(part, "col_chunks", 1))
+            if chunks:          # one asynchronous all-gather per COLUMN chunk, queued in order on NCCL's stream
+                pending = [parallel.allgather_rows_start(x[:, b0 * si:b1 * si].contiguous(), part) for b0, b1 in chunks]
+            else:
+                pending = parallel.allgather_rows_start(x, part)      # NCCL, asynchronous
             n_src_rows = part.n_global
         else:
             if n_own != gi.n_nodes:
@@ -295,17 +313,31 @@ class BddConvFn(torch.autograd.Function):
             gemm(x, loop_weight, out, bias=bias)
         else:
             epilogue_only(out, bias=bias) if bias is not None else out.zero_()
-        x_src = x
-        if pending is not None:
-            x_src = pending.wait()                    # [n_global, in] on this stream from here on
-        src_args = (None, L.ptr(peer.ptrs), peer.blk) if peer is not None else (L.f32(x_src), None, 0)
         pack = _rel_order(gi, 0, n_own, 4 * out_feat)
-        hints = (HINT_STREAM_X if n_src_rows * in_feat * 4 > L2_STREAM_BYTES else 0) | \
-                (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
-        L.call("kg_bdd_rel_fwd", *src_args, L.i32(pack), gi.n_edges, L.f32(weight),
-               L.f32(w_fwd), num_bases, si, so, L.f32(out), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
+        x_chunks = []
+        if isinstance(pending, list):
+            # chunk c runs as soon as ITS columns of every node's row have arrived; the later chunks' gathers
+            # proceed meanwhile (block-diagonal weights: a chunk of blocks reads only its own columns)
+            for (b0, b1), pend in zip(chunks, pending):
+                xc = pend.wait()
+                x_chunks.append(xc)
+                hints = (HINT_STREAM_X if xc.numel() * 4 > L2_STREAM_BYTES else 0) | \
+                        (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
+                L.call("kg_bdd_rel_fwd_cols", L.f32(xc), L.i32(pack), gi.n_edges, L.f32(weight), b0, b1 - b0, num_bases,
+                       si, so, L.f32(out), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
+            x_src = x
+        else:
+            x_src = x
+            if pending is not None:
+                x_src = pending.wait()                # [n_global, in] on this stream from here on
+            src_args = (None, L.ptr(peer.ptrs), peer.blk) if peer is not None else (L.f32(x_src), None, 0)
+            hints = (HINT_STREAM_X if n_src_rows * in_feat * 4 > L2_STREAM_BYTES else 0) | \
+                    (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
+            L.call("kg_bdd_rel_fwd", *src_args, L.i32(pack), gi.n_edges, L.f32(weight),
+                   L.f32(w_fwd), num_bases, si, so, L.f32(out), hints, L.stream(), tag=f"kg_bdd_rel_fwd[{si}x{so}]")
         if act == 1 or mask is not None:              # activation + dropout mask, in place
             epilogue_only(out, addend=out, relu=(act == 1), mask=mask)
+        ctx.x_chunks, ctx.chunks = x_chunks, (chunks if x_chunks else [])
         ctx.save_for_backward(x_src, weight, loop_weight, out, mask, w_bwd)
         ctx.gi, ctx.num_bases, ctx.act, ctx.si, ctx.so = gi, num_bases, act, si, so
         ctx.has_bias = h_bias is not None
@@ -317,12 +349,36 @@ class BddConvFn(torch.autograd.Function):
         x, weight, loop_weight, out, mask, w_bwd = ctx.saved_tensors
         gi, B, si, so, peer, part = ctx.gi, ctx.num_bases, ctx.si, ctx.so, ctx.peer, ctx.part
         g = _c(g)
-        lo = part.lo if ctx.gather else 0
-        x_own = x[lo:lo + ctx.n_own] if ctx.gather else x
+        chunked = bool(ctx.x_chunks)
+        lo = part.lo if (ctx.gather and not chunked) else 0
+        x_own = x[lo:lo + ctx.n_own] if (ctx.gather and not chunked) else x      # chunked: x is the local matrix
         gpre, dbias_fused = act_dropout_bwd(g, out, mask, ctx.act, want_colsum=ctx.has_bias)
         dx = dw = dloop = dbias = None
         pending = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        if chunked and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            from . import parallel
+            want_dx = ctx.needs_input_grad[0]
+            dw = torch.zeros_like(weight)
+            own_dx = None
+            if want_dx and loop_weight is not None:     # self-loop part of the input gradient (local rows only)
+                own_dx = torch.empty((ctx.n_own, x.shape[1]), dtype=torch.float32, device=x.device)
+                gemm(gpre, loop_weight, own_dx, trans_b=True)
+            pending = []
+            for (b0, b1), xc in zip(ctx.chunks, ctx.x_chunks):
+                dxc = torch.zeros_like(xc) if want_dx else None
+                pack = _rel_order(gi, 1, xc.shape[0], (8 if want_dx else 4) * xc.shape[1])
+                hints = (HINT_STREAM_D if gpre.numel() * 4 > L2_STREAM_BYTES else 0) | \
+                        (HINT_TILE_RESIDENT if pack is not gi.rel_pack else 0)
+                L.call("kg_bdd_rel_bwd_cols", L.f32(xc), L.f32(gpre), L.i32(pack), gi.n_edges, L.f32(weight), b0, b1 - b0,
+                       B, si, so, L.f32(dxc), L.f32(dw), hints, L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
+                if want_dx:
+                    if own_dx is not None:
+                        dxc[part.lo:part.lo + ctx.n_own] += own_dx[:, b0 * si:b1 * si]
+                    # this chunk's source gradients travel while the next chunk computes
+                    pending.append(parallel.reduce_scatter_rows_start(dxc, part))
+            if not ctx.needs_input_grad[1]:
+                dw = None
+        elif ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if peer is not None:       # source rows are still in the peers' blocks (published in forward)
                 n_src_rows = peer.blk * peer.world_size
                 src_args = (None, L.ptr(peer.ptrs), peer.blk)
@@ -352,7 +408,9 @@ class BddConvFn(torch.autograd.Function):
             gemm(x_own, gpre, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = dbias_fused
-        if pending is not None:
+        if isinstance(pending, list):
+            dx = torch.cat([p_.wait() for p_ in pending], dim=1) if pending else None
+        elif pending is not None:
             dx = pending.wait()
         return dx, dw, dloop, dbias, None, None, None, None, None, None, None
 

@@ -250,8 +250,11 @@ class Partition:
     destinations are local: dst - lo).  Attach to the graph object as ``g.partition``; RelGraphConv,
     KGVAE and LinkPredict then insert the all-gathers / reductions below."""
 
-    def __init__(self, lo, hi, n_global, group=None, peer_gather=None):
+    def __init__(self, lo, hi, n_global, group=None, peer_gather=None, col_chunks=2):
         self.lo, self.hi, self.n_global, self.group = int(lo), int(hi), int(n_global), group
+        # all-gather mode: layer inputs travel (and source gradients return) in this many COLUMN chunks, each
+        # pipelined against the message passing of the previous / next chunk (ops.BddConvFn); 1 = one collective
+        self.col_chunks = int(col_chunks)
         self.n_local = self.hi - self.lo
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)

@@ -119,6 +119,18 @@ int kg_bdd_rel_fwd(const float* x, const void* x_parts, int part_rows, const voi
 int kg_bdd_rel_bwd(const float* x, const void* x_parts, int part_rows, const float* dagg,
                    const void* rel_pack, int n_edges, const float* weight, const float* w_bwd,
                    int num_bases, int si, int so, float* dx, float* dweight, int hints, void* stream);
+
+/* Column chunks of the same layer (new; destination-partitioned training): blocks [block0, block0 + num_bases) of
+ * num_bases_total only touch columns [block0 si, ...) of x and [block0 so, ...) of agg, so a chunk can run as
+ * soon as ITS columns of the all-gathered layer input have arrived, and its source gradients can be
+ * reduce-scattered while the next chunk computes.  x_chunk / dx_chunk: compact [n_src, num_bases si] matrices;
+ * weight / dweight / agg / dagg: the full tensors.  5x5 and 5x10 blocks. */
+int kg_bdd_rel_fwd_cols(const float* x_chunk, const void* rel_pack, int n_edges, const float* weight,
+                        int block0, int num_bases, int num_bases_total, int si, int so, float* agg,
+                        int hints, void* stream);
+int kg_bdd_rel_bwd_cols(const float* x_chunk, const float* dagg, const void* rel_pack, int n_edges,
+                        const float* weight, int block0, int num_bases, int num_bases_total, int si, int so,
+                        float* dx_chunk, float* dweight, int hints, void* stream);
 /* The reference model's block shapes (5x5, 5x10; rgcn_bdd_own.cuh) read `weight` in the DGL layout
  * directly - a thread owns whole diagonal blocks in registers - and need no derived layout: pass
  * w_fwd / w_bwd = NULL when this returns 0.  Other shapes need kg_bdd_weight_layouts first. */

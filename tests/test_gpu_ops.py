@@ -785,3 +785,37 @@ def test_single_product_mode_is_reported_separately():
     # ~0.01: neighbours swap, nothing more (that is the tolerance this mode is reported with)
     diff = (exact.long() - approx.long()).abs()
     assert float(diff.float().mean()) < 2.0 and int(diff.max()) <= 8
+
+
+# ------------------------------------------------------------------------------ bdd layer by column chunks
+@pytest.mark.parametrize("n,e,r,B,so", [(300, 6000, 30, 100, 5), (300, 6000, 30, 100, 10), (64, 700, 5, 8, 5), (64, 700, 5, 8, 10)])
+def test_bdd_column_chunks_match_the_full_layer(n, e, r, B, so):
+    """kg_bdd_rel_fwd_cols / kg_bdd_rel_bwd_cols (column chunks for the pipelined all-gather / reduce-scatter of
+    destination-partitioned training): running the layer chunk by chunk on compact column slices of x gives the
+    same messages, source gradients and weight gradients as the one-launch form."""
+    si = 5
+    src, dst, et, norm = _rand_graph(11, n, e, r)
+    gen = torch.Generator(device=DEV).manual_seed(B + so)
+    x = torch.randn(n, B * si, device=DEV, generator=gen)
+    weight = torch.randn(r, B * si * so, device=DEV, generator=gen) * 0.3
+    dagg = torch.randn(n, B * so, device=DEV, generator=gen)
+    gi = _index(src, dst, et, norm, n, r)
+    agg = torch.zeros(n, B * so, device=DEV)
+    L.call("kg_bdd_rel_fwd", L.f32(x), None, 0, L.i32(gi.rel_pack), e, L.f32(weight), None, B, si, so, L.f32(agg), 0, L.stream())
+    dx, dw = torch.zeros_like(x), torch.zeros_like(weight)
+    L.call("kg_bdd_rel_bwd", L.f32(x), None, 0, L.f32(dagg), L.i32(gi.rel_pack), e, L.f32(weight), None, B, si, so,
+           L.f32(dx), L.f32(dw), 0, L.stream())
+    chunks = ops._block_chunks(B, si, so, 2)
+    assert len(chunks) == 2 and chunks[0][0] == 0 and chunks[-1][1] == B
+    agg_c, dw_c, dx_parts = torch.zeros_like(agg), torch.zeros_like(dw), []
+    for b0, b1 in chunks:
+        xc = x[:, b0 * si:b1 * si].contiguous()
+        L.call("kg_bdd_rel_fwd_cols", L.f32(xc), L.i32(gi.rel_pack), e, L.f32(weight), b0, b1 - b0, B, si, so,
+               L.f32(agg_c), 0, L.stream())
+        dxc = torch.zeros_like(xc)
+        L.call("kg_bdd_rel_bwd_cols", L.f32(xc), L.f32(dagg), L.i32(gi.rel_pack), e, L.f32(weight), b0, b1 - b0, B, si, so,
+               L.f32(dxc), L.f32(dw_c), 0, L.stream())
+        dx_parts.append(dxc)
+    assert_close(agg_c, agg, 1e-5, "chunked messages")
+    assert_close(torch.cat(dx_parts, 1), dx, 1e-5, "chunked source gradients")
+    assert_close(dw_c, dw, 1e-5, "chunked weight gradients")
