@@ -38,6 +38,45 @@ __host__ __device__ __forceinline__ Span make_span(int first, int n) {
 }
 __host__ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
 
+// a lane's WN weights from global memory: 128-bit loads when WN * 4 is a multiple of 16 (every lane's slice is then
+// 16-byte aligned), 64-bit loads otherwise (5x5 blocks, two per lane: 50 floats)
+template <int WN>
+__device__ __forceinline__ void ldg_weights(float (&w)[WN], const float* __restrict__ p) {
+  if (WN % 4 == 0) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < WN / 4; ++i) {
+      const float4 t = __ldg(q + i);
+      w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+    }
+  } else {
+    const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+    for (int i = 0; i < WN / 2; ++i) {
+      const float2 t = __ldg(q + i);
+      w[2 * i] = t.x; w[2 * i + 1] = t.y;
+    }
+  }
+}
+
+// dst[0..WN) += r[0..WN) with vector reductions, then r = 0 (owners only reduce; everyone clears)
+template <int WN>
+__device__ __forceinline__ void red_flush(float* dst, float (&r)[WN], bool owner) {
+  if (WN % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < WN; i += 4) {
+      if (owner) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+      r[i] = r[i + 1] = r[i + 2] = r[i + 3] = 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < WN; i += 2) {
+      if (owner) red_add_v2(dst + i, r[i], r[i + 1]);
+      r[i] = r[i + 1] = 0.f;
+    }
+  }
+}
+
 template <int N>
 __device__ __forceinline__ void park_raw(float* mine, const float (&v)[N]) {
   if (N % 4 == 0) {
@@ -123,12 +162,7 @@ fwd_kernel(RowSource feat, const int4* __restrict__ pack, int E, const float* __
     const int4 p = rec[k];
     if (p.z != cur) {                                          // relation run starts (warp-uniform)
       cur = p.z;
-      const float4* wr = reinterpret_cast<const float4*>(row_at(w_g, cur, ldw));
-#pragma unroll
-      for (int i = 0; i < WN / 4; ++i) {
-        const float4 t = __ldg(wr + i);
-        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-      }
+      ldg_weights<WN>(w, row_at(w_g, cur, ldw));
     }
     float xv[XN], m[CN];
     lds_vec<XN>(xv, xg + st * L.stage_f);
@@ -245,12 +279,7 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
   int cur = -1;
 
   auto flush = [&](int rel) {                 // dW role, owners only
-    float* dst = dW_g + (size_t)(unsigned)rel * KW;
-#pragma unroll
-    for (int i = 0; i < WN; i += 4) {
-      if (owner) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
-      r[i] = r[i + 1] = r[i + 2] = r[i + 3] = 0.f;
-    }
+    red_flush<WN>(dW_g + (size_t)(unsigned)rel * KW, r, owner);
   };
 
   if (xrole) {                                // warp-uniform: one loop per role keeps the live ranges apart
@@ -261,12 +290,7 @@ bwd_kernel(RowSource x, const float* __restrict__ dagg, const int4* __restrict__
       const float nv = __int_as_float(p.w);
       if (p.z != cur) {
         cur = p.z;
-        const float4* wr = reinterpret_cast<const float4*>(w_g + (size_t)(unsigned)cur * KW);
-#pragma unroll
-        for (int i = 0; i < WN / 4; ++i) {
-          const float4 t = __ldg(wr + i);
-          r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
-        }
+        ldg_weights<WN>(r, w_g + (size_t)(unsigned)cur * KW);
       }
       float dv[DN], m[XN];
       lds_vec<DN>(dv, dg + st * stage_f);
@@ -429,12 +453,7 @@ bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __res
       const float nv = __int_as_float(p.w);
       if (p.z != cur) {
         cur = p.z;
-        const float4* wr = reinterpret_cast<const float4*>(w_g + (size_t)(unsigned)cur * KW);
-#pragma unroll
-        for (int i = 0; i < WN / 4; ++i) {
-          const float4 t = __ldg(wr + i);
-          r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
-        }
+        ldg_weights<WN>(r, w_g + (size_t)(unsigned)cur * KW);
       }
       float dv[DN], m[XN];
       lds_vec<DN>(dv, dg + st * L.stage_f);
@@ -462,12 +481,7 @@ bwd_paired_kernel(RowSource x, const float* __restrict__ dagg, const int4* __res
     if (lane == 0) bulk_wait_all();
   } else {
     auto flush = [&](int rel) {               // owners only
-      float* dst = dW_g + (size_t)(unsigned)rel * KW;
-#pragma unroll
-      for (int i = 0; i < WN; i += 4) {
-        if (owner) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
-        r[i] = r[i + 1] = r[i + 2] = r[i + 3] = 0.f;
-      }
+      red_flush<WN>(dW_g + (size_t)(unsigned)rel * KW, r, owner);
     };
     int k = 0;
     _Pragma("unroll 1") while (k < n_my) {    // one relation run at a time: the accumulators start from zero
