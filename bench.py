@@ -1036,7 +1036,9 @@ def run_gpu(args):
             import partition_selfcheck
             partitioned["parity"] = partition_selfcheck.run_all(K, dev, rank, world)      # asserts
             log(f"  partition parity checks passed: {partitioned['parity']}")
-        for name, ag in ((("allgather", True), ("peer", False)) if world > 1 else (("single", True),)):
+        # the peer-memory gather measured 2.4x slower at N = 8 (profiles/r02f): only on request (--peer)
+        legs = (("single", True),) if world == 1 else ((("allgather", True), ("peer", False)) if args.peer else (("allgather", True),))
+        for name, ag in legs:
             partitioned["modes"][name] = partitioned_leg(args, dev, world, rank, log, allgather=ag, steps=3, warmup=3,
                                                          scale=args.scale)
             log(f"  [wikikg2-part x{world}, {name}] {partitioned['modes'][name]['ms_per_step']:.1f} ms/step")
