@@ -462,7 +462,7 @@ def partitioned_leg(args, dev, world, rank, log, allgather, steps, warmup, scale
     g._n = n_nodes if world > 1 else n_local
     g._dev_edges[dev] = (src, dst)
     if world > 1:
-        g.partition = parallel.Partition(lo, hi, n_nodes, peer_gather=not allgather)
+        g.partition = parallel.Partition(lo, hi, n_nodes, peer_gather=not allgather, col_chunks=args.col_chunks)
     torch.manual_seed(0)
     # the embedding table is sharded by owner: each rank holds (and updates) only its rows
     model = K.LinkPredict(K.KGVAE, max(n_local, 1), H, n_rels, num_bases=BASES, dropout=DROPOUT, use_cuda=True,
@@ -524,7 +524,8 @@ def partitioned_leg(args, dev, world, rank, log, allgather, steps, warmup, scale
            "entities": n_nodes, "relations": n_rels, "graph_edges": n_edges_global,
            "scored_triplets": n_scored, "scale": scale,
            "mode": ("single GPU, unpartitioned" if world == 1 else
-                    "NCCL all-gather of layer inputs (async, overlapped with the self-loop GEMM)" if allgather else
+                    f"NCCL all-gather of layer inputs in {args.col_chunks} column chunk(s), pipelined with message passing "
+                    f"and the self-loop GEMM" if allgather else
                     "layer inputs gathered from peer HBM by the message-passing kernels (NVLink, CUDA IPC)"),
            "top_ops_ms": dict(sorted(op_ms.items(), key=lambda kv: -kv[1])[:8]),
            "all_ops_ms": {k_: round(v, 3) for k_, v in sorted(op_ms.items(), key=lambda kv: -kv[1])},
@@ -1213,6 +1214,9 @@ def main():
                          "NVLink) instead of the NCCL all-gather")
     ap.add_argument("--replicas", action="store_true",
                     help="am-entity with N > 1: independent replicas (weak scaling) instead of one graph over the N GPUs")
+    ap.add_argument("--col-chunks", type=int, default=2,
+                    help="partitioned step: column chunks the layer-input all-gather / source-gradient reduce-scatter are "
+                         "pipelined in (1 = one collective per layer)")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="skip the wikikg2-shaped destination-partitioned leg of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
