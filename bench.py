@@ -524,7 +524,7 @@ def partitioned_leg(args, dev, world, rank, log, allgather, steps, warmup, scale
            "entities": n_nodes, "relations": n_rels, "graph_edges": n_edges_global,
            "scored_triplets": n_scored, "scale": scale,
            "mode": ("single GPU, unpartitioned" if world == 1 else
-                    f"NCCL all-gather of layer inputs in {args.col_chunks} column chunk(s), pipelined with message passing "
+                    f"NCCL all-gather of layer inputs in {g.partition.col_chunks} column chunk(s), pipelined with message passing "
                     f"and the self-loop GEMM" if allgather else
                     "layer inputs gathered from peer HBM by the message-passing kernels (NVLink, CUDA IPC)"),
            "top_ops_ms": dict(sorted(op_ms.items(), key=lambda kv: -kv[1])[:8]),
@@ -1214,9 +1214,9 @@ def main():
                          "NVLink) instead of the NCCL all-gather")
     ap.add_argument("--replicas", action="store_true",
                     help="am-entity with N > 1: independent replicas (weak scaling) instead of one graph over the N GPUs")
-    ap.add_argument("--col-chunks", type=int, default=2,
+    ap.add_argument("--col-chunks", type=int, default=0,
                     help="partitioned step: column chunks the layer-input all-gather / source-gradient reduce-scatter are "
-                         "pipelined in (1 = one collective per layer)")
+                         "pipelined in (1 = one collective per layer; 0 = by world size: 2 from 4 GPUs up)")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="skip the wikikg2-shaped destination-partitioned leg of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
