@@ -120,12 +120,14 @@ class GradBuckets:
         dev = self.groups[0][0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.slices, self._bucket_of, self._pending, self._handles, self._hooks = [], {}, [], [], []
+        self._views = {}
         off = 0
         for b, g in enumerate(self.groups):
             start = off
             for p in g:
                 n = p.numel()
                 p.grad = self.flat[off:off + n].view_as(p)
+                self._views[id(p)] = p.grad
                 self._bucket_of[id(p)] = b
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
                 off += n
@@ -147,6 +149,13 @@ class GradBuckets:
         self._handles = []
 
     def _hook(self, p):
+        view = self._views[id(p)]
+        if p.grad is not view and (p.grad is None or p.grad.data_ptr() != view.data_ptr()):
+            # someone dropped the view (optimizer.zero_grad(set_to_none=True), p.grad = None): autograd then made a
+            # fresh gradient tensor - move it into the flat buffer so that the bucket all-reduce sees it
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
         b = self._bucket_of[id(p)]
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.world_size > 1:

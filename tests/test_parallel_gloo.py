@@ -45,6 +45,8 @@ def _worker(rank, port, out):
         buckets = parallel.GradBuckets(bp, buckets=[[bp[1]], [bp[0]]])      # bp[2] lands in the trailing bucket
         for it in range(2):
             buckets.zero()
+            if it == 1:                  # a caller that forgets zero() semantics and drops a gradient view
+                bp[0].grad = None
             scale = float(rank + 1 + it)
             (bp[0].sum() * scale + (bp[1] * bp[1]).sum() * scale).backward()       # bp[2] unused: zeros
             buckets.finish()
