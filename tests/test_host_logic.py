@@ -174,3 +174,21 @@ def test_entity_classify_directory_loader(tmp_path):
     assert small.num_nodes == 3 and small.edge_src.max() < 3 and small.edge_dst.max() < 3
     toy = EC.load_data("toy:3")
     assert toy.num_nodes == 300 and len(toy.edge_src) == 2500
+
+
+def test_block_chunks_for_the_column_pipeline():
+    """ops._block_chunks: contiguous block ranges the column-chunk kernels accept (5x5 / 5x10 blocks, cuts at
+    multiples of 4 blocks so that every chunk's columns start 16-byte aligned, at most 64 blocks per chunk)."""
+    from gcn_vae_b200 import ops
+    assert ops._block_chunks(100, 5, 5, 2) == [(0, 48), (48, 100)]
+    assert ops._block_chunks(100, 5, 10, 2) == [(0, 48), (48, 100)]
+    assert ops._block_chunks(8, 5, 5, 2) == [(0, 4), (4, 8)]
+    assert ops._block_chunks(100, 5, 10, 1) == []                 # one collective per layer
+    assert ops._block_chunks(25, 20, 20, 2) == []                 # other block shapes: no chunked kernels
+    assert ops._block_chunks(6, 5, 5, 2) == []                    # not a multiple of 4 blocks
+    assert ops._block_chunks(200, 5, 5, 2) == []                  # chunks would exceed 64 blocks
+    for B, n in ((100, 2), (100, 4), (64, 2), (128, 4)):
+        ch = ops._block_chunks(B, 5, 10, n)
+        if ch:
+            assert ch[0][0] == 0 and ch[-1][1] == B and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            assert all((b1 - b0) % 2 == 0 and b0 % 4 == 0 for b0, b1 in ch)
