@@ -100,7 +100,7 @@ KERNELS_PER_CALL = {
     "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 1,
     "kg_gemm_f32": 4,        # operand conversions (1-2 kernels each) + the product (+ split-K finish): a lower bound
    
-    "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3,
+    "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3, "kg_distmult_topk": 5,
 }
 launches = 0          # running count of kernels launched through this binding
 profile = None        # when a dict: name -> [(start_event, end_event), ...] per call

@@ -80,7 +80,7 @@ __global__ void prior_prepare_kernel(const float* __restrict__ z_pre, int k, int
 // the essentials: -t^2/(2v) with one approximate division, log(sqrt(v)) = 0.5 log v, and for the
 // mixture terms only fma(-(z-m_i)^2, 1/(2 v_i), .): the sum of log(sqrt(v_i)) + log(sqrt(2 pi)) over
 // the columns does not depend on the row and is accumulated once per warp.
-static constexpr int kKlWarpRows = 2;
+static constexpr int kKlWarpRows = 4;
 
 template <int KM, int V>
 __global__ void __launch_bounds__(128, 4)
@@ -178,7 +178,8 @@ kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
 
 static constexpr int kKlRows = 32;   // rows per CTA in the backward kernel
 
-__global__ void __launch_bounds__(128)
+template <int KM>
+__global__ void __launch_bounds__(128, 4)
 kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
                   const float* __restrict__ zv, const float* __restrict__ z_pre,
                   const float* __restrict__ ws, const float* __restrict__ resp, float scale, int n,
@@ -192,15 +193,15 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
   const float c_add = coefs ? __ldg(coefs + 1) : 0.f, c_z = coefs ? __ldg(coefs + 2) : 0.f;
   if (coefs) scale *= __ldg(coefs);
   const int r0 = blockIdx.x * kKlRows, r1 = min(n, r0 + kKlRows);
-  float pm[kMaxMix], ipv[kMaxMix], gpm[kMaxMix], gpv[kMaxMix];
+  float pm[KM], ipv[KM], gpm[KM], gpv[KM];
 #pragma unroll
-  for (int i = 0; i < kMaxMix; ++i) {
+  for (int i = 0; i < KM; ++i) {
     pm[i] = i < k ? z_pre[(size_t)i * h + d] : 0.f;
     ipv[i] = i < k ? 1.f / ws[(size_t)i * h + d] : 0.f;
     gpm[i] = 0.f;
     gpv[i] = 0.f;
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int row = r0; row < r1; ++row) {
     const size_t off = (size_t)row * h + d;
     const float zc = z[off], v = zv[off];
@@ -210,7 +211,7 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
     dmean[off] = scale * t * iv;
     dvar[off] = scale * (0.5f * t * t * iv * iv - 0.5f * iv);
 #pragma unroll
-    for (int i = 0; i < kMaxMix; ++i)
+    for (int i = 0; i < KM; ++i)
       if (i < k) {
         const float ri = __ldg(resp + (size_t)row * k + i);
         const float u = zc - pm[i];
@@ -224,7 +225,7 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
     dz[off] = out;
   }
 #pragma unroll
-  for (int i = 0; i < kMaxMix; ++i)
+  for (int i = 0; i < KM; ++i)
     if (i < k) {
       atomicAdd(dz_pre + (size_t)i * h + d, scale * gpm[i]);
       atomicAdd(dz_pre + (size_t)(k + i) * h + d,
@@ -258,6 +259,16 @@ extern "C" int kg_kl_mog_fwd(const float* z, const float* z_mean, const float* z
   return KG_OK;
 }
 
+// the per-thread mixture arrays are sized by the smallest instantiation that holds k (registers -> occupancy)
+static void launch_kl_bwd(dim3 grid, cudaStream_t st, const float* z, const float* zm, const float* zv, const float* z_pre,
+                          const float* ws, const float* resp, float scale, int n, int h, int k, const float* coefs,
+                          const float* add, float* dz, float* dmean, float* dvar, float* dz_pre) {
+  if (k <= 4) kl_mog_bwd_kernel<4><<<grid, 128, 0, st>>>(z, zm, zv, z_pre, ws, resp, scale, n, h, k, coefs, add, dz, dmean, dvar, dz_pre);
+  else if (k <= 8) kl_mog_bwd_kernel<8><<<grid, 128, 0, st>>>(z, zm, zv, z_pre, ws, resp, scale, n, h, k, coefs, add, dz, dmean, dvar, dz_pre);
+  else if (k <= 12) kl_mog_bwd_kernel<12><<<grid, 128, 0, st>>>(z, zm, zv, z_pre, ws, resp, scale, n, h, k, coefs, add, dz, dmean, dvar, dz_pre);
+  else kl_mog_bwd_kernel<16><<<grid, 128, 0, st>>>(z, zm, zv, z_pre, ws, resp, scale, n, h, k, coefs, add, dz, dmean, dvar, dz_pre);
+}
+
 extern "C" int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z_var,
                              const float* z_pre, const float* prior_ws, const float* resp, float scale,
                              int n, int h, int k, float* dz, float* dmean, float* dvar, float* dz_pre,
@@ -265,8 +276,8 @@ extern "C" int kg_kl_mog_bwd(const float* z, const float* z_mean, const float* z
   KG_REQUIRE(n >= 0 && h > 0 && k > 0 && k <= kMaxMix, "kl bwd: need 0 < k <= 16");
   if (n == 0) return KG_OK;
   dim3 grid(kg_div_up(n, kKlRows), kg_div_up(h, 128));
-  kl_mog_bwd_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, z_mean, z_var, z_pre, prior_ws, resp, scale, n,
-                                                         h, k, nullptr, nullptr, dz, dmean, dvar, dz_pre);
+  launch_kl_bwd(grid, kg_stream(stream), z, z_mean, z_var, z_pre, prior_ws, resp, scale, n, h, k, nullptr, nullptr, dz,
+                dmean, dvar, dz_pre);
   KG_LAUNCH_OK();
   return KG_OK;
 }
@@ -283,8 +294,8 @@ extern "C" int kg_kl_mog_bwd_fused(const float* z, const float* z_mean, const fl
   KG_REQUIRE(coefs != nullptr, "kl bwd fused: coefs is required");
   if (n == 0) return KG_OK;
   dim3 grid(kg_div_up(n, kKlRows), kg_div_up(h, 128));
-  kl_mog_bwd_kernel<<<grid, 128, 0, kg_stream(stream)>>>(z, z_mean, z_var, z_pre, prior_ws, resp, scale, n,
-                                                         h, k, coefs, add, dz, dmean, dvar, dz_pre);
+  launch_kl_bwd(grid, kg_stream(stream), z, z_mean, z_var, z_pre, prior_ws, resp, scale, n, h, k, coefs, add, dz, dmean,
+                dvar, dz_pre);
   KG_LAUNCH_OK();
   return KG_OK;
 }
