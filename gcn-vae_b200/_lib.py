@@ -49,6 +49,11 @@ _SIGNATURES = {
     "kg_colsum": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     "kg_gemm_f32_workspace_bytes": (_Z, [_I, _I, _I]),
     "kg_gemm_f32": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _Z, _P]),
+    "kg_gemm_f32_uses_tensor_cores": (_I, [_I, _I, _I]),
+    "kg_gemm_prep_bytes": (_Z, [_I, _I]),
+    "kg_gemm_prepare": (_I, [_P, _I, _I, _I, _P, _Z, _P]),
+    "kg_gemm_f32_prepared_workspace_bytes": (_Z, [_I, _I, _I]),
+    "kg_gemm_f32_prepared": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _Z, _P]),
     "kg_reparam_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "kg_reparam_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_kl_mog_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
@@ -98,8 +103,8 @@ def lib():
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
     "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 1,
-    "kg_gemm_f32": 4,        # operand conversions (1-2 kernels each) + the product (+ split-K finish): a lower bound
-   
+    "kg_gemm_f32": 5,        # two operand preparations (2 kernels each) + the product (+ split-K finish): a lower bound
+    "kg_gemm_prepare": 2,
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3, "kg_distmult_topk": 5,
 }
 launches = 0          # running count of kernels launched through this binding

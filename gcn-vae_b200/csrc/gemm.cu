@@ -8,7 +8,7 @@
 // 1e-4 relative vs the reference).
 #include "gemm_tile.cuh"
 
-size_t kg_gemm_tc_workspace_bytes(int M, int N, int K);
+size_t kg_gemm_tc_workspace_bytes(int M, int N, int K, int trans_a, int trans_b);
 bool kg_gemm_tc_eligible(int M, int N, int K);
 int kg_gemm_tc_run(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C,
                    int ldc, int M, int N, int K, const float* bias, const float* addend, int relu,
@@ -114,8 +114,17 @@ static int launch(const float* A, int lda, const float* B, int ldb, int M, int N
 }
 
 extern "C" size_t kg_gemm_f32_workspace_bytes(int M, int N, int K) {
-  return kg_gemm_tc_eligible(M, N, K) ? kg_gemm_tc_workspace_bytes(M, N, K) : 0;
+  // sized for the larger of the two storage orders of each operand (the padded widths differ)
+  if (!kg_gemm_tc_eligible(M, N, K)) return 0;
+  size_t best = 0;
+  for (int t = 0; t < 4; ++t) {
+    const size_t b = kg_gemm_tc_workspace_bytes(M, N, K, t & 1, t >> 1);
+    if (b > best) best = b;
+  }
+  return best;
 }
+
+extern "C" int kg_gemm_f32_uses_tensor_cores(int M, int N, int K) { return kg_gemm_tc_eligible(M, N, K) ? 1 : 0; }
 
 extern "C" int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
                            float* C, int ldc, int M, int N, int K, const float* bias,

@@ -150,40 +150,68 @@ __device__ __forceinline__ void pipe_mma(const Pipe& P, const TileMap& tmap, int
 // pair above streams 6 tiles per k-step; at K = 500 that traffic, not the tensor pipe, bounded the
 // GEMM.  Two stages fit the same shared memory as the four 48 KB ones (barriers full[0..1],
 // empty[0..1] of the same Pipe).
+//
+// Either operand may be K-major (array rows = the operand's M/N index, contraction along the array's
+// columns: one {64 x BM|BN} box per term) or MN-major (array rows = the contraction index: {64 x 64}
+// boxes, one per 64 elements of M/N, k-rows beyond the array read as zero).  `cp` is the column at which
+// the lo half of the operand's array starts.
 // ------------------------------------------------------------------------------------------
 constexpr int WIDE_STAGES = 2;
 constexpr int WIDE_STAGE_BYTES = 2 * STAGE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+constexpr int MN_BOX_BYTES = 64 * BK * 2;                  // one {64 x 64} fp16 box
 static_assert(WIDE_STAGES * WIDE_STAGE_BYTES <= STAGES * STAGE_BYTES, "wide stages must fit the pipe's shared memory");
+
+struct WideOperands {
+  int a_mn, b_mn;      // 1: MN-major
+  int a_cp, b_cp;      // first column of the lo half
+};
+
+template <int TILE_MN>
+__device__ __forceinline__ void wide_load(uint8_t* hi, uint8_t* lo, const CUtensorMap* tm, uint64_t* bar, int mn_major,
+                                          int cp, int mn0, int ks, bool want_lo) {
+  if (!mn_major) {
+    tma_load_2d(hi, tm, bar, ks * BK, mn0);
+    if (want_lo) tma_load_2d(lo, tm, bar, cp + ks * BK, mn0);
+  } else {
+#pragma unroll
+    for (int j = 0; j < TILE_MN / 64; ++j) {
+      const int c = mn0 + 64 * j;
+      const bool inside = c < cp;                    // a box past the padded width reads zeros (fully out of bounds)
+      tma_load_2d(hi + j * MN_BOX_BYTES, tm, bar, inside ? c : 2 * cp, ks * BK);
+      if (want_lo) tma_load_2d(lo + j * MN_BOX_BYTES, tm, bar, inside ? cp + c : 2 * cp, ks * BK);
+    }
+  }
+}
 
 // warp 0
 __device__ __forceinline__ void pipe_producer_wide(const Pipe& P, const CUtensorMap* tm_a, const CUtensorMap* tm_b,
-                                                   const TileMap& tmap, int Kp, int n_terms = 3) {
+                                                   const TileMap& tmap, const WideOperands& op, int n_terms = 3) {
   if (!elect_one()) return;
   int stage = 0;
   uint32_t phase = 0;
   const int total = tmap.total();
+  const bool lo = n_terms == 3;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     int m0, n0, split, ks0, nks;
     tmap.decode(tile, m0, n0, split, ks0, nks);
     for (int ks = ks0; ks < ks0 + nks; ++ks) {
       mbar_wait(P.empty + stage, phase ^ 1);
       uint8_t* st = P.smem + stage * WIDE_STAGE_BYTES;
-      mbar_arrive_expect_tx(P.full + stage, n_terms == 3 ? WIDE_STAGE_BYTES : STAGE_BYTES);
-      tma_load_2d(st, tm_a, P.full + stage, ks * BK, m0);                              // A_hi
-      tma_load_2d(st + 2 * A_BYTES, tm_b, P.full + stage, ks * BK, n0);                // B_hi
-      if (n_terms == 3) {
-        tma_load_2d(st + A_BYTES, tm_a, P.full + stage, Kp + ks * BK, m0);               // A_lo
-        tma_load_2d(st + 2 * A_BYTES + B_BYTES, tm_b, P.full + stage, Kp + ks * BK, n0); // B_lo
-      }
+      mbar_arrive_expect_tx(P.full + stage, lo ? WIDE_STAGE_BYTES : STAGE_BYTES);
+      wide_load<BM>(st, st + A_BYTES, tm_a, P.full + stage, op.a_mn, op.a_cp, m0, ks, lo);
+      wide_load<BN>(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, tm_b, P.full + stage, op.b_mn, op.b_cp, n0, ks, lo);
       if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }
     }
   }
 }
 
 // warp 1
-__device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap, int n_terms = 3) {
+__device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap, const WideOperands& op, int n_terms = 3) {
   if (!elect_one()) return;
-  constexpr uint32_t idesc = instr_desc_f16(0, BM, BN);
+  const uint32_t idesc = instr_desc_f16(0, BM, BN, op.a_mn, op.b_mn);
+  // descriptor address field is in 16-byte units: a K = 16 step is 32 bytes along a K-major row, two 1024-byte
+  // atoms of an MN-major tile
+  const uint32_t a_step = op.a_mn ? 2048 >> 4 : 32 >> 4, b_step = op.b_mn ? 2048 >> 4 : 32 >> 4;
   int stage = 0;
   uint32_t phase = 0;
   int it = 0;
@@ -199,18 +227,21 @@ __device__ __forceinline__ void pipe_mma_wide(const Pipe& P, const TileMap& tmap
       mbar_wait(P.full + stage, phase);
       fence_after_thread_sync();
       const uint32_t sa = smem_u32(P.smem + stage * WIDE_STAGE_BYTES);
-      const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + A_BYTES);
-      const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * A_BYTES), b_lo = smem_desc_k_sw128(sa + 2 * A_BYTES + B_BYTES);
+      const uint32_t sb = sa + 2 * A_BYTES;
+      const uint64_t a_hi = op.a_mn ? smem_desc_mn_sw128(sa, MN_BOX_BYTES) : smem_desc_k_sw128(sa);
+      const uint64_t a_lo = op.a_mn ? smem_desc_mn_sw128(sa + A_BYTES, MN_BOX_BYTES) : smem_desc_k_sw128(sa + A_BYTES);
+      const uint64_t b_hi = op.b_mn ? smem_desc_mn_sw128(sb, MN_BOX_BYTES) : smem_desc_k_sw128(sb);
+      const uint64_t b_lo = op.b_mn ? smem_desc_mn_sw128(sb + B_BYTES, MN_BOX_BYTES) : smem_desc_k_sw128(sb + B_BYTES);
       if (n_terms == 3) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);   // small terms first
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_lo + k * a_step, b_hi + k * b_step, idesc, (ks | k) != 0);   // small terms first
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + k * a_step, b_lo + k * b_step, idesc, true);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + k * a_step, b_hi + k * b_step, idesc, true);
       } else {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (ks | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) mma_f16_ss(tacc, a_hi + k * a_step, b_hi + k * b_step, idesc, (ks | k) != 0);
       }
       mma_commit(P.empty + stage);        // frees the stage once these MMAs have read it
       if (++stage == WIDE_STAGES) { stage = 0; phase ^= 1; }

@@ -119,11 +119,29 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: A/B format 0 = F16, 1 = BF16; fp32 accumulate; both K-major.
-__host__ __device__ constexpr uint32_t instr_desc_f16(int ab_format, int M, int N) {
+// The same for an MN-major operand tile: what TMA boxes {64 x 16-bit along M/N, 64 rows along K} write, one
+// 8 KB box per 64 elements of M/N.  A swizzle atom is 8 k-rows x 128 bytes (64 M/N elements); the stride byte
+// offset is the distance between atoms along K (1024 bytes: the k-rows of a box are consecutive), the leading
+// byte offset the distance between atoms along M/N (the box pitch).  One K = 16 MMA step covers two atoms along K:
+// the start address advances by 2048 bytes per step.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t box_pitch_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address       bits [0,14)
+  d |= (uint64_t)(box_pitch_bytes >> 4) << 16;        // leading byte offset bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                             // version             bits [46,48)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B        bits [61,64)
+  return d;
+}
+
+// Instruction descriptor, kind::f16: A/B format 0 = F16, 1 = BF16; fp32 accumulate; a_mn / b_mn = 1 when that
+// operand's tile is MN-major in shared memory (0 = K-major).
+__host__ __device__ constexpr uint32_t instr_desc_f16(int ab_format, int M, int N, int a_mn = 0, int b_mn = 0) {
   return (1u << 4)                       // C format F32
          | ((uint32_t)ab_format << 7)    // A format
          | ((uint32_t)ab_format << 10)   // B format
+         | ((uint32_t)a_mn << 15)        // A major
+         | ((uint32_t)b_mn << 16)        // B major
          | ((uint32_t)(N >> 3) << 17)    // N
          | ((uint32_t)(M >> 4) << 24);   // M
 }

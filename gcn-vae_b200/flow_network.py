@@ -24,9 +24,9 @@ class MaskedLinear(nn.Linear):
     def masked_weight(self):
         return self.mask * self.weight
 
-    def forward(self, x, relu=False, weight=None):
+    def forward(self, x, relu=False, weight=None, prepared=None):
         w = self.masked_weight() if weight is None else weight
-        return ops.LinearFn.apply(x, w, self.bias, relu)
+        return ops.LinearFn.apply(x, w, self.bias, relu, prepared)
 
 
 class PermuteLayer(nn.Module):
@@ -72,10 +72,10 @@ class MADE(nn.Module):
     def _linears(self):
         return [layer for layer in self.net if isinstance(layer, MaskedLinear)]
 
-    def _run_net(self, x, weights):
+    def _run_net(self, x, weights, prepared=None):
         linears = self._linears()
         for i, (layer, w) in enumerate(zip(linears, weights)):
-            x = layer(x, relu=(i + 1 < len(linears)), weight=w)
+            x = layer(x, relu=(i + 1 < len(linears)), weight=w, prepared=prepared[i] if prepared else None)
         return x
 
     def forward(self, z):
@@ -86,6 +86,10 @@ class MADE(nn.Module):
         weights = [layer.masked_weight() for layer in self._linears()]
         if self._col_mult[0].device != z.device:
             self._col_mult = [m.to(z.device) for m in self._col_mult]
+        # every full pass multiplies by the same masked weights: split them for the tensor cores once
+        prepared = [ops.prepare(w.contiguous(), z.shape[0]) for w in weights] if z.is_cuda else None
+        if prepared is not None and not any(isinstance(p_, ops.Prepared) for p_ in prepared):
+            prepared = None
         x = torch.zeros_like(z)
         log_det = None
         n_pass = len(self.m)
@@ -96,7 +100,7 @@ class MADE(nn.Module):
                 # backward the expand turns the N-row gradient into its column sum before the network
                 out = self._run_net(x[:1], weights).expand(z.shape[0], -1)
             else:
-                out = self._run_net(x, weights)
+                out = self._run_net(x, weights, prepared)
             x, log_det = ops.IafUpdateFn.apply(z, out, x, mult, p + 1 == n_pass)
         return x, log_det
 

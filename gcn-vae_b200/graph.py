@@ -42,6 +42,15 @@ class Graph:
         self._dev_edges = {}     # device -> (src int32, dst int32)
         self._index = None       # (key, ops.GraphIndex)
 
+    @classmethod
+    def from_device_edges(cls, num_nodes, src, dst):
+        """A graph whose edge list already lives on the GPU (int32 ``src`` / ``dst``): nothing is copied; the
+        host-side queries pull the edges over on first use."""
+        g = cls()
+        g._n = int(num_nodes)
+        g._dev_edges[src.device] = (src, dst)
+        return g
+
     # ---- DGLGraph construction surface -------------------------------------------------
     def add_nodes(self, n):
         self._n += int(n)

@@ -128,6 +128,81 @@ class LinkPredict(nn.Module):
         return loss, predict_loss, kl, mmd
 
 
+class CapturedTrainStep:
+    """The train step of kgvae/link_predict.py:217-228 - edge index, forward, ``get_loss``, backward,
+    ``clip_grad_norm_``, ``optimizer.step()`` - for inputs of FIXED shape (full-graph training, or any fixed
+    number of nodes / edges / scored triplets), captured once into a CUDA graph and replayed.
+
+    An eager step is ~150 kernel launches issued through autograd and ctypes; at 4-5 ms of GPU work per step
+    the host cannot stay ahead of the device, and the GPU idles between kernels.  A replay is one launch: the
+    step then costs what its kernels cost.  Everything in the step is stream-ordered device work (no host
+    read-back, device-resident Adam step counters, Philox offsets advanced per replay by PyTorch), so the replay
+    computes exactly what the eager step computes on the tensors in ``inputs``.
+
+    ``example``: dict of device tensors ``node_id [n,1]``, ``src``/``dst``/``etype [E]`` (int32), ``norm [E,1]``,
+    ``samples [S,3]`` (int32), ``labels [S]`` - their shapes are the captured shapes.  The optimizer must be
+    ``capturable`` (``torch.optim.Adam(..., fused=True, capturable=True)``).  The ``warmup`` eager steps that
+    precede the capture ARE train steps on ``example``.  ``step(**tensors)`` copies new inputs of the same shapes
+    into place (device-to-device or from pinned host memory, stream-ordered), replays, and returns the loss
+    tensor (device; read it with ``float()`` when needed)."""
+
+    FIELDS = ("node_id", "src", "dst", "etype", "norm", "samples", "labels")
+
+    def __init__(self, model, optimizer, example, num_nodes, buckets=None, grad_norm=1.0, warmup=3):
+        from . import _lib
+        from .graph import Graph
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise RuntimeError("CapturedTrainStep: the optimizer must be constructed with capturable=True")
+        dev = example["src"].device
+        if dev.type != "cuda":
+            raise RuntimeError("kgvae_b200: CapturedTrainStep needs CUDA tensors (no CPU fallback)")
+        self._Graph = Graph
+        self.model, self.optimizer, self.num_nodes, self.grad_norm = model, optimizer, int(num_nodes), grad_norm
+        self.buckets = buckets if buckets is not None else model.grad_buckets()
+        self.inputs = {k: example[k].clone() for k in self.FIELDS}
+        self.predict_loss = self.kl = self.mmd = None
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):         # lazy initialisation, optimizer state and allocator warm-up off the capture
+            for _ in range(max(int(warmup), 1)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before, prof = _lib.launches, _lib.profile
+        _lib.profile = None                   # no timing events inside a capture
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager()
+        finally:
+            _lib.profile = prof
+        self.launches_per_step = _lib.launches - before      # kernels of this library inside one replay
+
+    def _eager(self):
+        t = self.inputs
+        g = self._Graph.from_device_edges(self.num_nodes, t["src"], t["dst"])
+        self.buckets.zero()
+        embed = self.model(g, t["node_id"], t["etype"], t["norm"])
+        loss, self.predict_loss, self.kl, self.mmd = self.model.get_loss(g, embed, t["samples"], t["labels"])
+        loss.backward()
+        self.buckets.finish()
+        self.buckets.clip_(self.grad_norm)
+        self.optimizer.step()
+        return loss.detach()
+
+    def load(self, **tensors):
+        for k, v in tensors.items():
+            self.inputs[k].copy_(v.view_as(self.inputs[k]), non_blocking=True)
+
+    def step(self, **tensors):
+        if tensors:
+            self.load(**tensors)
+        self.graph.replay()
+        return self.loss
+
+    __call__ = step
+
+
 def node_norm_to_edge_norm(g, node_norm):
     """edge_norm[e] = node_norm[dst[e]] (link_predict.py:95-100)."""
     g = g.local_var()

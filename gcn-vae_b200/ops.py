@@ -157,17 +157,54 @@ def graph_build(src, rel, dst, n_nodes, n_rels, node_major=False):
 # ---------------------------------------------------------------------------------------------
 # dense GEMM helper
 # ---------------------------------------------------------------------------------------------
+class Prepared:
+    """A matrix in the tensor-core GEMM's operand form (kg_gemm_prepare): split once, then usable by every product
+    it takes part in, in either orientation.  Keeps the fp32 source for products too small for the tensor cores."""
+    __slots__ = ("src", "buf", "shape", "device")
+
+    def __init__(self, src):
+        rows, cols = src.shape
+        self.src, self.shape, self.device = src, src.shape, src.device
+        nbytes = L.lib().kg_gemm_prep_bytes(rows, cols)
+        self.buf = L.workspace(nbytes, src.device)
+        L.call("kg_gemm_prepare", L.f32(src), src.stride(0), rows, cols, L.ptr(self.buf), nbytes, L.stream())
+
+
+def uses_tensor_cores(M, N, K):
+    return bool(L.lib().kg_gemm_f32_uses_tensor_cores(M, N, K))
+
+
+def prepare(t, other_dim):
+    """Prepared form of the 2-D fp32 matrix ``t`` when its products with a matrix whose free dimension is
+    ``other_dim`` run on the tensor cores (all three extents >= 64 and a large enough volume); else ``t``."""
+    if isinstance(t, Prepared):
+        return t
+    r, c = t.shape
+    if min(r, c, other_dim) >= 64 and uses_tensor_cores(r, c, other_dim):
+        return Prepared(t)
+    return t
+
+
 def gemm(a, b, out, trans_a=False, trans_b=False, bias=None, addend=None, relu=False, mask=None,
          accumulate=False):
-    """out[M,N] (+)= epilogue(op(a) @ op(b)); a, b, out 2-D contiguous fp32."""
+    """out[M,N] (+)= epilogue(op(a) @ op(b)); a, b 2-D fp32 with contiguous rows or ``Prepared``, out 2-D fp32."""
     M, N = out.shape
     K = a.shape[0] if trans_a else a.shape[1]
-    nbytes = L.lib().kg_gemm_f32_workspace_bytes(M, N, K)
-    ws = L.workspace(nbytes, out.device) if nbytes else None
-    L.call("kg_gemm_f32", L.f32(a), a.shape[1], int(trans_a), L.f32(b), b.shape[1], int(trans_b),
-           L.f32(out), out.shape[1], M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask),
-           int(accumulate), L.ptr(ws), nbytes, L.stream(),
-           tag=f"kg_gemm_f32[{M}x{N}x{K},{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]")
+    tag = f"kg_gemm_f32[{M}x{N}x{K},{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]"
+    if uses_tensor_cores(M, N, K):
+        pa = a if isinstance(a, Prepared) else Prepared(a)
+        pb = b if isinstance(b, Prepared) else Prepared(b)
+        nbytes = L.lib().kg_gemm_f32_prepared_workspace_bytes(M, N, K)
+        ws = L.workspace(nbytes, out.device)
+        L.call("kg_gemm_f32_prepared", L.ptr(pa.buf), int(trans_a), L.ptr(pb.buf), int(trans_b), L.f32(out),
+               out.stride(0), M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask), int(accumulate),
+               L.ptr(ws), nbytes, L.stream(), tag=tag)
+        return out
+    a = a.src if isinstance(a, Prepared) else a
+    b = b.src if isinstance(b, Prepared) else b
+    L.call("kg_gemm_f32", L.f32(a), a.stride(0), int(trans_a), L.f32(b), b.stride(0), int(trans_b),
+           L.f32(out), out.stride(0), M, N, K, L.f32(bias), L.f32(addend), int(relu), L.f32(mask),
+           int(accumulate), None, 0, L.stream(), tag=tag)
     return out
 
 
@@ -310,7 +347,9 @@ class BddConvFn(torch.autograd.Function):
         out = torch.empty((n_own, out_feat), dtype=torch.float32, device=dev)
         if loop_weight is not None:                   # out = x_own @ loop_weight + bias   (only local rows)
             loop_weight = _c(loop_weight)
-            gemm(x, loop_weight, out, bias=bias)
+            xp, lwp = prepare(x, out_feat), prepare(loop_weight, n_own)
+            gemm(xp, lwp, out, bias=bias)
+            ctx.prepared = (xp, lwp)   # reused by the backward products  g W_loop^T  and  x^T g
         else:
             epilogue_only(out, bias=bias) if bias is not None else out.zero_()
         pack = _rel_order(gi, 0, n_own, 4 * out_feat)
@@ -351,9 +390,12 @@ class BddConvFn(torch.autograd.Function):
         g = _c(g)
         chunked = bool(ctx.x_chunks)
         lo = part.lo if (ctx.gather and not chunked) else 0
-        x_own = x[lo:lo + ctx.n_own] if (ctx.gather and not chunked) else x      # chunked: x is the local matrix
         gpre, dbias_fused = act_dropout_bwd(g, out, mask, ctx.act, want_colsum=ctx.has_bias)
         dx = dw = dloop = dbias = None
+        xp = lwp = None
+        if loop_weight is not None:
+            xp, lwp = ctx.prepared
+        gp = prepare(gpre, x.shape[1]) if loop_weight is not None else gpre
         pending = None
         if chunked and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             from . import parallel
@@ -362,7 +404,7 @@ class BddConvFn(torch.autograd.Function):
             own_dx = None
             if want_dx and loop_weight is not None:     # self-loop part of the input gradient (local rows only)
                 own_dx = torch.empty((ctx.n_own, x.shape[1]), dtype=torch.float32, device=x.device)
-                gemm(gpre, loop_weight, own_dx, trans_b=True)
+                gemm(gp, lwp, own_dx, trans_b=True)
             pending = []
             for (b0, b1), xc in zip(ctx.chunks, ctx.x_chunks):
                 dxc = torch.zeros_like(xc) if want_dx else None
@@ -395,7 +437,7 @@ class BddConvFn(torch.autograd.Function):
                    B, si, so, L.f32(dx), L.f32(dw), hints, L.stream(), tag=f"kg_bdd_rel_bwd[{si}x{so}]")
             if dx is not None and loop_weight is not None:
                 own_lo = peer.rank * peer.blk if peer is not None else lo
-                gemm(gpre, loop_weight, dx[own_lo:own_lo + ctx.n_own], trans_b=True, accumulate=True)
+                gemm(gp, lwp, dx[own_lo:own_lo + ctx.n_own], trans_b=True, accumulate=True)
             if dx is not None and (peer is not None or ctx.gather):
                 # every rank holds partial sums for all nodes: reduce-scatter to the owners, asynchronously -
                 # the weight-gradient GEMM below does not depend on it
@@ -405,7 +447,7 @@ class BddConvFn(torch.autograd.Function):
                 dw = None
         if loop_weight is not None and ctx.needs_input_grad[2]:
             dloop = torch.empty_like(loop_weight)
-            gemm(x_own, gpre, dloop, trans_a=True)
+            gemm(xp, gp, dloop, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = dbias_fused
         if isinstance(pending, list):
@@ -484,14 +526,19 @@ class KlMogFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     """y = [relu](x @ w^T + b): MaskedLinear (+ the in-place ReLU after it) with the masked
-    weight precomputed once per MADE call (kgvae/flow_network.py:15,53-63)."""
+    weight precomputed - and, as ``wp``, split for the tensor cores - once per MADE call
+    (kgvae/flow_network.py:15,53-63)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu):
+    def forward(ctx, x, w, b, relu, wp=None):
         x, w = _c(x), _c(w)
+        if not isinstance(wp, Prepared) or wp.src.data_ptr() != w.data_ptr():
+            wp = prepare(w, x.shape[0])
+        xp = prepare(x, w.shape[0])
         y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
-        gemm(x, w, y, trans_b=True, bias=None if b is None else _c(b), relu=relu)
+        gemm(xp, wp, y, trans_b=True, bias=None if b is None else _c(b), relu=relu)
         ctx.save_for_backward(x, w, y if relu else None)
+        ctx.prepared = (xp, wp)        # the split operands serve the two backward products as they are
         ctx.relu, ctx.has_bias = relu, b is not None
         return y
 
@@ -503,15 +550,17 @@ class LinearFn(torch.autograd.Function):
         if ctx.relu:                 # ReLU backward and the bias gradient in one pass over g
             g, db_fused = act_dropout_bwd(g, y, None, 1, want_colsum=ctx.has_bias and ctx.needs_input_grad[2])
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            gemm(g, w, dx)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            gemm(g, x, dw, trans_a=True)
+        xp, wp = ctx.prepared
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = db_fused if db_fused is not None else colsum(g)
-        return dx, dw, db, None
+        gp = prepare(g, x.shape[1])
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(gp, wp, dx)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            gemm(gp, xp, dw, trans_a=True)
+        return dx, dw, db, None, None
 
 
 class IafUpdateFn(torch.autograd.Function):

@@ -205,7 +205,7 @@ int kg_colsum(const float* x, int rows, int cols, float* out, void* workspace, s
  *   epilogue: v = acc (+ bias[n]) (+ addend[m*ldc+n]); if relu v = max(v,0);
  *             if mask v *= mask[m*ldc+n]; C = v   (accumulate: C += v)
  * Products with M, N >= 64, K >= 32 and M*N*K >= 2^22 run on the tensor cores (tcgen05,
- * two-term fp16 split of both operands, fp32 accumulate: fp32-accurate); they need
+ * two-term fp16 split of both operands made inside the call, fp32 accumulate: fp32-accurate); they need
  * kg_gemm_f32_workspace_bytes(M, N, K) bytes of workspace (0 for the small-product FMA kernel).
  * ---------------------------------------------------------------------------------- */
 size_t kg_gemm_f32_workspace_bytes(int M, int N, int K);
@@ -213,6 +213,24 @@ int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, i
                 float* C, int ldc, int M, int N, int K,
                 const float* bias, const float* addend, int relu, const float* mask,
                 int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Prepared operands of the tensor-core GEMM (new; the reference's torch.matmul has no counterpart).
+ * kg_gemm_prepare splits a row-major fp32 matrix src[rows, cols] (row pitch ld) once into the two-term fp16
+ * form the tensor-core product reads, under one power-of-two scale for the whole matrix, into a caller-owned
+ * buffer of kg_gemm_prep_bytes(rows, cols) bytes (16-byte aligned).  The same prepared matrix serves every
+ * product it takes part in, in either orientation: a layer prepares x, W and its upstream gradient g once for
+ *   y = x W^T (kgvae/flow_network.py:15),  dx = g W,  dW = g^T x   (and likewise kgvae/model.py:55,58 via DGL).
+ * kg_gemm_f32_prepared is kg_gemm_f32 on prepared operands: prep_a holds A as stored ([M, K], or [K, M] when
+ * trans_a), prep_b holds B as stored ([K, N], or [N, K] when trans_b).  Only for products that
+ * kg_gemm_f32_uses_tensor_cores(M, N, K); workspace kg_gemm_f32_prepared_workspace_bytes(M, N, K). */
+int kg_gemm_f32_uses_tensor_cores(int M, int N, int K);
+size_t kg_gemm_prep_bytes(int rows, int cols);
+int kg_gemm_prepare(const float* src, int ld, int rows, int cols, void* prep, size_t prep_bytes, void* stream);
+size_t kg_gemm_f32_prepared_workspace_bytes(int M, int N, int K);
+int kg_gemm_f32_prepared(const void* prep_a, int trans_a, const void* prep_b, int trans_b,
+                         float* C, int ldc, int M, int N, int K,
+                         const float* bias, const float* addend, int relu, const float* mask,
+                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * a5  mean/variance heads + reparameterised sample
