@@ -47,6 +47,17 @@ class LinkPredict(nn.Module):
         params = [p for p in self.parameters() if p.requires_grad and id(p) not in skip]
         return parallel.GradBuckets(params, buckets=[b for b in order if b], group=group, average=average)
 
+    def release_graph(self):
+        """Detach the tensors the encoder caches between ``forward`` and ``get_loss`` (``z_mean``, ``z_sigma``, the
+        flow's log-determinants - the reference keeps them as attributes, kgvae/model.py:113-123).  They hold the
+        whole autograd graph of the last forward alive, and with it the parameters' gradient-accumulation nodes,
+        which are bound to the stream they were created on."""
+        enc = self.encoder
+        for name in ("z_mean", "z_sigma", "log_det_sum", "flow_log_prob"):
+            v = getattr(enc, name, None)
+            if isinstance(v, torch.Tensor) and v.grad_fn is not None:
+                setattr(enc, name, v.detach())
+
     def _flow_shift(self):
         if self.n_flows > 0 and isinstance(self.encoder, KGVAE):
             return self.encoder.get_flow_log_prob()
@@ -161,18 +172,23 @@ class CapturedTrainStep:
         self.buckets = buckets if buckets is not None else model.grad_buckets()
         self.inputs = {k: example[k].clone() for k in self.FIELDS}
         self.predict_loss = self.kl = self.mmd = None
+        # Warm-up and capture run on ONE side stream, and no autograd graph of an earlier step may be alive: a
+        # parameter's gradient-accumulation node runs on the stream it was created on, and one left over from an
+        # eager step on the default stream would make that stream wait on the capture (illegal).
+        model.release_graph()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):         # lazy initialisation, optimizer state and allocator warm-up off the capture
-            for _ in range(max(int(warmup), 1)):
-                self._eager()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
         before, prof = _lib.launches, _lib.profile
         _lib.profile = None                   # no timing events inside a capture
         try:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.stream(side):     # lazy initialisation, optimizer state and allocator warm-up
+                for _ in range(max(int(warmup), 1)):
+                    self._eager()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.launches
+            with torch.cuda.graph(self.graph, stream=side):
                 self.loss = self._eager()
         finally:
             _lib.profile = prof
@@ -188,7 +204,16 @@ class CapturedTrainStep:
         self.buckets.finish()
         self.buckets.clip_(self.grad_norm)
         self.optimizer.step()
+        self.model.release_graph()
         return loss.detach()
+
+    def close(self):
+        """Release the captured graph and its memory pool (required before the process group is destroyed when the
+        capture contains NCCL kernels)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def load(self, **tensors):
         for k, v in tensors.items():

@@ -95,3 +95,74 @@ def test_entity_classify_driver_on_disk_dataset(tmp_path, capsys):
     out = capsys.readouterr().out
     assert "Epoch 00039" in out and "Test Accuracy" in out
     assert res["train_loss"] < 1.0 and res["test_acc"] > 0.5
+
+
+def _toy_step_inputs(dev, n=300, n_rel=6, e=2400, s=3000, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    deg = torch.bincount(dst, minlength=n).clamp(min=1).float()
+    t = {"node_id": torch.arange(n, dtype=torch.int32).view(-1, 1), "src": src.int(), "dst": dst.int(),
+         "etype": torch.randint(0, 2 * n_rel, (e,), generator=g).int(), "norm": (1.0 / deg)[dst].view(-1, 1),
+         "samples": torch.stack([torch.randint(0, n, (s,), generator=g), torch.randint(0, n_rel, (s,), generator=g),
+                                 torch.randint(0, n, (s,), generator=g)], 1).int(),
+         "labels": (torch.rand(s, generator=g) < 0.3).float()}
+    return {k: v.to(dev) for k, v in t.items()}
+
+
+@pytest.mark.parametrize("n_flows", [0, 1])
+def test_captured_train_step_replays_the_eager_step(n_flows):
+    """link_predict.CapturedTrainStep: the CUDA-graph replay of the train step (kgvae/link_predict.py:217-228)
+    leaves the model where the same number of eager steps leaves it - same noise (the Philox seed is re-read at
+    every replay), same gradients, same Adam updates - on the captured inputs and on new inputs copied into place."""
+    import copy
+    dev = torch.device("cuda:0")
+    n, n_rel = 300, 6
+    torch.manual_seed(0)
+    base = K.LinkPredict(K.KGVAE, n, 40, n_rel, num_bases=8, dropout=0.2, use_cuda=True, reg_param=0.01,
+                         kl_param=1e-3, k=4, n_flows=n_flows).to(dev)
+    inputs = [_toy_step_inputs(dev, n, n_rel, seed=i) for i in range(3)]
+
+    def eager_run():
+        m = copy.deepcopy(base).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+        bk = m.grad_buckets()
+        losses = []
+        for i, t in enumerate(inputs):
+            torch.manual_seed(100 + i)
+            g = K.Graph.from_device_edges(n, t["src"], t["dst"])
+            bk.zero()
+            emb = m(g, t["node_id"], t["etype"], t["norm"])
+            loss = m.get_loss(g, emb, t["samples"], t["labels"])[0]
+            loss.backward()
+            bk.finish()
+            bk.clip_(1.0)
+            opt.step()
+            losses.append(float(loss))
+        return m, losses
+
+    def captured_run():
+        m = copy.deepcopy(base).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+        torch.manual_seed(100)
+        cap = K.link_predict.CapturedTrainStep(m, opt, inputs[0], n, grad_norm=1.0, warmup=1)   # warm-up = step 0
+        assert cap.launches_per_step > 10
+        losses = []
+        for i in (1, 2):
+            torch.manual_seed(100 + i)
+            losses.append(float(cap.step(**inputs[i])))
+        return m, losses
+
+    m_e, l_e = eager_run()
+    m_c, l_c = captured_run()
+    assert np.allclose(l_e[1:], l_c, rtol=1e-5), (l_e, l_c)
+    for (name, p), q in zip(m_e.named_parameters(), m_c.parameters()):
+        # Adam normalises the update: an element whose gradient is fp32 reduction noise moves by up to lr either way
+        err = float((p - q).abs().max() / p.abs().max().clamp(min=1e-12))
+        assert err < 1e-3, (name, err)
+
+
+def test_captured_train_step_needs_a_capturable_optimizer():
+    dev = torch.device("cuda:0")
+    m = K.LinkPredict(K.KGVAE, 300, 40, 6, num_bases=8, use_cuda=True, k=2).to(dev)
+    with pytest.raises(RuntimeError, match="capturable"):
+        K.link_predict.CapturedTrainStep(m, torch.optim.Adam(m.parameters(), fused=True), _toy_step_inputs(dev), 300)
