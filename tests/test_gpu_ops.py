@@ -148,6 +148,41 @@ def test_gemm_tensor_core_path(M, N, K, ta, tb):
     assert err2 < 2e-6, err2
 
 
+def test_gemm_prepared_operands_serve_all_three_layer_products():
+    """kg_gemm_prepare / kg_gemm_f32_prepared: x, W and g are split once and reused, in both orientations, by the
+    three products of a linear layer (kgvae/flow_network.py:15 and its backward): y = x W^T, dx = g W, dW = g^T x.
+    Row slices (ld > cols) and a ragged K (not a multiple of 64) included; bitwise equal to the unprepared call."""
+    g = torch.Generator().manual_seed(11)
+    n, din, dout = 3001, 500, 1000
+    xw = torch.randn(n, din + 12, generator=g).to(DEV)
+    x = xw[:, :din]                                           # row pitch 512, 500 columns
+    W = (torch.randn(dout, din, generator=g) * 0.05).to(DEV)
+    gr = (torch.randn(n, dout, generator=g) * 1e-4).to(DEV)   # gradients are small: the scale is per matrix
+    xp = ops.Prepared(x) if x.is_contiguous() else ops.Prepared(x.contiguous())
+    Wp, gp = ops.Prepared(W), ops.Prepared(gr)
+    xc = x.contiguous()
+    y, dx, dW = (torch.empty(n, dout, device=DEV), torch.empty(n, din, device=DEV), torch.empty(dout, din, device=DEV))
+    ops.gemm(xp, Wp, y, trans_b=True)
+    ops.gemm(gp, Wp, dx)
+    ops.gemm(gp, xp, dW, trans_a=True)
+    x64, W64, g64 = xc.double().cpu(), W.double().cpu(), gr.double().cpu()
+    for got, want, what in ((y, x64 @ W64.t(), "y"), (dx, g64 @ W64, "dx"), (dW, g64.t() @ x64, "dW")):
+        assert_close(got, want, 3e-6, f"prepared {what}")
+    y2, dW2 = torch.empty_like(y), torch.empty_like(dW)
+    ops.gemm(xc, W, y2, trans_b=True)
+    ops.gemm(gr, xc, dW2, trans_a=True)
+    assert torch.equal(y, y2) and torch.equal(dW, dW2)
+    # a strided source is split straight from its rows (no copy): same bits as the contiguous copy
+    n_bytes = L.lib().kg_gemm_prep_bytes(n, din)
+    b1, b2 = torch.zeros(n_bytes, dtype=torch.uint8, device=DEV), torch.zeros(n_bytes, dtype=torch.uint8, device=DEV)
+    L.call("kg_gemm_prepare", x.data_ptr(), x.stride(0), n, din, L.ptr(b1), n_bytes, L.stream())
+    L.call("kg_gemm_prepare", L.f32(xc), din, n, din, L.ptr(b2), n_bytes, L.stream())
+    assert torch.equal(b1, b2)
+    with pytest.raises(RuntimeError, match="below the tensor-core size"):
+        L.call("kg_gemm_f32_prepared", L.ptr(b1), 0, L.ptr(b2), 1, L.f32(y), dout, 8, 8, 8, None, None, 0, None, 0,
+               None, 0, L.stream())
+
+
 def test_colsum_and_reductions():
     g = torch.Generator().manual_seed(1)
     for rows, cols in [(1, 1), (300, 37), (14541, 100), (0, 5)]:
