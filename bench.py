@@ -692,11 +692,27 @@ def run_entity(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    # Every timed section starts from the SAME model / optimizer state (in-place restore: the captured step keeps its
+    # addresses).  With IAF flows the reference's loss is unbounded below (the flows' mean log-determinant is added
+    # to every score, kgvae/link_predict.py:75-76) and a few dozen consecutive steps on one batch overflow.
+    def snapshot():
+        return ([p.detach().clone() for p in model.parameters()],
+                [{k: v.clone() for k, v in opt.state[p].items() if torch.is_tensor(v)} for p in model.parameters() if p in opt.state])
+
+    def restore(snap):
+        with torch.no_grad():
+            for p, v in zip(model.parameters(), snap[0]):
+                p.copy_(v)
+            for p, st in zip([p for p in model.parameters() if p in opt.state], snap[1]):
+                for k, v in st.items():
+                    opt.state[p][k].copy_(v)
+
     model.train()
     clocks.mark()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sync_all()
+    snap = snapshot()
     L.launches = 0
     L.profile = {}
     ms_dev = max_over_ranks(timed(lambda: step(resident), args.steps))
@@ -960,8 +976,10 @@ def run_gpu(args):
     ms_eager_prof = max_over_ranks(timed(lambda: step(resident), args.steps))
     launches = L.launches
     prof, L.profile = L.profile, None
+    restore(snap)
     ms_eager = max_over_ranks(timed(lambda: step(resident), args.steps))
     sync_all()
+    restore(snap)
     captured = None
     if not args.eager:
         # the step's shapes are fixed (one sampled batch / the full graph): capture it once, replay it
@@ -970,6 +988,7 @@ def run_gpu(args):
                          "etype": resident["etype"], "norm": resident["norm"], "samples": resident["samples"],
                          "labels": resident["labels"]}, N, buckets=buckets, grad_norm=1.0, warmup=max(args.warmup, 3))
         sync_all()
+        restore(snap)
         launches = captured.launches_per_step * args.steps
         ms_dev = max_over_ranks(timed(lambda: captured.step(), args.steps))
 
@@ -979,10 +998,12 @@ def run_gpu(args):
     else:
         ms_dev = ms_eager
     sync_all()
+    restore(snap)
     for _ in range(2):
         e2e_step()
     timed_e2e(2)
     sync_all()
+    restore(snap)
     ms_e2e = max_over_ranks(timed_e2e(args.steps))
     sync_all()
     log("  e2e losses read back: " + " ".join(f"{v:.4f}" for v in e2e_losses))
@@ -990,6 +1011,7 @@ def run_gpu(args):
         captured.close()        # a CUDA graph that holds NCCL kernels must be gone before its communicator is
         sync_all()
     # end to end INCLUDING the sampler (fresh sample every step), three ways
+    restore(snap)
     timed_with_device_sampler(2)
     sync_all()
     ms_dev_sampler = max_over_ranks(timed_with_device_sampler(args.steps)) / args.steps
