@@ -692,27 +692,11 @@ def run_entity(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    # Every timed section starts from the SAME model / optimizer state (in-place restore: the captured step keeps its
-    # addresses).  With IAF flows the reference's loss is unbounded below (the flows' mean log-determinant is added
-    # to every score, kgvae/link_predict.py:75-76) and a few dozen consecutive steps on one batch overflow.
-    def snapshot():
-        return ([p.detach().clone() for p in model.parameters()],
-                [{k: v.clone() for k, v in opt.state[p].items() if torch.is_tensor(v)} for p in model.parameters() if p in opt.state])
-
-    def restore(snap):
-        with torch.no_grad():
-            for p, v in zip(model.parameters(), snap[0]):
-                p.copy_(v)
-            for p, st in zip([p for p in model.parameters() if p in opt.state], snap[1]):
-                for k, v in st.items():
-                    opt.state[p][k].copy_(v)
-
     model.train()
     clocks.mark()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sync_all()
-    snap = snapshot()
     L.launches = 0
     L.profile = {}
     ms_dev = max_over_ranks(timed(lambda: step(resident), args.steps))
@@ -965,11 +949,27 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    # Every timed section starts from the SAME model / optimizer state (in-place restore: the captured step keeps its
+    # addresses).  With IAF flows the reference's loss is unbounded below (the flows' mean log-determinant is added
+    # to every score, kgvae/link_predict.py:75-76) and a few dozen consecutive steps on one batch overflow.
+    def snapshot():
+        return ([p.detach().clone() for p in model.parameters()],
+                [{k: v.clone() for k, v in opt.state[p].items() if torch.is_tensor(v)} for p in model.parameters() if p in opt.state])
+
+    def restore(snap):
+        with torch.no_grad():
+            for p, v in zip(model.parameters(), snap[0]):
+                p.copy_(v)
+            for p, st in zip([p for p in model.parameters() if p in opt.state], snap[1]):
+                for k, v in st.items():
+                    opt.state[p][k].copy_(v)
+
     model.train()
     clocks.mark()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sync_all()
+    snap = snapshot()
     # per-op CUDA-event times of the EAGER step (the op list under `roofline`, and the eager step time itself)
     L.launches = 0
     L.profile = {}

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, port, n_flows, mode, mmd, out):
+def _worker(rank, port, n_flows, mode, mmd, chunks, out):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import gcn_vae_b200 as K
@@ -30,22 +30,23 @@ def _worker(rank, port, n_flows, mode, mmd, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=dev)
     try:
-        out[rank] = partition_selfcheck.run(K, dev, rank, WORLD, n_flows, mode, None, mmd)     # asserts the parity bars
+        out[rank] = partition_selfcheck.run(K, dev, rank, WORLD, n_flows, mode, None, mmd, chunks)     # asserts the parity bars
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_flows,mode,mmd", [(0, "allgather", 0.0), (1, "allgather", 0.0), (0, "peer", 0.0), (1, "peer", 0.0),
-                                              (1, "allgather", 1.0)])
-def test_partitioned_step_matches_single_gpu(n_flows, mode, mmd):
-    """mode "allgather": NCCL all-gather of every layer input; mode "peer": the message-passing kernels
-    gather source rows from the owners' HBM over NVLink (CUDA IPC row blocks), reduce-scatter backward."""
+@pytest.mark.parametrize("n_flows,mode,mmd,chunks", [(0, "allgather", 0.0, None), (1, "allgather", 0.0, None), (0, "peer", 0.0, None),
+                                                     (1, "peer", 0.0, None), (1, "allgather", 1.0, None), (0, "allgather", 0.0, 2)])
+def test_partitioned_step_matches_single_gpu(n_flows, mode, mmd, chunks):
+    """mode "allgather": NCCL all-gather of every layer input (``chunks`` = 2: in two column chunks pipelined with
+    message passing, the form used from 4 ranks up); mode "peer": the message-passing kernels gather source rows
+    from the owners' HBM over NVLink (CUDA IPC row blocks), reduce-scatter backward."""
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 GPUs")
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(port, n_flows, mode, mmd, out), nprocs=WORLD, join=True)
+        mp.spawn(_worker, args=(port, n_flows, mode, mmd, chunks, out), nprocs=WORLD, join=True)
         res = [out[r] for r in range(WORLD)]
     for r in range(WORLD):
         assert res[r]["loss"] <= 1e-4 and res[r]["z"] <= 1e-4 and max(res[r]["grads"].values()) <= (2e-4 if mmd == 0 else 1e-3)

@@ -8,7 +8,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-VARIANTS = [(0, "allgather", 0.0), (1, "allgather", 0.0), (0, "peer", 0.0), (1, "peer", 0.0), (1, "allgather", 1.0)]
+# (n_flows, mode, mmd_param, column chunks of the layer-input gathers; None = the Partition's own choice: 2 from 4 ranks up)
+VARIANTS = [(0, "allgather", 0.0, None), (1, "allgather", 0.0, None), (0, "peer", 0.0, None), (1, "peer", 0.0, None),
+            (1, "allgather", 1.0, None), (0, "allgather", 0.0, 2)]
 
 
 def setup(K, dev, n_flows, mmd_param=0.0):
@@ -27,7 +29,7 @@ def setup(K, dev, n_flows, mmd_param=0.0):
     return model, g, etype, node_norm, trip, labels, eps, m1, m2, n_ent
 
 
-def run(K, dev, rank, world, n_flows, mode, group=None, mmd_param=0.0):
+def run(K, dev, rank, world, n_flows, mode, group=None, mmd_param=0.0, col_chunks=None):
     """Returns {"loss", "z", "grads": {name: rel err}} of this rank; raises AssertionError beyond 1e-4 / 2e-4.
     ``mmd_param`` > 0 adds the MMD term of the README configuration (kgvae/model.py:89-102): python's ``random``
     and the device generator are re-seeded before each of the two steps so that both draw the same 200 rows
@@ -60,7 +62,7 @@ def run(K, dev, rank, world, n_flows, mode, group=None, mmd_param=0.0):
     pg = K.Graph()
     pg.add_nodes(N)
     pg.add_edges(mine["src"], mine["dst"] - lo)
-    pg.partition = parallel.Partition(lo, hi, N, group=group, peer_gather=peer)
+    pg.partition = parallel.Partition(lo, hi, N, group=group, peer_gather=peer, col_chunks=col_chunks)
     assert pg.partition.use_peer_gather(len(mine["src"])) == peer
     random.seed(7)
     torch.manual_seed(123)
@@ -138,10 +140,10 @@ def run_entity(K, dev, rank, world, group=None):
 
 
 def run_all(K, dev, rank, world, group=None):
-    """All four variants; returns a one-line summary (raises on the first mismatch)."""
+    """All variants; returns a one-line summary (raises on the first mismatch)."""
     worst = 0.0
-    for n_flows, mode, mmd in VARIANTS:
-        r = run(K, dev, rank, world, n_flows, mode, group, mmd)
+    for n_flows, mode, mmd, chunks in VARIANTS:
+        r = run(K, dev, rank, world, n_flows, mode, group, mmd, chunks)
         worst = max(worst, r["loss"], r["z"], *r["grads"].values())
     e = run_entity(K, dev, rank, world, group)
     worst = max(worst, e["loss"], e["logits"], *e["grads"].values())
