@@ -98,6 +98,73 @@ epilogue_only_vec4_kernel(Epilogue ep) {
   }
 }
 
+// M <= 8 (the first pass of every MADE call multiplies ONE row by the masked weights, flow_network.py:91; its
+// input-gradient product has the same shape): a 128 x 128 tile kernel would run one nearly empty CTA row through
+// K sequential steps.  B k-contiguous: a warp per output column, lanes striding k (coalesced rows of B);
+// otherwise a lane per output column (coalesced across n) with the CTA's eight warps splitting K.
+constexpr int kSmallM = 8;
+
+__device__ __forceinline__ void small_m_store(const Epilogue& ep, int m, int n, float v) {
+  const size_t off = (size_t)m * ep.ldc + n;
+  if (ep.bias) v += __ldg(ep.bias + n);
+  if (ep.addend) v += __ldg(ep.addend + off);
+  if (ep.relu) v = fmaxf(v, 0.f);
+  if (ep.mask) v *= __ldg(ep.mask + off);
+  if (ep.accumulate) v += ep.C[off];
+  ep.C[off] = v;
+}
+
+template <bool B_KC>
+__global__ void __launch_bounds__(256)
+gemm_small_m_kernel(const float* __restrict__ A, int lda, int trans_a, const float* __restrict__ B, int ldb, int K,
+                    Epilogue ep) {
+  __shared__ float red[8][kSmallM][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, M = ep.M, N = ep.N;
+  float acc[kSmallM];
+#pragma unroll
+  for (int m = 0; m < kSmallM; ++m) acc[m] = 0.f;
+  auto a_at = [&](int m, int k) { return trans_a ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k); };
+  if (B_KC) {
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    const float* b = B + (size_t)n * ldb;
+    for (int k = lane; k < K; k += 32) {
+      const float bv = __ldg(b + k);
+#pragma unroll
+      for (int m = 0; m < kSmallM; ++m)
+        if (m < M) acc[m] = fmaf(a_at(m, k), bv, acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < kSmallM; ++m) {
+      const float v = kg_warp_sum(acc[m]);
+      if (m < M && lane == 0) small_m_store(ep, m, n, v);
+    }
+  } else {
+    const int n = blockIdx.x * 32 + lane;
+    const int kc = (K + 7) / 8, k0 = warp * kc, k1 = min(K, k0 + kc);
+    if (n < N)
+      for (int k = k0; k < k1; ++k) {
+        const float bv = __ldg(B + (size_t)k * ldb + n);
+#pragma unroll
+        for (int m = 0; m < kSmallM; ++m)
+          if (m < M) acc[m] = fmaf(a_at(m, k), bv, acc[m]);
+      }
+#pragma unroll
+    for (int m = 0; m < kSmallM; ++m) red[warp][m][lane] = acc[m];
+    __syncthreads();
+    if (warp == 0 && n < N) {
+#pragma unroll
+      for (int m = 0; m < kSmallM; ++m)
+        if (m < M) {
+          float v = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) v += red[w8][m][lane];
+          small_m_store(ep, m, n, v);
+        }
+    }
+  }
+}
+
 template <bool A_KC, bool B_KC>
 static int launch(const float* A, int lda, const float* B, int ldb, int M, int N, int K, int splits,
                   int k_chunk, Epilogue ep, cudaStream_t st) {
@@ -152,6 +219,14 @@ extern "C" int kg_gemm_f32(const float* A, int lda, int trans_a, const float* B,
   if (kg_gemm_tc_eligible(M, N, K))
     return kg_gemm_tc_run(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, addend, relu, mask,
                           accumulate, workspace, workspace_bytes, st);
+
+  if (M <= kSmallM && K >= 32) {
+    Epilogue ep{C, ldc, M, N, bias, addend, mask, relu, accumulate, 0};
+    if (trans_b) gemm_small_m_kernel<true><<<kg_div_up(N, 8), 256, 0, st>>>(A, lda, trans_a, B, ldb, K, ep);
+    else gemm_small_m_kernel<false><<<kg_div_up(N, 32), 256, 0, st>>>(A, lda, trans_a, B, ldb, K, ep);
+    KG_LAUNCH_OK();
+    return KG_OK;
+  }
 
   // split-K only for plain / masked products whose output tiling cannot fill the machine
   int splits = 1;

@@ -193,32 +193,37 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
   const float c_add = coefs ? __ldg(coefs + 1) : 0.f, c_z = coefs ? __ldg(coefs + 2) : 0.f;
   if (coefs) scale *= __ldg(coefs);
   const int r0 = blockIdx.x * kKlRows, r1 = min(n, r0 + kKlRows);
-  float pm[KM], ipv[KM], gpm[KM], gpv[KM];
+  // per mixture component i and column d, summed over the CTA's rows with r = resp[row, i], u = z - m_i:
+  //   gpm = -sum r u / v_i          (gradient wrt the component mean)
+  //   gpv = -sum r (u^2 / (2 v_i^2) - 1 / (2 v_i)) = -acc / (2 v_i)   with acc = sum ((r u / v_i) u - r)
+  // so the inner loop is eight instructions per (row, component): load r, u, w = u / v_i, q = r w, and the sums.
+  float pm[KM], ipv[KM], gpm[KM], acc[KM];
 #pragma unroll
   for (int i = 0; i < KM; ++i) {
     pm[i] = i < k ? z_pre[(size_t)i * h + d] : 0.f;
     ipv[i] = i < k ? 1.f / ws[(size_t)i * h + d] : 0.f;
     gpm[i] = 0.f;
-    gpv[i] = 0.f;
+    acc[i] = 0.f;
   }
 #pragma unroll 4
   for (int row = r0; row < r1; ++row) {
     const size_t off = (size_t)row * h + d;
     const float zc = z[off], v = zv[off];
     const float t = zc - zm[off];
-    const float iv = 1.f / v;
-    float gz = -t * iv;                      // d/dz log N(z; m, v)
-    dmean[off] = scale * t * iv;
-    dvar[off] = scale * (0.5f * t * t * iv * iv - 0.5f * iv);
+    const float iv = __frcp_rn(v);
+    const float tiv = t * iv;
+    float gz = -tiv;                         // d/dz log N(z; m, v)
+    dmean[off] = scale * tiv;
+    dvar[off] = scale * 0.5f * iv * (t * tiv - 1.f);
 #pragma unroll
     for (int i = 0; i < KM; ++i)
       if (i < k) {
         const float ri = __ldg(resp + (size_t)row * k + i);
         const float u = zc - pm[i];
-        const float q = ri * u * ipv[i];     // resp_i * (z - m_i)/v_i
+        const float q = ri * (u * ipv[i]);   // resp_i * (z - m_i)/v_i
         gz += q;                             // d/dz of -log MoG
         gpm[i] -= q;
-        gpv[i] -= ri * (0.5f * u * u * ipv[i] * ipv[i] - 0.5f * ipv[i]);
+        acc[i] += fmaf(q, u, -ri);
       }
     float out = scale * gz;
     if (coefs) out += c_z * zc + (add ? c_add * add[off] : 0.f);
@@ -229,7 +234,7 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
     if (i < k) {
       atomicAdd(dz_pre + (size_t)i * h + d, scale * gpm[i]);
       atomicAdd(dz_pre + (size_t)(k + i) * h + d,
-                scale * gpv[i] * kg_sigmoid(z_pre[(size_t)(k + i) * h + d]));
+                scale * (-0.5f * ipv[i] * acc[i]) * kg_sigmoid(z_pre[(size_t)(k + i) * h + d]));
     }
 }
 

@@ -70,7 +70,8 @@ def test_graph_build_matches_reference_order(n, t, r):
 
 
 # ------------------------------------------------------------------------------ gemm
-@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (130, 70, 33), (257, 500, 500), (64, 1000, 20), (500, 100, 3000)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (130, 70, 33), (257, 500, 500), (64, 1000, 20), (500, 100, 3000),
+                                   (1, 500, 500), (3, 77, 1000), (8, 1000, 45)])        # last three: the M <= 8 kernel
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_layouts(M, N, K, ta, tb):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
@@ -96,6 +97,15 @@ def test_gemm_epilogue_and_accumulate():
     out2 = base.to(DEV).clone()
     ops.gemm(a.to(DEV), b.to(DEV), out2, accumulate=True)
     assert_close(out2, base + a @ b, 2e-5, "accumulate")
+    # the M <= 8 kernel (first pass of a MADE call: one row, bias + ReLU in the epilogue; flow_network.py:91)
+    for tb in (False, True):
+        a1, b1 = torch.randn(2, 300, generator=g), torch.randn((N, 300) if tb else (300, N), generator=g)
+        add1, mask1 = torch.randn(2, N, generator=g), (torch.rand(2, N, generator=g) < 0.8).float() / 0.8
+        base1 = torch.randn(2, N, generator=g)
+        out5 = base1.to(DEV).clone()
+        ops.gemm(a1.to(DEV), b1.to(DEV), out5, trans_b=tb, bias=bias.to(DEV), addend=add1.to(DEV), relu=True,
+                 mask=mask1.to(DEV), accumulate=True)
+        assert_close(out5, base1 + torch.relu(a1 @ (b1.t() if tb else b1) + bias + add1) * mask1, 2e-5, "small-M epilogue")
     # K = 0: epilogue only
     out3 = torch.empty(M, N, device=DEV)
     ops.epilogue_only(out3, bias=bias.to(DEV), addend=add.to(DEV))
