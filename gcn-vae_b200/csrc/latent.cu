@@ -179,7 +179,7 @@ kl_mog_fwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
 static constexpr int kKlRows = 32;   // rows per CTA in the backward kernel
 
 template <int KM>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 6)
 kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
                   const float* __restrict__ zv, const float* __restrict__ z_pre,
                   const float* __restrict__ ws, const float* __restrict__ resp, float scale, int n,
@@ -205,7 +205,7 @@ kl_mog_bwd_kernel(const float* __restrict__ z, const float* __restrict__ zm,
     gpm[i] = 0.f;
     acc[i] = 0.f;
   }
-#pragma unroll 4
+#pragma unroll 2
   for (int row = r0; row < r1; ++row) {
     const size_t off = (size_t)row * h + d;
     const float zc = z[off], v = zv[off];
