@@ -1015,6 +1015,40 @@ def run_gpu(args):
     timed_with_device_sampler(2)
     sync_all()
     ms_dev_sampler = max_over_ranks(timed_with_device_sampler(args.steps)) / args.steps
+    # the same loop as ONE replay per step: the full-batch device sampler captured together with the train step
+    ms_dev_sampler_captured = None
+    if not args.eager and batch == len(data.train):
+        restore(snap)
+        torch.manual_seed(1000 + rank)
+        sampler = K.utils.FullBatchDeviceSampler(train_dev, data.num_rels, NEG, split_size=0.5)
+        cap2 = K.link_predict.CapturedTrainStep(model, opt, None, sampler.n, buckets=buckets, grad_norm=1.0, warmup=3,
+                                                sampler=sampler)
+        sync_all()
+
+        def timed_captured_sampler(n_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            got = []
+            for i in range(n_steps):
+                loss_host[i & 1].copy_(cap2.step().reshape(1), non_blocking=True)
+                loss_done[i & 1].record()
+                if i > 0:
+                    loss_done[(i - 1) & 1].synchronize()
+                    got.append(float(loss_host[(i - 1) & 1]))
+            loss_done[(n_steps - 1) & 1].synchronize()
+            got.append(float(loss_host[(n_steps - 1) & 1]))
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b), got
+
+        timed_captured_sampler(2)
+        sync_all()
+        ms_c, sampler_losses = timed_captured_sampler(args.steps)
+        ms_dev_sampler_captured = max_over_ranks(ms_c) / args.steps
+        log(f"  sampler + step as one replay: {ms_dev_sampler_captured:.3f} ms/step; losses " +
+            " ".join(f"{v:.4f}" for v in sampler_losses))
+        cap2.close()
+        sync_all()
     n_host = 3
     ms_host_sampler = max_over_ranks(timed_with_host_sampler(n_host, threaded=False)) / n_host
     ms_host_threaded = max_over_ranks(timed_with_host_sampler(n_host, threaded=True)) / n_host
@@ -1248,6 +1282,12 @@ def run_gpu(args):
                     "what": "kgvae/link_predict.py:200-236 with a FRESH sample every step: sampler + copies + edge "
                             "index + step + loss read-back; ms per step, max over ranks",
                     "device_sampler_ms": ms_dev_sampler, "device_sampler_edges_per_s": E * world / (ms_dev_sampler * 1e-3),
+                    "device_sampler_captured_ms": ms_dev_sampler_captured,
+                    "device_sampler_captured_edges_per_s": (E * world / (ms_dev_sampler_captured * 1e-3)
+                                                            if ms_dev_sampler_captured else None),
+                    "device_sampler_captured_what": "utils.FullBatchDeviceSampler drawn INSIDE the captured step "
+                                                    "(link_predict.CapturedTrainStep(sampler=...)): one CUDA-graph "
+                                                    "replay per training iteration, loss read back every step",
                     "host_sampler_ms": ms_host_sampler, "host_sampler_edges_per_s": E * world / (ms_host_sampler * 1e-3),
                     "host_sampler_threaded_ms": ms_host_threaded,
                     "note": "the host sampler is the reference's numpy code (bit-exact sampled indices), single "

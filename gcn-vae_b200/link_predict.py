@@ -155,22 +155,28 @@ class CapturedTrainStep:
     ``capturable`` (``torch.optim.Adam(..., fused=True, capturable=True)``).  The ``warmup`` eager steps that
     precede the capture ARE train steps on ``example``.  ``step(**tensors)`` copies new inputs of the same shapes
     into place (device-to-device or from pinned host memory, stream-ordered), replays, and returns the loss
-    tensor (device; read it with ``float()`` when needed)."""
+    tensor (device; read it with ``float()`` when needed).
+
+    ``sampler``: an object whose ``sample()`` returns that dict with fixed shapes using only stream-ordered device
+    work (``utils.FullBatchDeviceSampler``): the draw is then captured too and ``step()`` - no arguments - is the
+    whole iteration of the reference's loop (kgvae/link_predict.py:200-236): fresh negatives, fresh graph split,
+    edge index, forward, loss, backward, clip, Adam, in one replay (``example`` may be ``None``)."""
 
     FIELDS = ("node_id", "src", "dst", "etype", "norm", "samples", "labels")
 
-    def __init__(self, model, optimizer, example, num_nodes, buckets=None, grad_norm=1.0, warmup=3):
+    def __init__(self, model, optimizer, example, num_nodes, buckets=None, grad_norm=1.0, warmup=3, sampler=None):
         from . import _lib
         from .graph import Graph
         if not all(g.get("capturable", False) for g in optimizer.param_groups):
             raise RuntimeError("CapturedTrainStep: the optimizer must be constructed with capturable=True")
-        dev = example["src"].device
+        dev = example["src"].device if example is not None else next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("kgvae_b200: CapturedTrainStep needs CUDA tensors (no CPU fallback)")
         self._Graph = Graph
         self.model, self.optimizer, self.num_nodes, self.grad_norm = model, optimizer, int(num_nodes), grad_norm
         self.buckets = buckets if buckets is not None else model.grad_buckets()
-        self.inputs = {k: example[k].clone() for k in self.FIELDS}
+        self.sampler = sampler
+        self.inputs = None if sampler is not None else {k: example[k].clone() for k in self.FIELDS}
         self.predict_loss = self.kl = self.mmd = None
         # Warm-up and capture run on ONE side stream, and no autograd graph of an earlier step may be alive: a
         # parameter's gradient-accumulation node runs on the stream it was created on, and one left over from an
@@ -195,7 +201,7 @@ class CapturedTrainStep:
         self.launches_per_step = _lib.launches - before      # kernels of this library inside one replay
 
     def _eager(self):
-        t = self.inputs
+        t = self.inputs if self.sampler is None else self.sampler.sample()
         g = self._Graph.from_device_edges(self.num_nodes, t["src"], t["dst"])
         self.buckets.zero()
         embed = self.model(g, t["node_id"], t["etype"], t["norm"])
@@ -216,6 +222,8 @@ class CapturedTrainStep:
             self.graph = None
 
     def load(self, **tensors):
+        if self.inputs is None:
+            raise RuntimeError("CapturedTrainStep: this step draws its own inputs (sampler=...)")
         for k, v in tensors.items():
             self.inputs[k].copy_(v.view_as(self.inputs[k]), non_blocking=True)
 

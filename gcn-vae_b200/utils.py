@@ -178,6 +178,52 @@ def generate_sampled_graph_and_labels_device(triplets, sample_size, split_size, 
     return g, uniq_v.view(-1, 1), edge_type, edge_norm, samples, labels
 
 
+class FullBatchDeviceSampler:
+    """``generate_sampled_graph_and_labels_device`` for the case ``sample_size == len(triplets)`` (full-graph
+    training: every step scores ALL training triples with fresh negatives and builds the graph from a fresh random
+    ``split_size`` of them, kgvae/utils.py:79-124,158-171).  The sampled edge set is then always the whole training
+    set, so the node relabelling is fixed and is computed once; a call to ``sample()`` draws the negatives and the
+    graph split and returns tensors of FIXED shapes - ``node_id [n, 1]``, ``src`` / ``dst`` / ``etype [E]`` (int32,
+    both directions), ``norm [E, 1]`` (1 / in-degree), ``samples [S, 3]`` (int32), ``labels [S]`` - with no host
+    read-back, using only stream-ordered tensor ops: it can run inside a CUDA-graph capture
+    (``link_predict.CapturedTrainStep(..., sampler=...)``), which makes a training step - sampler included - one
+    replay.  Same procedure as the host sampler, not numpy's random stream."""
+
+    def __init__(self, triplets, num_rels, negative_rate, split_size=0.5):
+        if not triplets.is_cuda:
+            raise RuntimeError("FullBatchDeviceSampler needs the triples on a CUDA device (no CPU fallback)")
+        tri = triplets.long()
+        B = tri.shape[0]
+        uniq_v, inv = torch.unique(torch.cat([tri[:, 0], tri[:, 2]]), return_inverse=True)
+        self.n = int(uniq_v.numel())                                  # the only host read-back, once
+        self.num_rels, self.rate, self.B = int(num_rels), int(negative_rate), B
+        self.keep_n = int(B * split_size)
+        self.node_id = uniq_v.view(-1, 1)
+        self.src, self.rel, self.dst = inv[:B].contiguous(), tri[:, 1].contiguous(), inv[B:].contiguous()
+        self.pos = torch.stack([self.src, self.rel, self.dst], dim=1).to(torch.int32)
+        self.neg_s, self.neg_r, self.neg_o = (t.repeat(self.rate) for t in (self.src, self.rel, self.dst))
+        self.labels = torch.zeros(B * (self.rate + 1), dtype=torch.float32, device=tri.device)
+        self.labels[:B] = 1
+        self.n_edges, self.n_samples = 2 * self.keep_n, B * (self.rate + 1)
+
+    def sample(self):
+        dev = self.src.device
+        m = self.B * self.rate
+        values = torch.randint(self.n, (m,), device=dev)
+        head = torch.rand(m, device=dev) > 0.5
+        neg = torch.stack([torch.where(head, values, self.neg_s), self.neg_r, torch.where(head, self.neg_o, values)], dim=1)
+        samples = torch.cat([self.pos, neg.to(torch.int32)])
+        keep = torch.argsort(torch.rand(self.B, device=dev))[:self.keep_n]       # a uniform random subset
+        s, r, d = self.src[keep], self.rel[keep], self.dst[keep]
+        src2, dst2 = torch.cat([s, d]), torch.cat([d, s])
+        etype = torch.cat([r, r + self.num_rels]).to(torch.int32)
+        deg = torch.zeros(self.n, dtype=torch.float32, device=dev).index_add_(
+            0, dst2, torch.ones(dst2.shape[0], dtype=torch.float32, device=dev))
+        norm = (1.0 / deg.clamp_(min=1.0))[dst2].view(-1, 1)
+        return {"node_id": self.node_id, "src": src2.to(torch.int32), "dst": dst2.to(torch.int32), "etype": etype,
+                "norm": norm, "samples": samples, "labels": self.labels}
+
+
 # --------------------------------------------------------------------------------------------
 # evaluation (kgvae/utils.py:180-221,293-314)
 # --------------------------------------------------------------------------------------------

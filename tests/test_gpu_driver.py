@@ -166,3 +166,61 @@ def test_captured_train_step_needs_a_capturable_optimizer():
     m = K.LinkPredict(K.KGVAE, 300, 40, 6, num_bases=8, use_cuda=True, k=2).to(dev)
     with pytest.raises(RuntimeError, match="capturable"):
         K.link_predict.CapturedTrainStep(m, torch.optim.Adam(m.parameters(), fused=True), _toy_step_inputs(dev), 300)
+
+
+def test_full_batch_device_sampler_follows_the_reference_procedure():
+    """utils.FullBatchDeviceSampler (kgvae/utils.py:79-124,158-171 with sample_size = all training triples): positives
+    kept, every negative differs from its positive in exactly the subject OR the object (about half each, replacement
+    among the sampled nodes), labels 1 / 0, the graph is a random ``split_size`` of the positives in both directions with
+    reverse relation ids and 1 / in-degree norms; two draws differ."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    n_ent, n_rel, T, rate = 500, 7, 4000, 5
+    train = np.stack([rng.integers(0, n_ent, T), rng.integers(0, n_rel, T), rng.integers(0, n_ent, T)], 1)
+    sm = K.utils.FullBatchDeviceSampler(torch.from_numpy(train).to(dev), n_rel, rate, split_size=0.5)
+    torch.manual_seed(0)
+    a, b = sm.sample(), sm.sample()
+    uniq = np.unique(np.concatenate([train[:, 0], train[:, 2]]))
+    assert np.array_equal(a["node_id"].cpu().numpy().reshape(-1), uniq) and sm.n == len(uniq)
+    relabel = {v: i for i, v in enumerate(uniq)}
+    pos = np.array([[relabel[s], r, relabel[o]] for s, r, o in train])
+    smp = a["samples"].cpu().numpy()
+    assert smp.shape == (T * (rate + 1), 3) and np.array_equal(smp[:T], pos)
+    neg = smp[T:].reshape(rate, T, 3)
+    same_s, same_o = neg[:, :, 0] == pos[None, :, 0], neg[:, :, 2] == pos[None, :, 2]
+    assert np.array_equal(neg[:, :, 1], np.broadcast_to(pos[None, :, 1], (rate, T)))
+    assert (same_s | same_o).all()                         # at most one end is replaced
+    frac_head = float((~same_s).mean())
+    assert 0.45 < frac_head < 0.55 and 0 <= smp.min() and smp[:, [0, 2]].max() < sm.n
+    lab = a["labels"].cpu().numpy()
+    assert lab[:T].min() == 1 and lab[T:].max() == 0
+    src, dst, et = (a[k].cpu().numpy() for k in ("src", "dst", "etype"))
+    E = len(src) // 2
+    assert E == T // 2 and np.array_equal(src[:E], dst[E:]) and np.array_equal(dst[:E], src[E:])
+    assert np.array_equal(et[E:], et[:E] + n_rel) and et[:E].max() < n_rel
+    pos_set = {tuple(p) for p in pos}
+    assert all((s, r, o) in pos_set for s, r, o in zip(src[:E], et[:E], dst[:E]))
+    deg = np.bincount(dst, minlength=sm.n)
+    assert np.allclose(a["norm"].cpu().numpy().reshape(-1), 1.0 / deg[dst])
+    assert not np.array_equal(smp[T:], b["samples"].cpu().numpy()[T:]) and not np.array_equal(src, b["src"].cpu().numpy())
+
+
+def test_captured_step_with_its_own_sampler_trains():
+    """CapturedTrainStep(sampler=...): the whole loop iteration of kgvae/link_predict.py:200-236 - fresh negatives and
+    graph split, edge index, forward, loss, backward, clip, Adam - is one replay; the loss goes down over replays and
+    successive replays see different samples (the loss sequence is not constant)."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    n_ent, n_rel, T = 300, 6, 3000
+    train = np.stack([rng.integers(0, n_ent, T), rng.integers(0, n_rel, T), rng.integers(0, n_ent, T)], 1)
+    sm = K.utils.FullBatchDeviceSampler(torch.from_numpy(train).to(dev), n_rel, 4)
+    torch.manual_seed(0)
+    m = K.LinkPredict(K.KGVAE, sm.n, 40, n_rel, num_bases=8, dropout=0.2, use_cuda=True, reg_param=0.01,
+                      kl_param=1e-3, k=4, n_flows=0).to(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=True, capturable=True)
+    cap = K.link_predict.CapturedTrainStep(m, opt, None, sm.n, warmup=2, sampler=sm)
+    losses = [float(cap.step()) for _ in range(40)]
+    assert all(np.isfinite(losses)) and len(set(losses)) > 30
+    assert np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5])
+    with pytest.raises(RuntimeError, match="draws its own inputs"):
+        cap.step(labels=torch.zeros(1, device=dev))

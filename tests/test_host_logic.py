@@ -192,3 +192,40 @@ def test_block_chunks_for_the_column_pipeline():
         if ch:
             assert ch[0][0] == 0 and ch[-1][1] == B and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
             assert all((b1 - b0) % 2 == 0 and b0 % 4 == 0 for b0, b1 in ch)
+
+
+def test_captured_train_step_rejects_what_it_cannot_capture():
+    """link_predict.CapturedTrainStep checks its preconditions before touching the device: a capturable optimizer
+    (device-resident step counters) and CUDA inputs (there is no CPU fallback)."""
+    import pytest
+    model = K.LinkPredict(K.KGVAE, 20, 8, 3, num_bases=2, use_cuda=True, k=2)
+    ex = {"node_id": torch.arange(20, dtype=torch.int32).view(-1, 1), "src": torch.zeros(4, dtype=torch.int32),
+          "dst": torch.ones(4, dtype=torch.int32), "etype": torch.zeros(4, dtype=torch.int32), "norm": torch.ones(4, 1),
+          "samples": torch.zeros(5, 3, dtype=torch.int32), "labels": torch.zeros(5)}
+    with pytest.raises(RuntimeError, match="capturable"):
+        K.link_predict.CapturedTrainStep(model, torch.optim.Adam(model.parameters()), ex, 20)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        K.link_predict.CapturedTrainStep(model, torch.optim.Adam(model.parameters(), capturable=True), ex, 20)
+
+
+def test_graph_from_device_edges_keeps_the_host_surface():
+    """Graph.from_device_edges adopts an edge list without copying it; the DGLGraph queries the reference's loop makes
+    (g.in_degrees, g.edges, number_of_edges; kgvae/link_predict.py:216) still answer from it."""
+    src, dst = torch.tensor([0, 1, 2, 2], dtype=torch.int32), torch.tensor([1, 2, 0, 1], dtype=torch.int32)
+    g = K.Graph.from_device_edges(3, src, dst)
+    assert g.number_of_nodes() == 3 and g.number_of_edges() == 4
+    assert g.in_degrees(range(3)).tolist() == [1, 2, 1]
+    s, d = g.edges()
+    assert s.tolist() == [0, 1, 2, 2] and d.tolist() == [1, 2, 0, 1]
+
+
+def test_release_graph_detaches_the_cached_encoder_outputs():
+    """LinkPredict.release_graph: the tensors KGVAE keeps between forward and get_loss (kgvae/model.py:113-123) stop
+    holding the autograd graph of the last step - which is what lets a step be captured on another stream."""
+    model = K.LinkPredict(K.KGVAE, 20, 8, 3, num_bases=2, use_cuda=True, k=2)
+    x = torch.randn(20, 8, requires_grad=True)
+    model.encoder.z_mean, model.encoder.z_sigma = x * 2, x.exp()
+    model.encoder.flow_log_prob = None
+    model.release_graph()
+    assert model.encoder.z_mean.grad_fn is None and model.encoder.z_sigma.grad_fn is None
+    assert torch.equal(model.encoder.z_mean, (x * 2).detach())
