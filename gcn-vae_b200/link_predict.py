@@ -251,6 +251,25 @@ def _graph_inputs(graph, rel, norm, num_nodes, device):
     return node_id, rel_t, edge_norm
 
 
+def _validate(model, args, epoch, best_mrr, val_graph, val_node_id, val_rel, val_norm, valid_t):
+    """Periodic validation with checkpoints (kgvae/link_predict.py:238-259); returns the best MRR so far."""
+    model.eval()
+    print("start eval")
+    torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
+    with torch.no_grad():
+        embed = model(val_graph, val_node_id, val_rel, val_norm)
+    mrr = utils.calc_mrr(embed, model.w_relation, valid_t, hits=[1, 3, 10],
+                         eval_bz=args.eval_batch_size, all_batches=False,
+                         flow_log_prob=model._flow_shift())
+    model.release_graph()
+    if mrr < best_mrr:
+        torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file + "_latest")
+    else:
+        best_mrr = mrr
+        torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
+    return best_mrr
+
+
 def main(args):
     data = datasets.load_data(args.dataset)
     num_nodes, num_rels = data.num_nodes, data.num_rels
@@ -271,7 +290,8 @@ def main(args):
     val_graph, val_rel, val_norm = utils.build_test_graph(num_nodes, num_rels, valid_t)
     val_node_id, val_rel, val_norm = _graph_inputs(val_graph, val_rel, val_norm, num_nodes, device)
     adj_list, degrees = utils.get_adj_and_degrees(num_nodes, train_data)
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, fused=True)
+    capture = bool(getattr(args, "capture_step", False))
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, fused=True, capturable=capture)
     # gradients live in one flat buffer: zeroing is one memset, clipping one norm + one scale
     # (same arithmetic as optimizer.zero_grad() / clip_grad_norm_ of kgvae/link_predict.py:227,236)
     buckets = model.grad_buckets()
@@ -306,9 +326,36 @@ def main(args):
         epoch = checkpoint["epoch"]
 
     train_dev = None
+    captured = None
+    if capture:
+        # full-graph training: every iteration scores all training triples with fresh negatives on a fresh graph
+        # split - fixed shapes, so sampler + step are captured once and every iteration is one CUDA-graph replay
+        if args.graph_batch_size < len(train_data) or args.edge_sampler != "uniform":
+            raise RuntimeError("--capture-step needs full-batch uniform sampling: --graph-batch-size >= the number "
+                               f"of training triples ({len(train_data)}) and --edge-sampler uniform")
+        model.train()
+        train_dev = torch.from_numpy(np.asarray(train_data)).to(device)
+        sampler = utils.FullBatchDeviceSampler(train_dev, num_rels, args.negative_sample, args.graph_split_size)
+        captured = CapturedTrainStep(model, optimizer, None, sampler.n, buckets=buckets, grad_norm=args.grad_norm,
+                                     warmup=1, sampler=sampler)
+        epoch += 1                       # the warm-up step that precedes the capture is a training step
     while True:
         model.train()
         epoch += 1
+        if captured is not None:
+            torch.cuda.synchronize()
+            t0 = time.time()
+            loss = captured.step()
+            torch.cuda.synchronize()
+            forward_time.append(time.time() - t0)          # the replay is forward + backward + update in one
+            backward_time.append(0.0)
+            print("Epoch {:04d} | Loss {:.4f} | Best MRR {:.4f} | pred_loss {:.4f} | kl {:.4f} | mmd {:.4f}".format(
+                epoch, loss.item(), best_mrr, captured.predict_loss.item(), captured.kl.item(), captured.mmd.item()))
+            if epoch % args.evaluate_every == 0:
+                best_mrr = _validate(model, args, epoch, best_mrr, val_graph, val_node_id, val_rel, val_norm, valid_t)
+            if epoch >= args.n_epochs:
+                break
+            continue
         if getattr(args, "device_sampler", False) and args.edge_sampler == "uniform":
             # opt-in: the same sampling procedure drawn on the GPU (not numpy's random stream)
             if train_dev is None:
@@ -343,20 +390,7 @@ def main(args):
         buckets.zero()
 
         if epoch % args.evaluate_every == 0:
-            model.eval()
-            print("start eval")
-            torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
-            with torch.no_grad():
-                embed = model(val_graph, val_node_id, val_rel, val_norm)
-            mrr = utils.calc_mrr(embed, model.w_relation, valid_t, hits=[1, 3, 10],
-                                 eval_bz=args.eval_batch_size, all_batches=False,
-                                 flow_log_prob=model._flow_shift())
-            if mrr < best_mrr:
-                torch.save({"state_dict": model.state_dict(), "epoch": epoch},
-                           args.model_state_file + "_latest")
-            else:
-                best_mrr = mrr
-                torch.save({"state_dict": model.state_dict(), "epoch": epoch}, args.model_state_file)
+            best_mrr = _validate(model, args, epoch, best_mrr, val_graph, val_node_id, val_rel, val_norm, valid_t)
         if epoch >= args.n_epochs:
             break
 
@@ -393,6 +427,10 @@ def build_parser():
     p.add_argument("--model-class", type=str, default="KGVAE")
     p.add_argument("--load", type=bool, default=False)
     p.add_argument("--generate", type=bool, default=False)
+    p.add_argument("--capture-step", action="store_true",
+                   help="(new) full-graph training (--graph-batch-size >= the number of training triples): negatives, "
+                        "graph split, edge index, forward, loss, backward, clipping and Adam are captured once into a "
+                        "CUDA graph and every iteration is one replay; one warm-up iteration precedes the capture")
     p.add_argument("--device-sampler", action="store_true",
                    help="(new) draw the uniform edge sample, the negatives and the graph split on the GPU; same "
                         "procedure as the reference's host sampler, not its numpy random stream")

@@ -224,3 +224,20 @@ def test_captured_step_with_its_own_sampler_trains():
     assert np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5])
     with pytest.raises(RuntimeError, match="draws its own inputs"):
         cap.step(labels=torch.zeros(1, device=dev))
+
+
+def test_driver_capture_step_trains_validates_and_checkpoints(tmp_path, capsys):
+    """--capture-step: the reference's loop (kgvae/link_predict.py:200-259) with every iteration - sampler included -
+    as one CUDA-graph replay; validation, checkpoints and the printed line are the eager loop's."""
+    np.random.seed(0)
+    torch.manual_seed(0)
+    args = _args(tmp_path, "--capture-step", "--graph-batch-size", "1000000", "--n-flows", "0", "--n-epochs", "6")
+    best = K.link_predict.main(args)
+    out = capsys.readouterr().out
+    assert "Epoch 0002" in out and "Epoch 0006" in out and "start eval" in out and "training done" in out
+    losses = [float(line.split("Loss")[1].split("|")[0]) for line in out.splitlines() if line.startswith("Epoch")]
+    assert len(losses) == 5 and all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert 0.0 < best <= 1.0
+    assert torch.load(args.model_state_file, map_location="cpu")["epoch"] in (2, 4, 6)
+    with pytest.raises(RuntimeError, match="full-batch"):
+        K.link_predict.main(_args(tmp_path, "--capture-step", "--graph-batch-size", "10"))
