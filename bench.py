@@ -1256,14 +1256,30 @@ def run_gpu(args):
         roof["partitioned"] = partitioned
         roof["gemm_vs_library"] = gemm_cmp
         if streaming:
-            worst = min(((k_, v) for k_, v in streaming["kernels"]["uniform"].items()), key=lambda kv: kv[1]["frac_of_hbm_peak"])
+            # each streaming launch against the resource that binds it: HBM for the launches whose HBM floor is the larger
+            # one, the L2 reduction rate (probe) for the 5x10 forward, which reduces 4 KB per edge for 2 KB gathered
+            ks = streaming["kernels"]["uniform"]
+            hbm_bound = {k_: v for k_, v in ks.items() if v.get("bound", "hbm") == "hbm"} or ks
+            worst = min(hbm_bound.items(), key=lambda kv: kv[1]["frac_of_hbm_peak"])
             roof["hbm"] = {"kernel": worst[0] + " @ wikikg2 shape (2.5 M nodes, 32 M edges)", "bound": "hbm",
                            "achieved": worst[1]["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": worst[1]["frac_of_hbm_peak"], "traffic": traffic.get(worst[0] + ":streaming"),
                            "peak_source": pk["source"], "ms_per_launch": worst[1]["ms"],
                            "algorithmic_bytes": worst[1]["algorithmic_bytes"],
-                           "note": "the message-passing launch furthest below the HBM roofline in the streaming "
-                                   "regime; all four launches under rgcn_streaming"}
+                           "note": "the HBM-bound message-passing launch furthest below the HBM roofline in the "
+                                   "streaming regime; all four launches under rgcn_streaming"}
+            red_bound = {k_: v for k_, v in ks.items() if v.get("bound") == "l2 reductions"}
+            if red_bound:
+                w2 = min(red_bound.items(), key=lambda kv: kv[1]["frac_of_l2_reduce_probe"])
+                roof["l2_reduction"] = {
+                    "kernel": w2[0] + " @ wikikg2 shape (2.5 M nodes, 32 M edges)", "bound": "l2",
+                    "achieved": w2[1]["l2_reduce_gbs"], "peak": l2_peak["reduce_gbs"], "unit": "GB/s",
+                    "frac": w2[1]["frac_of_l2_reduce_probe"], "ms_per_launch": w2[1]["ms"],
+                    "algorithmic_bytes": w2[1]["reduce_bytes"], "frac_of_hbm_peak": w2[1]["frac_of_hbm_peak"],
+                    "traffic": traffic.get(w2[0] + ":streaming"),
+                    "peak_source": "kg_probe_l2 (whole-row reductions into an L2-resident matrix), measured in this run",
+                    "note": "every edge's message is reduced into an L2-resident tile: 4 KB reduced per edge for 2 KB "
+                            "gathered, so the L2 reduction rate binds this launch, not HBM (frac_of_hbm_peak for reference)"}
 
     total_edges = E * world * args.steps
     line = {
