@@ -72,6 +72,9 @@ _SIGNATURES = {
     "kg_distmult_bce_workspace_bytes": (_Z, [_I]),
     "kg_distmult_bce_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "kg_distmult_bwd_dz": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "kg_triplet_index_trailing": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "kg_distmult_bce_fwd_lead": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "kg_distmult_bwd_dz_trailing": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_bwd_dw": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "kg_distmult_rank_workspace_bytes": (_Z, [_I, _I, _I]),
     "kg_distmult_rank": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _Z, _P, _P, _P]),
@@ -102,7 +105,7 @@ def lib():
 
 # kernels launched per entry point (bench.py's gpu_launches; CUB sorts/scans counted as 2 each)
 KERNELS_PER_CALL = {
-    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_distmult_bce_fwd": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 1,
+    "kg_graph_build": 14, "kg_graph_index": 10, "kg_graph_rel_tiled": 5, "kg_triplet_index": 13, "kg_triplet_index_trailing": 18, "kg_distmult_bce_fwd": 5, "kg_distmult_bce_fwd_lead": 5, "kg_colsum": 2, "kg_act_dropout_bwd_colsum": 1,
     "kg_gemm_f32": 5,        # two operand preparations (2 kernels each) + the product (+ split-K finish): a lower bound
     "kg_gemm_prepare": 2,
     "kg_kl_mog_fwd": 2, "kg_bce_logits_fwd": 2, "kg_sum_squares": 2, "kg_sum": 2, "kg_distmult_rank": 3, "kg_distmult_topk": 5,

@@ -160,39 +160,53 @@ extern "C" int kg_sum(const float* x, long long n, float* out, void* workspace, 
 // equal (r, a), so the end with the LONGER run should lead: with negative sampling a positive and the
 // negatives that corrupt its other end share it (runs of ~6 instead of 1).  Run lengths are estimated
 // with a hashed counter table - collisions only cost speed, never correctness.
-static constexpr int kOrientBits = 22;
+// Table size: 2^22 counters up to 4 M triplets (the FB15k-237 step: 3 M); beyond that about two slots per triplet,
+// at most 2^28 (1 GB) - at the ogbl-wikikg2 shape (176 M triplets, 32 M distinct (relation, entity) pairs) a 4 M-slot
+// table made every count a sum over ~8 unrelated pairs, the orientation came out random and the runs 1.8 triplets
+// long instead of ~5.5 (ncu: 5 KB of DRAM reads per triplet instead of 3 KB).
+static int orient_bits(int S) {
+  if (S <= (1 << 22)) return 22;
+  int b = 23;
+  while (b < 28 && (1LL << b) < 2LL * S) ++b;
+  return b;
+}
 
-__device__ __forceinline__ unsigned orient_slot(unsigned r, unsigned e) {
+__device__ __forceinline__ unsigned orient_slot(unsigned r, unsigned e, unsigned mask) {
   unsigned x = r * 0x9E3779B1u ^ (e + 0x7F4A7C15u) * 0x85EBCA6Bu;
   x ^= x >> 15;
   x *= 0x2C1B3C6Du;
   x ^= x >> 13;
-  return x & ((1u << kOrientBits) - 1u);
+  return x & mask;
 }
 
-__global__ void orient_count(const int* __restrict__ trip, int S, unsigned* __restrict__ table) {
+__global__ void orient_count(const int* __restrict__ trip, int S, unsigned* __restrict__ table, unsigned mask) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S) return;
   const unsigned s = (unsigned)trip[3 * (size_t)t], r = (unsigned)trip[3 * (size_t)t + 1],
                  o = (unsigned)trip[3 * (size_t)t + 2];
-  atomicAdd(table + orient_slot(r, s), 1u);
-  atomicAdd(table + orient_slot(r, o), 1u);
+  atomicAdd(table + orient_slot(r, s, mask), 1u);
+  atomicAdd(table + orient_slot(r, o, mask), 1u);
 }
 
 // rs_key leads with whichever end has the longer (estimated) run; bit 31 of rs_val marks a swap.
 // KeyT: 32-bit keys when relation and entity bits fit (23 bits at the FB15k-237 shape) - a third less sort traffic.
+// ent_mode 1: (entity, r) keys for BOTH ends of every triplet (2S entries); 2: for the TRAILING end only - the one
+// the (r, leading entity)-ordered pass does not keep in registers (S entries; bit 31 of ent_val marks a swap)
 template <typename KeyT>
 __global__ void triplet_keys(const int* __restrict__ trip, int S, int nb, int rb,
                              const unsigned* __restrict__ table, KeyT* rs_key, int* rs_val,
-                             KeyT* ent_key, int* ent_val) {
+                             KeyT* ent_key, int* ent_val, int ent_mode, unsigned mask) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S) return;
   const KeyT s = (unsigned)trip[3 * (size_t)t], r = (unsigned)trip[3 * (size_t)t + 1],
              o = (unsigned)trip[3 * (size_t)t + 2];
-  const bool swap = table != nullptr && table[orient_slot((unsigned)r, (unsigned)o)] > table[orient_slot((unsigned)r, (unsigned)s)];
+  const bool swap = table != nullptr && table[orient_slot((unsigned)r, (unsigned)o, mask)] > table[orient_slot((unsigned)r, (unsigned)s, mask)];
   rs_key[t] = (r << nb) | (swap ? o : s);
   rs_val[t] = swap ? (t | 0x80000000) : t;
-  if (ent_key) {
+  if (ent_key && ent_mode == 2) {
+    ent_key[t] = ((swap ? s : o) << rb) | r;
+    ent_val[t] = swap ? (t | 0x80000000) : t;
+  } else if (ent_key) {
     ent_key[t] = (s << rb) | r;      ent_val[t] = t;          // subject side
     ent_key[S + t] = (o << rb) | r;  ent_val[S + t] = S + t;  // object side
   }
@@ -216,6 +230,15 @@ __global__ void fill_ent_pack(const int* __restrict__ trip, const int* __restric
   const int t = v < S ? v : v - S;
   const int other = v < S ? trip[3 * (size_t)t + 2] : trip[3 * (size_t)t];
   pack[k] = make_int4(other, trip[3 * (size_t)t + 1], t, 0);
+}
+
+// trailing-end index: pack = {leading entity, relation, triplet, 0}
+__global__ void fill_trail_pack(const int* __restrict__ trip, const int* __restrict__ sorted_val, int S,
+                                int4* __restrict__ pack) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const int v = sorted_val[k], t = v & 0x7fffffff;
+  pack[k] = make_int4(v < 0 ? trip[3 * (size_t)t + 2] : trip[3 * (size_t)t], trip[3 * (size_t)t + 1], t, 0);
 }
 
 // ptr[v] = first position whose key has entity >= v (keys sorted ascending)
@@ -251,19 +274,21 @@ static size_t triplet_cub_bytes(int S) {
 }
 
 template <typename KeyT>
-static int triplet_sorts(const int32_t* triplets, int S, int n_nodes, int nb, int rb, const unsigned* table, bool want_ent,
+static int triplet_sorts(const int32_t* triplets, int S, int n_nodes, int nb, int rb, const unsigned* table, unsigned mask, int ent_mode,
                          KeyT* rk_in, KeyT* rk_out, int* rv_in, int* rv_out, KeyT* ek_in, KeyT* ek_out, int* ev_in,
                          int* ev_out, void* temp, size_t temp_bytes, void* rs_rec, int32_t* ent_ptr, void* ent_pack,
                          cudaStream_t st) {
   triplet_keys<KeyT><<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, nb, rb, table, rk_in, rv_in,
-                                                                  want_ent ? ek_in : nullptr, ev_in);
+                                                                  ent_mode ? ek_in : nullptr, ev_in, ent_mode, mask);
   KG_LAUNCH_OK();
   size_t tb = temp_bytes;
-  if (want_ent) {
-    KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, 2 * S, 0, nb + rb, st));
-    fill_ent_pack<<<kg_div_up(2LL * S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
+  if (ent_mode) {
+    const int n_ent = ent_mode == 2 ? S : 2 * S;
+    KG_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ek_in, ek_out, ev_in, ev_out, n_ent, 0, nb + rb, st));
+    if (ent_mode == 2) fill_trail_pack<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
+    else fill_ent_pack<<<kg_div_up(2LL * S, kThreads), kThreads, 0, st>>>(triplets, ev_out, S, reinterpret_cast<int4*>(ent_pack));
     KG_LAUNCH_OK();
-    ent_lower_bound<KeyT><<<kg_div_up(n_nodes + 1, kThreads), kThreads, 0, st>>>(ek_out, 2 * S, rb, n_nodes, ent_ptr);
+    ent_lower_bound<KeyT><<<kg_div_up(n_nodes + 1, kThreads), kThreads, 0, st>>>(ek_out, n_ent, rb, n_nodes, ent_ptr);
     KG_LAUNCH_OK();
   }
   tb = temp_bytes;
@@ -277,22 +302,22 @@ extern "C" size_t kg_triplet_index_workspace_bytes(int n_triplets) {
   int S = n_triplets > 0 ? n_triplets : 1;
   return 2 * kg_align_up(((size_t)2 * S + 1) * 8) + 2 * kg_align_up(((size_t)2 * S + 1) * 4) +
          2 * kg_align_up(((size_t)S + 1) * 8) + 2 * kg_align_up(((size_t)S + 1) * 4) + triplet_cub_bytes(S) +
-         kg_align_up(sizeof(unsigned) << kOrientBits) + 1024;
+         kg_align_up(sizeof(unsigned) << orient_bits(S)) + 1024;
 }
 
-extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
-                                void* rs_rec, int32_t* ent_ptr, void* ent_pack, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+static int triplet_index_impl(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
+                              void* rs_rec, int32_t* ent_ptr, void* ent_pack, int ent_mode_req, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   KG_REQUIRE(n_triplets >= 0 && n_nodes > 0 && n_rels > 0, "triplet index: bad sizes");
   KG_REQUIRE(n_nodes < (1 << 24) && n_rels < (1 << 16), "triplet index: n_nodes < 2^24, n_rels < 2^16");
   cudaStream_t st = kg_stream(stream);
   const int S = n_triplets;
   if (S == 0) {
-    KG_CUDA(cudaMemsetAsync(ent_ptr, 0, sizeof(int) * (n_nodes + 1), st));
+    if (ent_ptr) KG_CUDA(cudaMemsetAsync(ent_ptr, 0, sizeof(int) * (n_nodes + 1), st));
     return KG_OK;
   }
   KgArena ws(workspace, workspace_bytes);
-  const bool want_ent = ent_ptr != nullptr && ent_pack != nullptr;     // the (entity, r) index is optional
+  const int ent_mode = (ent_ptr != nullptr && ent_pack != nullptr) ? ent_mode_req : 0;   // the (entity, r) index is optional
   unsigned long long* ek_in = ws.take<unsigned long long>(2 * (size_t)S + 1);
   unsigned long long* ek_out = ws.take<unsigned long long>(2 * (size_t)S + 1);
   int* ev_in = ws.take<int>(2 * (size_t)S + 1);
@@ -303,24 +328,42 @@ extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_n
   int* rv_out = ws.take<int>((size_t)S + 1);
   size_t temp_bytes = triplet_cub_bytes(S);
   void* temp = ws.take<char>(temp_bytes);
-  unsigned* table = ws.take<unsigned>((size_t)1 << kOrientBits);
+  const int obits = orient_bits(S);
+  unsigned* table = ws.take<unsigned>((size_t)1 << obits);
   if (!ek_in || !ek_out || !ev_in || !ev_out || !rk_in || !rk_out || !rv_in || !rv_out || !temp || !table)
     return kg_fail(KG_ERR_WORKSPACE, "triplet index: workspace too small");
   const int nb = bits_for(n_nodes), rb = bits_for(n_rels);
   const bool orient = S >= (1 << 14);          // small batches: not worth the extra pass
   if (orient) {
-    KG_CUDA(cudaMemsetAsync(table, 0, sizeof(unsigned) << kOrientBits, st));
-    orient_count<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, table);
+    KG_CUDA(cudaMemsetAsync(table, 0, sizeof(unsigned) << obits, st));
+    orient_count<<<kg_div_up(S, kThreads), kThreads, 0, st>>>(triplets, S, table, (1u << obits) - 1u);
     KG_LAUNCH_OK();
   }
   if (nb + rb <= 32)           // the 64-bit key buffers hold the 32-bit keys
-    return triplet_sorts<unsigned>(triplets, S, n_nodes, nb, rb, orient ? table : nullptr, want_ent,
+    return triplet_sorts<unsigned>(triplets, S, n_nodes, nb, rb, orient ? table : nullptr, (1u << obits) - 1u, ent_mode,
                                    reinterpret_cast<unsigned*>(rk_in), reinterpret_cast<unsigned*>(rk_out), rv_in, rv_out,
                                    reinterpret_cast<unsigned*>(ek_in), reinterpret_cast<unsigned*>(ek_out), ev_in, ev_out,
                                    temp, temp_bytes, rs_rec, ent_ptr, ent_pack, st);
-  return triplet_sorts<unsigned long long>(triplets, S, n_nodes, nb, rb, orient ? table : nullptr, want_ent, rk_in, rk_out,
+  return triplet_sorts<unsigned long long>(triplets, S, n_nodes, nb, rb, orient ? table : nullptr, (1u << obits) - 1u, ent_mode, rk_in, rk_out,
                                            rv_in, rv_out, ek_in, ek_out, ev_in, ev_out, temp, temp_bytes, rs_rec, ent_ptr,
                                            ent_pack, st);
+}
+
+extern "C" int kg_triplet_index(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
+                                void* rs_rec, int32_t* ent_ptr, void* ent_pack, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  return triplet_index_impl(triplets, n_triplets, n_nodes, n_rels, rs_rec, ent_ptr, ent_pack, 1, workspace, workspace_bytes,
+                            stream);
+}
+
+// rs_rec as above plus the (trailing entity, r)-ordered index of the S triplets: trail_ptr [n_nodes + 1],
+// trail_pack [S] int4 {leading entity, r, t, 0} - what kg_distmult_bwd_dz_trailing walks
+extern "C" int kg_triplet_index_trailing(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
+                                         void* rs_rec, int32_t* trail_ptr, void* trail_pack, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  KG_REQUIRE(trail_ptr && trail_pack, "triplet index (trailing): null output");
+  return triplet_index_impl(triplets, n_triplets, n_nodes, n_rels, rs_rec, trail_ptr, trail_pack, 2, workspace,
+                            workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,7 +381,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
-template <int NV, bool FUSED, bool DZ>
+// DZ: 0 = no gradient wrt z; 1 = both ends (dz[o] reduced per triplet); 2 = leading end only (dz[s] over the run):
+// the trailing end's gradient is then gathered by kg_distmult_bwd_dz_trailing - the form for a z that does not fit L2,
+// where a reduction into a random row is a DRAM read-modify-write (4 KB of traffic) and a gather is a 2 KB read
+template <int NV, bool FUSED, int DZ>
 __global__ void __launch_bounds__(kThreads)
 distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, const int4* __restrict__ rec,
                    const float* __restrict__ labels, const float* __restrict__ g_in,
@@ -431,7 +477,7 @@ distmult_rs_kernel(const float* __restrict__ z, const float* __restrict__ w, con
     } else {
       g = __ldg(g_in + rc.w);
     }
-    if (DZ) {                                 // dz[o] += g w[r] z[s]: one coalesced 2 KB vector reduction per triplet
+    if (DZ == 1) {                            // dz[o] += g w[r] z[s]: one coalesced 2 KB vector reduction per triplet
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
@@ -522,7 +568,7 @@ distmult_rs_generic(const float* __restrict__ z, const float* __restrict__ w, co
 template <bool FUSED>
 static int launch_rs(const float* z, const float* w, const void* rs_rec, const float* labels, const float* g_in,
                      const float* shift, int S, int h, float* score_out, float* g_out, float* dw, float* dz,
-                     float* loss_part, float* gsum_part, cudaStream_t st) {
+                     float* loss_part, float* gsum_part, cudaStream_t st, bool lead_only = false) {
   const int warps = kg_div_up(S, kChunkT);
   const int grid = kg_div_up((long long)warps * 32, kThreads);
   const int4* rec = reinterpret_cast<const int4*>(rs_rec);
@@ -532,12 +578,15 @@ static int launch_rs(const float* z, const float* w, const void* rs_rec, const f
                      reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
 #define KG_RS_LAUNCH(NV_)                                                                                       \
   do {                                                                                                          \
-    if (dz)                                                                                                     \
-      distmult_rs_kernel<NV_, FUSED, true><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, \
-                                                                      score_out, g_out, dw, dz, loss_part, gsum_part); \
+    if (dz && lead_only)                                                                                        \
+      distmult_rs_kernel<NV_, FUSED, 2><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S,    \
+                                                                   score_out, g_out, dw, dz, loss_part, gsum_part); \
+    else if (dz)                                                                                                \
+      distmult_rs_kernel<NV_, FUSED, 1><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S,    \
+                                                                   score_out, g_out, dw, dz, loss_part, gsum_part); \
     else                                                                                                        \
-      distmult_rs_kernel<NV_, FUSED, false><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, \
-                                                                       score_out, g_out, dw, dz, loss_part, gsum_part); \
+      distmult_rs_kernel<NV_, FUSED, 0><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S,    \
+                                                                   score_out, g_out, dw, dz, loss_part, gsum_part); \
   } while (0)
   if (!vec) distmult_rs_generic<FUSED><<<grid, kThreads, 0, st>>>(z, w, rec, labels, g_in, shift, S, h, inv_S, score_out, g_out, dw, dz, loss_part, gsum_part);
   else if (h <= 128) KG_RS_LAUNCH(1);
@@ -560,11 +609,16 @@ extern "C" size_t kg_distmult_bce_workspace_bytes(int n_triplets) {
 //   dz (optional, zero-filled by the caller) += sum_t g_t w[r_t] (z[o_t] into row s_t, z[s_t] into row o_t):
 //   the whole backward into z in the same pass - z[o] is in registers anyway, dz[s] is kept in registers over
 //   an (r, s) run and dz[o] goes out as one coalesced 2 KB vector reduction per triplet
-extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
-                                   int n_triplets, int h, const float* shift, float* score_out, float* g_out,
-                                   float* dw, float* dz, float* loss_out, float* gsum_out, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+static int distmult_bce_impl(const float* z, const float* w, const void* rs_rec, const float* labels,
+                             int n_triplets, int h, const float* shift, float* score_out, float* g_out,
+                             float* dw, float* dz, float* loss_out, float* gsum_out, void* workspace,
+                             size_t workspace_bytes, void* stream, bool lead_only) {
   KG_REQUIRE(n_triplets >= 0 && h > 0, "distmult bce: bad sizes");
+  if (lead_only)
+    KG_REQUIRE(dz && h % 4 == 0 && h <= 1024 &&
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw) |
+                     reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+               "distmult bce (leading end): needs dz, h % 4 == 0, h <= 1024 and 16-byte aligned rows");
   cudaStream_t st = kg_stream(stream);
   if (n_triplets == 0) {
     KG_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
@@ -578,13 +632,32 @@ extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* r
   float* red = ws.take<float>(kMaxPartials);
   if (!loss_part || !gsum_part || !red) return kg_fail(KG_ERR_WORKSPACE, "distmult bce: workspace too small");
   int rc = launch_rs<true>(z, w, rs_rec, labels, nullptr, shift, n_triplets, h, score_out, g_out, dw, dz, loss_part,
-                           gsum_part, st);
+                           gsum_part, st, lead_only);
   if (rc != KG_OK) return rc;
   rc = run_reduce(loss_part, nullptr, (long long)warps, 0, 1.0f / (float)n_triplets, 0.f, nullptr, loss_out, red,
                   sizeof(float) * kMaxPartials, st);
   if (rc != KG_OK) return rc;
   return run_reduce(gsum_part, nullptr, (long long)warps, 0, 1.f, 0.f, nullptr, gsum_out, red,
                     sizeof(float) * kMaxPartials, st);
+}
+
+extern "C" int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, const float* labels,
+                                   int n_triplets, int h, const float* shift, float* score_out, float* g_out,
+                                   float* dw, float* dz, float* loss_out, float* gsum_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return distmult_bce_impl(z, w, rs_rec, labels, n_triplets, h, shift, score_out, g_out, dw, dz, loss_out, gsum_out,
+                           workspace, workspace_bytes, stream, false);
+}
+
+// The same pass with only the LEADING end's share of dz (the entity each rs_rec run keeps in registers):
+//   dz[lead_t] += g_t w[r_t] z[trail_t];   the trailing end's share is kg_distmult_bwd_dz_trailing's.
+// For a z that does not fit L2: a reduction into a random row is then a DRAM read-modify-write.
+extern "C" int kg_distmult_bce_fwd_lead(const float* z, const float* w, const void* rs_rec, const float* labels,
+                                        int n_triplets, int h, const float* shift, float* score_out, float* g_out,
+                                        float* dw, float* dz, float* loss_out, float* gsum_out, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return distmult_bce_impl(z, w, rs_rec, labels, n_triplets, h, shift, score_out, g_out, dw, dz, loss_out, gsum_out,
+                           workspace, workspace_bytes, stream, true);
 }
 
 // dw[r,:] += sum_{t: rel_t = r} gscore[t] * z[s_t,:] * z[o_t,:]; dw zero-filled by the caller
@@ -600,7 +673,7 @@ extern "C" int kg_distmult_bwd_dw(const float* z, const float* gscore, const voi
 // dz[v, :] = sum over the (entity, r)-ordered index of gscore[t] * w[r, :] * z[other, :]
 // one thread per (entity, VEC consecutive columns); w[r] stays in registers while r repeats; no atomics
 // ------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, bool ACC>
 __global__ void __launch_bounds__(kThreads)
 distmult_dz_kernel(const float* __restrict__ z, const float* __restrict__ w,
                    const float* __restrict__ gscore, const int* __restrict__ ent_ptr,
@@ -634,28 +707,47 @@ distmult_dz_kernel(const float* __restrict__ z, const float* __restrict__ w,
       acc[0] = fmaf(g * a.x, __ldg(z + (size_t)p.x * h + c), acc[0]);
     }
   }
+  if (ACC && e_end == __ldg(ent_ptr + v)) return;     // nothing to add to this row
   if (VEC == 4) {
-    reinterpret_cast<float4*>(dz + (size_t)v * h)[c] = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    float4* p4 = reinterpret_cast<float4*>(dz + (size_t)v * h) + c;
+    float4 o4 = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    if (ACC) { const float4 q = *p4; o4.x += q.x; o4.y += q.y; o4.z += q.z; o4.w += q.w; }
+    *p4 = o4;
   } else {
-    dz[(size_t)v * h + c] = acc[0];
+    dz[(size_t)v * h + c] = ACC ? dz[(size_t)v * h + c] + acc[0] : acc[0];
   }
 }
 
-extern "C" int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore,
-                                  const int32_t* ent_ptr, const void* ent_pack, int n_nodes, int h,
-                                  float* dz, void* stream) {
+template <bool ACC>
+static int launch_dz(const float* z, const float* w, const float* gscore, const int32_t* ent_ptr, const void* ent_pack,
+                     int n_nodes, int h, float* dz, void* stream) {
   KG_REQUIRE(n_nodes >= 0 && h > 0, "distmult dz: bad sizes");
   if (n_nodes == 0) return KG_OK;
   const bool vec = (h % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
   const int4* pk = reinterpret_cast<const int4*>(ent_pack);
   if (vec) {
-    distmult_dz_kernel<4><<<kg_div_up((long long)n_nodes * (h / 4), kThreads), kThreads, 0, kg_stream(stream)>>>(
+    distmult_dz_kernel<4, ACC><<<kg_div_up((long long)n_nodes * (h / 4), kThreads), kThreads, 0, kg_stream(stream)>>>(
         z, w, gscore, ent_ptr, pk, n_nodes, h, dz);
   } else {
-    distmult_dz_kernel<1><<<kg_div_up((long long)n_nodes * h, kThreads), kThreads, 0, kg_stream(stream)>>>(
+    distmult_dz_kernel<1, ACC><<<kg_div_up((long long)n_nodes * h, kThreads), kThreads, 0, kg_stream(stream)>>>(
         z, w, gscore, ent_ptr, pk, n_nodes, h, dz);
   }
   KG_LAUNCH_OK();
   return KG_OK;
+}
+
+extern "C" int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore,
+                                  const int32_t* ent_ptr, const void* ent_pack, int n_nodes, int h,
+                                  float* dz, void* stream) {
+  return launch_dz<false>(z, w, gscore, ent_ptr, ent_pack, n_nodes, h, dz, stream);
+}
+
+// dz[v, :] += sum over the triplets whose TRAILING end is v of gscore[t] * w[r, :] * z[leading end, :]
+// (kg_triplet_index_trailing's index; each row has one owner thread group: plain loads and stores, no atomics,
+// a fixed summation order).  Completes kg_distmult_bce_fwd_lead.
+extern "C" int kg_distmult_bwd_dz_trailing(const float* z, const float* w, const float* gscore,
+                                           const int32_t* trail_ptr, const void* trail_pack, int n_nodes, int h,
+                                           float* dz, void* stream) {
+  return launch_dz<true>(z, w, gscore, trail_ptr, trail_pack, n_nodes, h, dz, stream);
 }

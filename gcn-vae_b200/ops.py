@@ -611,19 +611,57 @@ class ReverseColumnsFn(torch.autograd.Function):
 # a9  DistMult + BCE + regulariser
 # ---------------------------------------------------------------------------------------------
 class TripletIndex:
-    """(r, s)-ordered and, on request, (entity, r)-ordered views of one batch of triplets."""
+    """(r, s)-ordered and, on request, (entity, r)-ordered views of one batch of triplets.  ``trailing``: the entity
+    index covers only the TRAILING end of every triplet (S entries) - what the two-pass decoder gathers over."""
 
-    def __init__(self, triplets, n_nodes, n_rels, entity_index=True):
+    def __init__(self, triplets, n_nodes, n_rels, entity_index=True, trailing=False):
         dev = triplets.device
         S = triplets.shape[0]
         i32 = dict(dtype=torch.int32, device=dev)
         self.n = S
         self.rs_rec = torch.empty((max(S, 1), 4), **i32)
-        self.ent_ptr = torch.empty(n_nodes + 1, **i32) if entity_index else None
-        self.ent_pack = torch.empty((max(2 * S, 1), 4), **i32) if entity_index else None
+        want = entity_index or trailing
+        self.ent_ptr = torch.empty(n_nodes + 1, **i32) if want else None
+        self.ent_pack = torch.empty((max(S if trailing else 2 * S, 1), 4), **i32) if want else None
         ws = L.workspace(L.lib().kg_triplet_index_workspace_bytes(S), dev)
-        L.call("kg_triplet_index", L.i32(triplets), S, n_nodes, n_rels, L.i32(self.rs_rec), L.i32(self.ent_ptr),
-               L.i32(self.ent_pack), L.ptr(ws), ws.numel(), L.stream())
+        L.call("kg_triplet_index_trailing" if trailing else "kg_triplet_index", L.i32(triplets), S, n_nodes, n_rels,
+               L.i32(self.rs_rec), L.i32(self.ent_ptr), L.i32(self.ent_pack), L.ptr(ws), ws.numel(), L.stream(),
+               tag="kg_triplet_index")
+
+
+# None: two passes when z is far larger than L2 (a reduction into a random row of z's gradient is then a DRAM
+# read-modify-write: 6 KB of compulsory traffic per scored triplet instead of 4 KB; while z is L2-resident the fused
+# single pass is faster - 1.63 ms against 2.1 ms at the FB15k-237 shape); True / False force one form (tests)
+DECODER_TWO_PASS = None
+DECODER_TWO_PASS_BYTES = 256 << 20
+
+
+def distmult_bce_pass(z, w, triplets, labels, shift, want_dz):
+    """DistMult score + BCE-with-logits (mean) over ``triplets`` and its whole backward in the forward pass
+    (kgvae/link_predict.py:57-63,74-77): returns (out [2] = loss, sum of dloss/dscore; dw; dz or None).
+    One fused pass when z is L2-resident; for a larger z the gradient of the trailing entity of every triplet is
+    gathered over a (trailing entity, r) index instead of reduced (kg_distmult_bce_fwd_lead +
+    kg_distmult_bwd_dz_trailing)."""
+    S, (n, h) = triplets.shape[0], z.shape
+    dev = z.device
+    two_pass = DECODER_TWO_PASS
+    if two_pass is None:
+        two_pass = z.numel() * 4 > DECODER_TWO_PASS_BYTES
+    two_pass = bool(two_pass) and want_dz and h % 4 == 0 and h <= 1024 and S > 0
+    idx = TripletIndex(triplets, n, w.shape[0], entity_index=False, trailing=two_pass)
+    g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
+    dw = torch.zeros_like(w)
+    dz = torch.zeros_like(z) if want_dz else None
+    out = torch.empty(2, dtype=torch.float32, device=dev)             # loss, sum of g
+    sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
+    ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
+    L.call("kg_distmult_bce_fwd_lead" if two_pass else "kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec),
+           L.f32(labels), S, h, L.f32(sh), None, L.f32(g), L.f32(dw), L.f32(dz), L.ptr(out[0:1]), L.ptr(out[1:2]),
+           L.ptr(ws), ws.numel(), L.stream(), tag="kg_distmult_bce_fwd")
+    if two_pass:
+        L.call("kg_distmult_bwd_dz_trailing", L.f32(z), L.f32(w), L.f32(g), L.i32(idx.ent_ptr), L.i32(idx.ent_pack),
+               n, h, L.f32(dz), L.stream())
+    return out, dw, dz
 
 
 class DistMultScoreFn(torch.autograd.Function):
@@ -670,18 +708,7 @@ class DistMultBceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, w, triplets, labels, shift):
         z, w, labels = _c(z), _c(w), _c(labels)
-        S, h = triplets.shape[0], z.shape[1]
-        dev = z.device
-        idx = TripletIndex(triplets, z.shape[0], w.shape[0], entity_index=False)
-        g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
-        dw = torch.zeros_like(w)
-        dz = torch.zeros_like(z) if ctx.needs_input_grad[0] else None
-        out = torch.empty(2, dtype=torch.float32, device=dev)         # loss, sum of g
-        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
-        ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
-        L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
-               None, L.f32(g), L.f32(dw), L.f32(dz), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
-               L.stream())
+        out, dw, dz = distmult_bce_pass(z, w, triplets, labels, shift, ctx.needs_input_grad[0])
         ctx.save_for_backward(dw, dz, out)
         ctx.shift_shape = None if shift is None else shift.shape
         return out[0].clone()
@@ -712,18 +739,7 @@ class PartitionedDistMultBceFn(torch.autograd.Function):
         from . import parallel
         z = pending_z.wait()                                  # [n_global, h]
         w, labels = _c(w), _c(labels)
-        S, h = triplets.shape[0], z.shape[1]
-        dev = z.device
-        idx = TripletIndex(triplets, z.shape[0], w.shape[0], entity_index=False)
-        g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
-        dw = torch.zeros_like(w)
-        dz = torch.zeros_like(z)
-        out = torch.empty(2, dtype=torch.float32, device=dev)         # loss, sum of g
-        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
-        ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
-        L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
-               None, L.f32(g), L.f32(dw), L.f32(dz), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
-               L.stream())
+        out, dw, dz = distmult_bce_pass(z, w, triplets, labels, shift, True)
         ctx.pending_dz = parallel.reduce_scatter_rows_start(dz, part) if ctx.needs_input_grad[0] else None
         ctx.save_for_backward(dw, out)
         ctx.shift_shape = None if shift is None else shift.shape
@@ -762,16 +778,7 @@ class LossHeadFn(torch.autograd.Function):
         z, w, labels = _c(z), _c(w), _c(labels)
         S, (n, h) = triplets.shape[0], z.shape
         dev = z.device
-        idx = TripletIndex(triplets, n, w.shape[0], entity_index=False)
-        g = torch.empty(max(S, 1), dtype=torch.float32, device=dev)
-        dw = torch.zeros_like(w)
-        dz_pred = torch.zeros_like(z)
-        out = torch.empty(2, dtype=torch.float32, device=dev)         # pred loss, sum of g
-        sh = None if shift is None else _c(shift.reshape(1).to(torch.float32))
-        ws = L.workspace(L.lib().kg_distmult_bce_workspace_bytes(S), dev)
-        L.call("kg_distmult_bce_fwd", L.f32(z), L.f32(w), L.i32(idx.rs_rec), L.f32(labels), S, h, L.f32(sh),
-               None, L.f32(g), L.f32(dw), L.f32(dz_pred), L.ptr(out[0:1]), L.ptr(out[1:2]), L.ptr(ws), ws.numel(),
-               L.stream())
+        out, dw, dz_pred = distmult_bce_pass(z, w, triplets, labels, shift, True)       # out: pred loss, sum of g
         pred = out[0].clone()
         reg = _reduce("kg_sum_squares", z) / z.numel() + _reduce("kg_sum_squares", w) / w.numel()
         use_kl = kl_param > 0 and z_mean is not None

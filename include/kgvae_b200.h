@@ -333,6 +333,28 @@ int kg_distmult_bce_fwd(const float* z, const float* w, const void* rs_rec, cons
 /* dz[v,:] = sum_{(other, r, t) in ent(v)} gscore[t] * w[r,:] * z[other,:]    (no atomics) */
 int kg_distmult_bwd_dz(const float* z, const float* w, const float* gscore, const int32_t* ent_ptr,
                        const void* ent_pack, int n_nodes, int h, float* dz, void* stream);
+
+/* Two-pass form of the same backward for a z that does NOT fit L2 (ogbl-wikikg2 shape: 5 GB; new - the reference's
+ * index_put(accumulate) backward of kgvae/link_predict.py:57-63 has no counterpart):
+ *   kg_triplet_index_trailing   rs_rec as kg_triplet_index, plus the (trailing entity, r)-ordered index of the S
+ *                               triplets - trail_ptr [n_nodes + 1], trail_pack [S] int4 {leading entity, r, t, 0};
+ *                               "leading" is the end each rs_rec run keeps in registers, "trailing" the other one
+ *   kg_distmult_bce_fwd_lead    kg_distmult_bce_fwd with only the leading end's share of dz (accumulated over a run,
+ *                               flushed once): no reduction into the random trailing row
+ *   kg_distmult_bwd_dz_trailing dz[v] += sum over the triplets whose trailing end is v of g_t w[r_t] z[lead_t]: a
+ *                               gather with one owner per row (no atomics, fixed summation order)
+ * In DRAM a reduction into a random row is a read-modify-write (4 KB of traffic per 2 KB row), a gather a 2 KB read:
+ * 6 KB -> 4 KB of compulsory traffic per scored triplet.  Same workspace sizes as the one-pass entry points;
+ * kg_distmult_bce_fwd_lead needs h % 4 == 0, h <= 1024 and 16-byte aligned rows. */
+int kg_triplet_index_trailing(const int32_t* triplets, int n_triplets, int n_nodes, int n_rels,
+                              void* rs_rec, int32_t* trail_ptr, void* trail_pack,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int kg_distmult_bce_fwd_lead(const float* z, const float* w, const void* rs_rec, const float* labels,
+                             int n_triplets, int h, const float* shift, float* score_out, float* g_out,
+                             float* dw, float* dz, float* loss_out, float* gsum_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int kg_distmult_bwd_dz_trailing(const float* z, const float* w, const float* gscore, const int32_t* trail_ptr,
+                                const void* trail_pack, int n_nodes, int h, float* dz, void* stream);
 /* dw[r,:] += sum_{t: rel_t = r} gscore[t] * z[s_t,:] * z[o_t,:]; dw zero-filled by the caller */
 int kg_distmult_bwd_dw(const float* z, const float* gscore, const void* rs_rec, int n_triplets, int h,
                        float* dw, void* stream);

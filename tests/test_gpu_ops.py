@@ -533,6 +533,51 @@ def test_distmult_negative_sampled_batch():
     assert runs < 0.6 * plain                       # far fewer, longer runs than (r, s) order gives
 
 
+@pytest.mark.parametrize("n,h,r,pos,neg", [(5000, 64, 9, 3000, 10), (300, 500, 5, 400, 3), (40, 20, 3, 60, 0)])
+def test_distmult_two_pass_decoder(monkeypatch, n, h, r, pos, neg):
+    """The decoder's form for a z that does not fit L2 (kg_triplet_index_trailing + kg_distmult_bce_fwd_lead +
+    kg_distmult_bwd_dz_trailing; ops.DECODER_TWO_PASS forces it at test size): same loss and gradients as the oracle's
+    calc_score + BCE backward (kgvae/link_predict.py:57-63,74-77), the trailing index lists every triplet once under the
+    end that does not lead its rs_rec record, and the gathered gradient is bitwise repeatable (no atomics on that end)."""
+    rng = np.random.default_rng(n + pos)
+    p = np.stack([rng.integers(0, n, pos), rng.integers(0, r, pos), rng.integers(0, n, pos)], 1).astype(np.int64)
+    np.random.seed(7)
+    trip, lab = K.utils.negative_sampling(p, n, neg) if neg else (p, (rng.random(pos) < 0.4).astype(np.float32))
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(n, h, generator=g).requires_grad_(True)
+    w = torch.randn(r, h, generator=g).requires_grad_(True)
+    shift = torch.randn((), generator=g).requires_grad_(True)
+    labels = torch.from_numpy(np.asarray(lab, dtype=np.float32))
+    want = torch.nn.functional.binary_cross_entropy_with_logits(O.distmult_score(z, w, trip) + shift, labels)
+    want.backward()
+    t32 = torch.from_numpy(trip).to(torch.int32).to(DEV)
+    monkeypatch.setattr(ops, "DECODER_TWO_PASS", True)
+    grads = []
+    for rep in range(2):
+        cz, cw, cs = (t.detach().to(DEV).requires_grad_(True) for t in (z, w, shift))
+        loss = ops.DistMultBceFn.apply(cz, cw, t32, labels.to(DEV), cs)
+        (loss * 2.0).backward()
+        assert_close(loss, want, 1e-5, "two-pass bce")
+        assert_close(cz.grad, 2.0 * z.grad, RTOL, "two-pass dz")
+        assert_close(cw.grad, 2.0 * w.grad, RTOL, "two-pass dw")
+        assert_close(cs.grad, 2.0 * shift.grad, RTOL, "two-pass dshift")
+        grads.append(cz.grad.clone())
+    idx = ops.TripletIndex(t32, n, r, entity_index=False, trailing=True)
+    rec, pack, ptr = idx.rs_rec.cpu().numpy(), idx.ent_pack.cpu().numpy(), idx.ent_ptr.cpu().numpy()
+    S = len(trip)
+    assert pack.shape[0] == S and ptr[0] == 0 and ptr[-1] == S and np.all(np.diff(ptr) >= 0)
+    assert np.array_equal(np.sort(pack[:, 2]), np.arange(S))                 # every triplet once
+    lead_of = np.empty(S, dtype=np.int64); trail_of = np.empty(S, dtype=np.int64)
+    lead_of[rec[:, 3]], trail_of[rec[:, 3]] = rec[:, 0], rec[:, 2]
+    owner = np.repeat(np.arange(n), np.diff(ptr))                            # the entity each pack entry is listed under
+    assert np.array_equal(owner, trail_of[pack[:, 2]]) and np.array_equal(pack[:, 0], lead_of[pack[:, 2]])
+    assert np.array_equal(pack[:, 1], trip[pack[:, 2], 1])
+    # rows that are never a leading end receive only gathered contributions: bitwise equal between the two runs
+    never_lead = np.setdiff1d(np.arange(n), rec[:, 0])
+    if len(never_lead):
+        assert torch.equal(grads[0][never_lead], grads[1][never_lead])
+
+
 def test_mean_square():
     x = torch.randn(300, 50).requires_grad_(True)
     x.pow(2).mean().backward()
