@@ -114,10 +114,20 @@ launches = 0          # running count of kernels launched through this binding
 profile = None        # when a dict: name -> [(start_event, end_event), ...] per call
 
 
+_seen_dev = None      # device index of the tensors whose pointers were taken since the last call()
+
+
 def call(name, *args, tag=None):
-    """Invoke an int-returning entry point; raise RuntimeError with kg_last_error() on failure."""
-    global launches
+    """Invoke an int-returning entry point; raise RuntimeError with kg_last_error() on failure.  The kernels launch
+    on the CURRENT device's stream: tensors that live on another device would be dereferenced in the wrong context,
+    so the device of the pointers taken for this call (ptr()) is checked against it - one query per call."""
+    global launches, _seen_dev
     handle = lib()
+    if _seen_dev is not None:
+        dev, _seen_dev = _seen_dev, None
+        if dev != torch.cuda.current_device():
+            raise RuntimeError(f"kgvae_b200: {name} was given tensors on cuda:{dev} while the current device is "
+                               f"cuda:{torch.cuda.current_device()} (use torch.cuda.set_device / torch.cuda.device)")
     if profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -140,6 +150,12 @@ def ptr(t, dtype=None):
         raise RuntimeError(f"kgvae_b200: expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError("kgvae_b200: tensor must be contiguous")
+    global _seen_dev
+    idx = t.device.index
+    if _seen_dev is not None and _seen_dev != idx:
+        _seen_dev = None
+        raise RuntimeError("kgvae_b200: the tensors of one call live on different devices")
+    _seen_dev = idx
     return t.data_ptr()
 
 

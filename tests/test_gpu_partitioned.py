@@ -78,3 +78,19 @@ def test_partitioned_entity_classification_matches_single_gpu():
         res = [out[r] for r in range(WORLD)]
     for r in range(WORLD):
         assert res[r]["loss"] <= 1e-4 and res[r]["logits"] <= 1e-4 and max(res[r]["grads"].values()) <= 2e-4
+
+
+def test_ops_reject_tensors_on_a_non_current_device():
+    """Kernels launch on the current device's stream: tensors of another device are refused instead of being
+    dereferenced in the wrong context (one process per GPU is the supported layout)."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs 2 GPUs")
+    import gcn_vae_b200 as K
+    torch.cuda.set_device(0)
+    x = torch.ones(8, 4, device="cuda:1")
+    with pytest.raises(RuntimeError, match="current device"):
+        K.ops.colsum(x)
+    with torch.cuda.device(1):
+        assert K.ops.colsum(x).tolist() == [8.0] * 4
+    with pytest.raises(RuntimeError, match="different devices"):
+        K.ops.gemm(torch.ones(4, 4, device="cuda:0"), torch.ones(4, 4, device="cuda:1"), torch.ones(4, 4, device="cuda:0"))
