@@ -116,14 +116,31 @@ __global__ void decode_edge_keys(const unsigned long long* __restrict__ keys, in
   e_type[i] = (int)(k & 0xffffull);
 }
 
+// The relation histogram has few bins (474 at the FB15k-237 shape) and real relation frequencies are heavy-tailed:
+// one global atomic per edge serialises on the popular relations' counters.  With R2 <= kRelSmemBins the CTA counts
+// its edges in shared memory and adds each non-empty bin once.
+constexpr int kRelSmemBins = 4096;
+
 __global__ void histogram3(const int* __restrict__ e_src, const int* __restrict__ e_dst,
-                           const int* __restrict__ e_type, int E, int* deg_in, int* deg_out,
+                           const int* __restrict__ e_type, int E, int R2, int* deg_in, int* deg_out,
                            int* cnt_rel) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E) return;
-  atomicAdd(&deg_in[e_dst[i]], 1);
-  atomicAdd(&deg_out[e_src[i]], 1);
-  atomicAdd(&cnt_rel[e_type[i]], 1);
+  extern __shared__ int rel_s[];
+  const bool local = R2 <= kRelSmemBins;
+  if (local) {
+    for (int b = threadIdx.x; b < R2; b += blockDim.x) rel_s[b] = 0;
+    __syncthreads();
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) {
+    atomicAdd(&deg_in[e_dst[i]], 1);
+    atomicAdd(&deg_out[e_src[i]], 1);
+    if (local) atomicAdd(&rel_s[e_type[i]], 1);
+    else atomicAdd(&cnt_rel[e_type[i]], 1);
+  }
+  if (local) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < R2; b += blockDim.x)
+      if (rel_s[b]) atomicAdd(&cnt_rel[b], rel_s[b]);
+  }
 }
 
 // norm_v = 1/in_deg(v), inf -> 0 (kgvae/utils.py:127-132); float division, round-to-nearest
@@ -202,7 +219,9 @@ static int build_index(const int* e_src, const int* e_dst, const int* e_type, co
   KG_CUDA(cudaMemsetAsync(col_ptr, 0, sizeof(int) * (N + 1), st));
   KG_CUDA(cudaMemsetAsync(rel_ptr, 0, sizeof(int) * (R2 + 1), st));
   if (E > 0) {
-    histogram3<<<gridE, kThreads, 0, st>>>(e_src, e_dst, e_type, E, row_ptr, col_ptr, rel_ptr);
+    const int grid_h = gridE < 2 * kg_sm_count() ? gridE : 2 * kg_sm_count();   // a popular relation's counter: <= grid_h adds
+    histogram3<<<grid_h, kThreads, R2 <= kRelSmemBins ? sizeof(int) * R2 : 0, st>>>(e_src, e_dst, e_type, E, R2, row_ptr,
+                                                                                     col_ptr, rel_ptr);
     KG_LAUNCH_OK();
   }
   size_t tb = temp_bytes;
