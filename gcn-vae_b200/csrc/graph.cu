@@ -219,7 +219,7 @@ static int build_index(const int* e_src, const int* e_dst, const int* e_type, co
   KG_CUDA(cudaMemsetAsync(col_ptr, 0, sizeof(int) * (N + 1), st));
   KG_CUDA(cudaMemsetAsync(rel_ptr, 0, sizeof(int) * (R2 + 1), st));
   if (E > 0) {
-    const int grid_h = gridE < 2 * kg_sm_count() ? gridE : 2 * kg_sm_count();   // a popular relation's counter: <= grid_h adds
+    const int grid_h = gridE < 8 * kg_sm_count() ? gridE : 8 * kg_sm_count();   // full occupancy; a popular relation's counter: <= grid_h adds
     histogram3<<<grid_h, kThreads, R2 <= kRelSmemBins ? sizeof(int) * R2 : 0, st>>>(e_src, e_dst, e_type, E, R2, row_ptr,
                                                                                      col_ptr, rel_ptr);
     KG_LAUNCH_OK();
